@@ -1,0 +1,517 @@
+// oracle/graph.cpp — CPU restatement of the reference's greedy search, priority queue,
+// robust prune and single-insert build.  TEST INFRASTRUCTURE ONLY (see oracle.h).
+
+#include "oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <unordered_set>
+#include <vector>
+
+namespace {
+
+// ------------------------------------------------------------------ NeighborPriorityQueue
+// diskann/src/neighbor/queue.rs:66-318 (fixed-capacity flavour; search_param_l == capacity,
+// queue.rs:96-106).
+struct Queue {
+    size_t size = 0, capacity = 0, cursor = 0;
+    std::vector<uint32_t> ids;
+    std::vector<uint8_t> visited;
+    std::vector<float> dists;
+
+    explicit Queue(size_t cap) : capacity(cap) {
+        ids.reserve(cap);
+        visited.reserve(cap);
+        dists.reserve(cap);
+    }
+
+    // queue.rs:229-280: index of the first entry with distance >= target (linear scan)
+    size_t lower_bound(float d) const {
+        for (size_t i = 0; i < size; ++i)
+            if (dists[i] >= d) return i;
+        return size;
+    }
+
+    // queue.rs:130-171
+    void insert(uint32_t id, float d) {
+        if (std::isnan(d)) return;
+        if (size == capacity && dists[size - 1] < d) return;
+        size_t idx = size > 0 ? lower_bound(d) : 0;
+        if (size == capacity) {
+            ids.pop_back();
+            visited.pop_back();
+            dists.pop_back();
+            --size;
+        }
+        ids.insert(ids.begin() + idx, id);
+        visited.insert(visited.begin() + idx, 0);
+        dists.insert(dists.begin() + idx, d);
+        ++size;
+        if (idx < cursor) cursor = idx;
+    }
+
+    // queue.rs:316-318
+    bool has_notvisited() const { return cursor < std::min(capacity, size); }
+
+    // queue.rs:297-313
+    bool closest_notvisited(uint32_t* id, float* d) {
+        if (!has_notvisited()) return false;
+        size_t cur = cursor;
+        visited[cur] = 1;
+        ++cursor;
+        while (cursor < size && visited[cursor]) ++cursor;
+        *id = ids[cur];
+        *d = dists[cur];
+        return true;
+    }
+};
+
+// ------------------------------------------------------------------ query distance
+struct QueryDist {
+    const orc_index* idx;
+    int flavour;
+    int dq;               // dtype of the prepared query
+    const void* q;        // prepared query
+    std::vector<float> widened;  // f16 query -> f32 (layers/full.rs:421-423)
+    std::vector<float> lut;      // PQ table (TableL2 / TableIP)
+    std::vector<float> qf32;     // PQ: f32 view of the query
+
+    QueryDist(const orc_index* i, const void* query, int fl) : idx(i), flavour(fl) {
+        dq = idx->dtype;
+        q = query;
+        if (idx->dtype == ORC_F16) {
+            widened.resize(idx->dim);
+            const uint16_t* h = (const uint16_t*)query;
+            for (uint32_t k = 0; k < idx->dim; ++k) widened[k] = orc_f16_to_f32(h[k]);
+            dq = ORC_F32;
+            q = widened.data();
+        }
+        if (idx->pq_codes) {
+            // providers QuantAccessor: query converted to f32 (T: Into<f32>), then
+            // QueryComputer::new (pq/distance/dynamic.rs:63-87)
+            qf32.resize(idx->dim);
+            for (uint32_t k = 0; k < idx->dim; ++k) {
+                switch (idx->dtype) {
+                    case ORC_F32: qf32[k] = ((const float*)query)[k]; break;
+                    case ORC_F16: qf32[k] = widened[k]; break;
+                    case ORC_I8: qf32[k] = (float)((const int8_t*)query)[k]; break;
+                    default: qf32[k] = (float)((const uint8_t*)query)[k]; break;
+                }
+            }
+            if (idx->metric != ORC_COSINE) {
+                lut.resize((size_t)idx->pq_chunks * idx->pq_centers);
+                orc_pq_populate_lut(idx->pq_pivots, idx->pq_centers, idx->dim, idx->pq_offsets,
+                                    idx->pq_chunks,
+                                    idx->metric == ORC_INNER_PRODUCT ? ORC_INNER_PRODUCT : ORC_L2,
+                                    qf32.data(), lut.data());
+            }
+        }
+    }
+
+    float operator()(uint32_t id) const {
+        if (idx->pq_codes) {
+            const uint8_t* code = idx->pq_codes + (size_t)id * idx->pq_chunks;
+            if (idx->metric == ORC_COSINE)
+                return orc_pq_direct_distance(idx->pq_pivots, idx->dim, idx->pq_offsets,
+                                              idx->pq_chunks, ORC_COSINE, qf32.data(), code);
+            return orc_pq_lookup(code, idx->pq_chunks, lut.data(), idx->pq_centers);
+        }
+        const char* row = (const char*)idx->vectors + (size_t)id * idx->row_stride;
+        return orc_distance(flavour, dq, idx->dtype, idx->metric, q, row, idx->dim, nullptr);
+    }
+};
+
+struct Visit {
+    uint32_t id;
+    float dist;
+};
+
+// diskann/src/graph/index.rs:1933-2000.  `record` (optional) receives the nodes picked for
+// expansion in order (VisitedSearchRecord, used by insert).
+void search_internal(const orc_index* idx, const QueryDist& qd, uint32_t l_search,
+                     uint32_t beam_width, Queue& best, uint32_t* cmps_out, uint32_t* hops_out,
+                     std::vector<Visit>* record) {
+    std::unordered_set<uint32_t> visited;
+    uint32_t cmps = 0, hops = 0;
+    (void)l_search;
+    const uint64_t total = idx->n_points + idx->n_start;
+    // start_point_distances (diskann-inmem/src/provider.rs:406-433)
+    for (uint32_t s = 0; s < idx->n_start; ++s) {
+        uint32_t id = (uint32_t)(idx->n_points + s);
+        visited.insert(id);
+        best.insert(id, qd(id));
+        ++cmps;
+    }
+    std::vector<uint32_t> beam;
+    std::vector<Visit> neighbors;
+    if (beam_width == 0) beam_width = 1;
+    while (best.has_notvisited()) {
+        beam.clear();
+        uint32_t id;
+        float d;
+        while (beam.size() < beam_width && best.closest_notvisited(&id, &d)) {
+            if (record) record->push_back(Visit{id, d});
+            beam.push_back(id);
+        }
+        neighbors.clear();
+        // expand_beam (diskann-inmem/src/provider.rs:436-479, 620-690)
+        for (uint32_t node : beam) {
+            const uint32_t* row = idx->adj + (size_t)node * idx->adj_stride;
+            uint32_t deg = row[0];
+            for (uint32_t j = 0; j < deg; ++j) {
+                uint32_t n = row[1 + j];
+                if (!visited.insert(n).second) continue;  // pred.eval_mut
+                if (n >= total) continue;                 // is_in_bounds
+                neighbors.push_back(Visit{n, qd(n)});
+            }
+        }
+        for (const Visit& v : neighbors) best.insert(v.id, v.dist);
+        cmps += (uint32_t)neighbors.size();
+        hops += (uint32_t)beam.size();
+    }
+    *cmps_out = cmps;
+    *hops_out = hops;
+}
+
+uint32_t search_one(const orc_index* idx, const void* query, uint32_t k, uint32_t l_search,
+                    uint32_t beam_width, int flavour, uint32_t* out_ids, float* out_dists,
+                    uint32_t* out_cmps, uint32_t* out_hops) {
+    QueryDist qd(idx, query, flavour);
+    // scratch.rs:195-208: queue capacity = L + number of start points
+    Queue best((size_t)l_search + idx->n_start);
+    uint32_t cmps = 0, hops = 0;
+    search_internal(idx, qd, l_search, beam_width, best, &cmps, &hops, nullptr);
+    // post-process (diskann-inmem/src/provider.rs:907-950): skip ids with no external
+    // mapping (start points), stop when the output buffer is full.
+    uint32_t count = 0;
+    size_t n = std::min(best.capacity, best.size);
+    for (size_t i = 0; i < n && count < k; ++i) {
+        if (best.ids[i] >= idx->n_points) continue;
+        out_ids[count] = best.ids[i];
+        out_dists[count] = best.dists[i];
+        ++count;
+    }
+    for (uint32_t i = count; i < k; ++i) {
+        out_ids[i] = 0xFFFFFFFFu;
+        out_dists[i] = std::numeric_limits<float>::infinity();
+    }
+    if (out_cmps) *out_cmps = cmps;
+    if (out_hops) *out_hops = hops;
+    return count;
+}
+
+// ------------------------------------------------------------------ prune
+struct State {
+    float occlude_factor = 0.0f;
+    uint16_t last_checked = 0;
+    uint16_t neighbor = 0;
+};
+
+float pair_distance(const orc_index* idx, int flavour, uint32_t a, uint32_t b) {
+    const char* base = (const char*)idx->vectors;
+    return orc_distance(flavour, idx->dtype, idx->dtype, idx->metric, base + (size_t)a * idx->row_stride,
+                        base + (size_t)b * idx->row_stride, idx->dim, nullptr);
+}
+
+// diskann/src/graph/internal/prune.rs:106-259
+uint32_t robust_prune(const orc_index* idx, const uint32_t* pool_ids, const float* pool_dists,
+                      const uint8_t* excluded, uint32_t pool_len, uint32_t degree, float alpha,
+                      int flavour, uint32_t* out_pos, uint64_t* ncmp) {
+    std::vector<State> states(pool_len);
+    const int kind = idx->metric == ORC_INNER_PRODUCT ? 1 : 0;  // config/mod.rs:69-76
+    float current_alpha = 1.0f;
+    const float increment_factor = std::fmin(alpha, 1.2f);
+    uint32_t found = 0;
+    uint64_t cmp = 0;
+    while (found < degree) {
+        for (uint32_t i = 0; i < pool_len; ++i) {
+            if (found >= degree) break;
+            float occlude_factor = states[i].occlude_factor;
+            uint16_t last_checked = states[i].last_checked;
+            if (occlude_factor > current_alpha) continue;
+            if (excluded && excluded[i]) {
+                states[i].occlude_factor = std::numeric_limits<float>::max();
+                continue;
+            }
+            while (last_checked != found) {
+                uint32_t result_position = states[last_checked].neighbor;
+                ++last_checked;
+                if (result_position >= i) {
+                    states[i].last_checked = last_checked;
+                    continue;
+                }
+                float distance = (excluded && excluded[result_position])
+                                     ? std::numeric_limits<float>::max()
+                                     : pair_distance(idx, flavour, pool_ids[i], pool_ids[result_position]);
+                ++cmp;
+                occlude_factor = orc_update_occlude_factor(kind, pool_dists[i], distance,
+                                                           occlude_factor, current_alpha);
+                if (occlude_factor > current_alpha) break;
+            }
+            states[i].last_checked = last_checked;
+            if (occlude_factor > current_alpha) {
+                states[i].occlude_factor = occlude_factor;
+                continue;
+            }
+            states[i].occlude_factor = std::numeric_limits<float>::max();
+            states[found].neighbor = (uint16_t)i;
+            ++found;
+        }
+        if (current_alpha == alpha) break;
+        current_alpha = std::fmin(current_alpha * increment_factor, alpha);
+    }
+    for (uint32_t n = 0; n < found; ++n) out_pos[n] = states[n].neighbor;
+    if (ncmp) *ncmp = cmp;
+    return found;
+}
+
+// SortedNeighbors::new (graph/internal/sorted_neighbors.rs:26-44): sort by distance and
+// truncate.  The reference uses an unstable sort, so the order of exactly-tied candidates is
+// unspecified there; the oracle breaks ties by original position (stable).
+void sort_pool(std::vector<Visit>& pool, size_t max) {
+    std::stable_sort(pool.begin(), pool.end(),
+                     [](const Visit& a, const Visit& b) { return a.dist < b.dist; });
+    if (pool.size() > max) pool.resize(max);
+}
+
+constexpr size_t MAX_OCCLUSION = 750;  // graph/config/defaults.rs:13
+
+// occlude_list (index.rs:2565-2650) without saturation (defaults.rs SATURATE_AFTER_PRUNE=false)
+void occlude_list(const orc_index* idx, std::vector<Visit>& pool, uint32_t location,
+                  uint32_t degree, float alpha, int flavour, std::vector<uint32_t>& out) {
+    out.clear();
+    if (pool.empty()) return;
+    std::vector<uint32_t> ids(pool.size()), pos(pool.size());
+    std::vector<float> dists(pool.size());
+    std::vector<uint8_t> excl(pool.size());
+    for (size_t i = 0; i < pool.size(); ++i) {
+        ids[i] = pool[i].id;
+        dists[i] = pool[i].dist;
+        excl[i] = pool[i].id == location;
+    }
+    uint32_t found = robust_prune(idx, ids.data(), dists.data(), excl.data(), (uint32_t)pool.size(),
+                                  degree, alpha, flavour, pos.data(), nullptr);
+    for (uint32_t n = 0; n < found; ++n) out.push_back(ids[pos[n]]);
+}
+
+}  // namespace
+
+extern "C" {
+
+// graph/config/mod.rs:80-103
+float orc_update_occlude_factor(int kind, float d_ik, float d_jk, float cur, float alpha) {
+    if (kind == 0) {
+        if (d_jk == 0.0f) return std::numeric_limits<float>::max();
+        return std::fmax(cur, d_ik / d_jk);  // f32::max
+    }
+    if (d_jk < alpha * d_ik) return alpha + 0.01f;  // OCCLUDING_MASK, config/mod.rs:62
+    return cur;
+}
+
+uint32_t orc_robust_prune(const orc_index* idx, const uint32_t* pool_ids,
+                          const float* pool_dists, const uint8_t* excluded, uint32_t pool_len,
+                          uint32_t degree, float alpha, int flavour, uint32_t* out_pos,
+                          uint64_t* out_ncmp) {
+    return robust_prune(idx, pool_ids, pool_dists, excluded, pool_len, degree, alpha, flavour,
+                        out_pos, out_ncmp);
+}
+
+uint32_t orc_search(const orc_index* idx, const void* query, uint32_t k, uint32_t l_search,
+                    uint32_t beam_width, int flavour, uint32_t* out_ids, float* out_dists,
+                    uint32_t* out_cmps, uint32_t* out_hops) {
+    return search_one(idx, query, k, l_search, beam_width, flavour, out_ids, out_dists, out_cmps,
+                      out_hops);
+}
+
+// benchmark-core/src/search/api.rs:400-434 (PartitionIter: contiguous ranges, the first
+// nq % T ranges one longer).
+void orc_search_batch(const orc_index* idx, const void* queries, uint64_t query_stride,
+                      uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam_width,
+                      int flavour, int n_threads, uint32_t* out_ids, float* out_dists,
+                      uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops) {
+    if (n_threads < 1) n_threads = 1;
+    if ((uint32_t)n_threads > nq) n_threads = nq ? (int)nq : 1;
+    auto work = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t i = lo; i < hi; ++i) {
+            uint32_t c = 0, h = 0;
+            uint32_t cnt = search_one(idx, (const char*)queries + (size_t)i * query_stride, k,
+                                      l_search, beam_width, flavour, out_ids + (size_t)i * k,
+                                      out_dists + (size_t)i * k, &c, &h);
+            if (out_counts) out_counts[i] = cnt;
+            if (out_cmps) out_cmps[i] = c;
+            if (out_hops) out_hops[i] = h;
+        }
+    };
+    if (n_threads == 1) {
+        work(0, nq);
+        return;
+    }
+    std::vector<std::thread> ts;
+    uint32_t base = nq / n_threads, extra = nq % n_threads, lo = 0;
+    for (int t = 0; t < n_threads; ++t) {
+        uint32_t len = base + ((uint32_t)t < extra ? 1 : 0);
+        ts.emplace_back(work, lo, lo + len);
+        lo += len;
+    }
+    for (auto& t : ts) t.join();
+}
+
+// DiskANNIndex::insert for i = 0..n_points (index.rs:226-341), add_edge_and_prune
+// (index.rs:2264-2341), robust_prune_list (index.rs:2397-2454).  max_backedges defaults to
+// pruned_degree (config/mod.rs:292-306).
+void orc_build(int dtype, int metric, uint32_t dim, uint64_t n_points, uint32_t n_start,
+               const void* vectors, uint64_t row_stride, uint32_t pruned_degree,
+               uint32_t max_degree, uint32_t l_build, float alpha, uint32_t* adj,
+               uint32_t adj_stride) {
+    orc_index idx;
+    std::memset(&idx, 0, sizeof(idx));
+    idx.dtype = dtype;
+    idx.metric = metric;
+    idx.dim = dim;
+    idx.n_points = n_points;
+    idx.n_start = n_start;
+    idx.vectors = vectors;
+    idx.row_stride = row_stride;
+    idx.adj = adj;
+    idx.adj_stride = adj_stride;
+    const int flavour = ORC_FLAVOUR_AVX2;
+    auto row = [&](uint32_t id) { return adj + (size_t)id * adj_stride; };
+    auto set_neighbors = [&](uint32_t id, const std::vector<uint32_t>& v) {
+        uint32_t* r = row(id);
+        r[0] = (uint32_t)v.size();
+        for (size_t j = 0; j < v.size(); ++j) r[1 + j] = v[j];
+    };
+    std::vector<Visit> record, pool;
+    std::vector<uint32_t> new_neighbors, pruned, list;
+    for (uint64_t p = 0; p < n_points; ++p) {
+        uint32_t id = (uint32_t)p;
+        const void* vec = (const char*)vectors + (size_t)id * row_stride;
+        QueryDist qd(&idx, vec, flavour);
+        Queue best((size_t)l_build + n_start);
+        uint32_t cmps = 0, hops = 0;
+        record.clear();
+        search_internal(&idx, qd, l_build, 1, best, &cmps, &hops, &record);
+        sort_pool(record, MAX_OCCLUSION);
+        occlude_list(&idx, record, id, pruned_degree, alpha, flavour, new_neighbors);
+        set_neighbors(id, new_neighbors);
+        size_t nb = std::min<size_t>(new_neighbors.size(), pruned_degree);
+        for (size_t s = 0; s < nb; ++s) {
+            uint32_t source = new_neighbors[s];
+            uint32_t* r = row(source);
+            uint32_t deg = r[0];
+            bool present = false;
+            for (uint32_t j = 0; j < deg; ++j) present |= r[1 + j] == id;
+            if (present) continue;
+            if (deg + 1 <= max_degree) {
+                r[1 + deg] = id;
+                r[0] = deg + 1;
+                continue;
+            }
+            list.assign(r + 1, r + 1 + deg);
+            list.push_back(id);
+            pool.clear();
+            for (uint32_t other : list)
+                if (other != source) pool.push_back(Visit{other, pair_distance(&idx, flavour, source, other)});
+            sort_pool(pool, MAX_OCCLUSION);
+            occlude_list(&idx, pool, source, pruned_degree, alpha, flavour, pruned);
+            set_neighbors(source, pruned);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ queue C API
+struct orc_queue {
+    Queue q;
+    explicit orc_queue(uint32_t cap) : q(cap) {}
+};
+orc_queue* orc_queue_new(uint32_t capacity) { return new orc_queue(capacity); }
+void orc_queue_free(orc_queue* q) { delete q; }
+void orc_queue_insert(orc_queue* q, uint32_t id, float dist) { q->q.insert(id, dist); }
+int orc_queue_has_notvisited(const orc_queue* q) { return q->q.has_notvisited() ? 1 : 0; }
+int orc_queue_closest_notvisited(orc_queue* q, uint32_t* id, float* dist) {
+    return q->q.closest_notvisited(id, dist) ? 1 : 0;
+}
+uint32_t orc_queue_size(const orc_queue* q) { return (uint32_t)q->q.size; }
+void orc_queue_get(const orc_queue* q, uint32_t i, uint32_t* id, float* dist, int* visited) {
+    *id = q->q.ids[i];
+    *dist = q->q.dists[i];
+    *visited = q->q.visited[i];
+}
+
+// ------------------------------------------------------------------ measurement helpers
+void orc_bruteforce_knn(int dtype, int metric, uint32_t dim, const void* base, uint64_t n,
+                        uint64_t row_stride, const void* queries, uint64_t query_stride,
+                        uint32_t nq, uint32_t k, int n_threads, uint32_t* out_ids,
+                        float* out_dists) {
+    if (n_threads < 1) n_threads = 1;
+    auto work = [&](uint32_t lo, uint32_t hi) {
+        std::vector<std::pair<float, uint32_t>> heap;
+        std::vector<float> widened(dim);
+        for (uint32_t qi = lo; qi < hi; ++qi) {
+            const void* q = (const char*)queries + (size_t)qi * query_stride;
+            int dq = dtype;
+            if (dtype == ORC_F16) {
+                for (uint32_t j = 0; j < dim; ++j) widened[j] = orc_f16_to_f32(((const uint16_t*)q)[j]);
+                q = widened.data();
+                dq = ORC_F32;
+            }
+            heap.clear();
+            for (uint64_t i = 0; i < n; ++i) {
+                float d = orc_distance(ORC_FLAVOUR_AVX2, dq, dtype, metric, q,
+                                       (const char*)base + i * row_stride, dim, nullptr);
+                std::pair<float, uint32_t> e(d, (uint32_t)i);
+                if (heap.size() < k) {
+                    heap.push_back(e);
+                    std::push_heap(heap.begin(), heap.end());
+                } else if (e < heap.front()) {
+                    std::pop_heap(heap.begin(), heap.end());
+                    heap.back() = e;
+                    std::push_heap(heap.begin(), heap.end());
+                }
+            }
+            std::sort_heap(heap.begin(), heap.end());
+            for (uint32_t j = 0; j < k; ++j) {
+                out_ids[(size_t)qi * k + j] = j < heap.size() ? heap[j].second : 0xFFFFFFFFu;
+                out_dists[(size_t)qi * k + j] =
+                    j < heap.size() ? heap[j].first : std::numeric_limits<float>::infinity();
+            }
+        }
+    };
+    std::vector<std::thread> ts;
+    uint32_t per = (nq + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        uint32_t lo = std::min<uint32_t>(nq, t * per), hi = std::min<uint32_t>(nq, lo + per);
+        if (lo < hi) ts.emplace_back(work, lo, hi);
+    }
+    for (auto& t : ts) t.join();
+}
+
+// benchmark-core/src/recall.rs:146-236 (fixed-size ground truth, no distance ties):
+// integer hit counts over all queries divided once by nq * k.
+double orc_recall(const uint32_t* gt, uint32_t gt_stride, const uint32_t* res,
+                  uint32_t res_stride, const uint32_t* res_counts, uint32_t nq, uint32_t k,
+                  uint32_t n) {
+    uint64_t hits = 0;
+    for (uint32_t q = 0; q < nq; ++q) {
+        const uint32_t* g = gt + (size_t)q * gt_stride;
+        const uint32_t* r = res + (size_t)q * res_stride;
+        uint32_t rn = res_counts ? std::min(res_counts[q], n) : n;
+        for (uint32_t i = 0; i < k; ++i)
+            for (uint32_t j = 0; j < rn; ++j)
+                if (g[i] == r[j]) {
+                    ++hits;
+                    break;
+                }
+    }
+    return nq ? (double)hits / ((double)nq * (double)k) : 0.0;
+}
+
+int orc_hardware_threads(void) {
+    unsigned n = std::thread::hardware_concurrency();
+    return n ? (int)n : 1;
+}
+
+}  // extern "C"

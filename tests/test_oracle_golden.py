@@ -1,0 +1,484 @@
+"""Pins the CPU oracle against every portable golden vector / known-answer test the reference
+holds for the distance hot path.  CPU only."""
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+METRICS = [O.L2, O.INNER_PRODUCT, O.COSINE, O.COSINE_NORMALIZED]
+
+
+def approx(a, b, eps, rel):
+    """approx::relative_eq semantics (abs diff <= eps or <= rel * max(|a|,|b|))."""
+    if a == b:
+        return True
+    if math.isinf(a) or math.isinf(b):
+        return False
+    d = abs(a - b)
+    return d <= eps or d <= rel * max(abs(a), abs(b))
+
+
+# ---------------------------------------------------------------- known answers
+
+def test_kat_l2_f32_256_exact():
+    # distance_provider.rs:744-828: assert_eq!(distance, 429141.2)
+    g = json.load(open(os.path.join(GOLDEN, "kat_l2_f32_256.json")))
+    v = np.array(g["values"], np.float32)
+    x, y = v[:256], v[256:]
+    expected = np.float32(g["expected"])
+    assert O.distance(x, y, O.L2, O.SIMD) == expected
+    assert O.distance(x, y, O.L2, O.AVX2) == expected
+
+
+def test_specialize_3_l2():
+    # implementations.rs:61-70
+    x = np.array([1, 2, 3], np.float32)
+    y = np.array([2, 3, 4], np.float32)
+    for fl in (O.SIMD, O.SCALAR, O.AVX2):
+        assert O.distance(x, y, O.L2, fl) == np.float32(3.0)
+
+
+def test_f16_infinity_l2_is_nan():
+    # distance_provider.rs:970-977
+    a = np.full(384, np.inf, np.float16)
+    for fl in (O.SIMD, O.AVX2):
+        assert math.isnan(O.distance(a, a, O.L2, fl))
+
+
+def test_cosine_zero_norm_is_distance_one():
+    # simd.rs:2358-2360: similarity 0 when either norm < f32::MIN_POSITIVE -> distance 1
+    for dt in (np.float32, np.float16, np.int8, np.uint8):
+        z = np.zeros(37, dt)
+        o = np.ones(37, dt)
+        for fl in (O.SIMD, O.SCALAR, O.AVX2):
+            assert O.distance(z, o, O.COSINE, fl) == np.float32(1.0)
+            assert O.distance(o, z, O.COSINE, fl) == np.float32(1.0)
+    tiny = np.full(4, 1e-30, np.float32)
+    assert O.distance(tiny, np.ones(4, np.float32), O.COSINE) == np.float32(1.0)
+
+
+def test_metric_value_conventions():
+    # distance_provider.rs:30-43; implementations.rs:217-404
+    x = np.array([1, 2, 3, 4], np.float32)
+    y = np.array([4, 3, 2, 1], np.float32)
+    assert O.distance(x, y, O.L2) == np.float32(20.0)
+    assert O.distance(x, y, O.INNER_PRODUCT) == np.float32(-20.0)
+    assert O.distance(x, y, O.COSINE_NORMALIZED) == np.float32(1.0 - 20.0)
+    cos = 20.0 / 30.0
+    assert abs(float(O.distance(x, y, O.COSINE)) - (1.0 - cos)) < 1e-6
+    xi = x.astype(np.int8)
+    yi = y.astype(np.int8)
+    # integers: CosineNormalized == Cosine (distance_provider.rs:275-297)
+    assert O.distance(xi, yi, O.COSINE_NORMALIZED) == O.distance(xi, yi, O.COSINE)
+
+
+# ---------------------------------------------------------------- corner cases + fuzz
+
+def _pairs():
+    return [(np.float32, np.float32), (np.float16, np.float16), (np.float32, np.float16),
+            (np.int8, np.int8), (np.uint8, np.uint8)]
+
+
+def _corner(dt):
+    if dt in (np.float32, np.float16):
+        return [0.0, -5.0, 5.0, 10.0]
+    if dt == np.int8:
+        return [-128, 127, 0]
+    return [0, 255, 0]
+
+
+def _bounds(dt, metric):
+    # distance_provider.rs:465-499
+    if dt in (np.int8, np.uint8):
+        return (1e-6, 1e-6) if metric in (O.COSINE, O.COSINE_NORMALIZED) else (0.0, 0.0)
+    return (1e-5, 1e-5) if metric == O.L2 else (1e-4, 1e-4)
+
+
+def _fuzz(rng, dt, n):
+    if dt in (np.float32, np.float16):
+        return rng.normal(0.0, 1.0, n).astype(dt)  # reference: Normal(0, 1)
+    info = np.iinfo(dt)
+    return rng.integers(info.min, info.max + 1, n).astype(dt)
+
+
+@pytest.mark.parametrize("dl,dr", _pairs())
+def test_corner_cases_and_fuzz_all_dims(dl, dr):
+    """distance_provider.rs:551-606 sweep: dim 0..256 x 4 metrics, corner broadcasts
+    (test_util.rs:154-184, 269-305) + seeded fuzz; SIMD order vs the scalar definition
+    within the reference's bounds, AVX2 intrinsics == SIMD emulation bit for bit."""
+    rng = np.random.default_rng(0x5eed)
+    for dim in list(range(0, 66)) + [95, 96, 97, 100, 127, 128, 129, 160, 255, 256]:
+        cases = [(np.full(dim, a, dl), np.full(dim, b, dr)) for a in _corner(dl) for b in _corner(dr)]
+        cases += [(_fuzz(rng, dl, dim), _fuzz(rng, dr, dim)) for _ in range(4)]
+        for metric in METRICS:
+            eps, rel = _bounds(dr, metric)
+            for x, y in cases:
+                s = O.distance(x, y, metric, O.SIMD)
+                r = O.distance(x, y, metric, O.SCALAR)
+                a = O.distance(x, y, metric, O.AVX2)
+                assert s.tobytes() == a.tobytes() or (math.isnan(s) and math.isnan(a)), (dim, metric, s, a)
+                assert approx(float(s), float(r), eps, rel), (dim, metric, s, r)
+
+
+def test_integer_kernels_match_numpy_exactly():
+    rng = np.random.default_rng(7)
+    for dt in (np.int8, np.uint8):
+        for dim in (1, 15, 16, 17, 100, 128, 1000):
+            x = _fuzz(rng, dt, dim)
+            y = _fuzz(rng, dt, dim)
+            xi, yi = x.astype(np.int64), y.astype(np.int64)
+            assert O.distance(x, y, O.L2) == np.float32(((xi - yi) ** 2).sum())
+            assert O.distance(x, y, O.INNER_PRODUCT) == np.float32(-(xi * yi).sum())
+
+
+def test_resumable_equals_one_shot_when_chunks_are_multiples_of_eight():
+    # PQ direct distance over chunk boundaries aligned to the SIMD width restarts the
+    # accumulator rotation per chunk, so it only equals the one-shot kernel for one chunk.
+    rng = np.random.default_rng(3)
+    dim, chunks = 64, 1
+    piv = rng.normal(size=(256, dim)).astype(np.float32)
+    off = O.pq_offsets(dim, chunks)
+    q = rng.normal(size=dim).astype(np.float32)
+    code = np.array([17], np.uint8)
+    got = O.lib().orc_pq_direct_distance(O.ptr(piv), dim, O.ptr(off), chunks, O.L2, O.ptr(q), O.ptr(code))
+    assert np.float32(got) == O.distance(q, piv[17], O.L2)
+
+
+# ---------------------------------------------------------------- f16 conversion
+
+def test_f16_conversion_table_sample():
+    g = json.load(open(os.path.join(GOLDEN, "float16_sample.json")))
+    L = O.lib()
+    for bits, val in g["rows"]:
+        got = L.orc_f16_to_f32(bits)
+        if val == "nan":
+            assert math.isnan(got)
+        elif val == "neg_infinity":
+            assert got == -math.inf
+        elif val == "infinity":
+            assert got == math.inf
+        else:
+            assert np.float32(got) == np.float32(val), (bits, val, got)  # shortest f32 repr
+
+
+def test_f16_conversion_all_values_vs_numpy():
+    L = O.lib()
+    bits = np.arange(65536, dtype=np.uint16)
+    want = bits.view(np.float16).astype(np.float32)
+    for b in range(0, 65536):
+        got = L.orc_f16_to_f32(b)
+        w = float(want[b])
+        assert (math.isnan(got) and math.isnan(w)) or got == w
+    # narrowing: round to nearest even, checked on a sweep of f32 values
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([rng.normal(0, 100, 4000), rng.normal(0, 1e-5, 2000), [0.0, -0.0, 65504.0, 65520.0, 1e9]])
+    for v in vals.astype(np.float32):
+        assert L.orc_f32_to_f16(float(v)) == int(np.float32(v).astype(np.float16).view(np.uint16))
+
+
+# ---------------------------------------------------------------- queue (queue.rs:607-...)
+
+class Q:
+    def __init__(self, cap):
+        self.L = O.lib()
+        self.q = self.L.orc_queue_new(cap)
+
+    def __del__(self):
+        self.L.orc_queue_free(self.q)
+
+    def insert(self, i, d):
+        self.L.orc_queue_insert(self.q, i, d)
+
+    def size(self):
+        return self.L.orc_queue_size(self.q)
+
+    def get(self, i):
+        a, b, c = C.c_uint32(), C.c_float(), C.c_int()
+        self.L.orc_queue_get(self.q, i, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, bool(c.value)
+
+    def has(self):
+        return bool(self.L.orc_queue_has_notvisited(self.q))
+
+    def pop(self):
+        a, b = C.c_uint32(), C.c_float()
+        ok = self.L.orc_queue_closest_notvisited(self.q, C.byref(a), C.byref(b))
+        return (a.value, b.value) if ok else None
+
+
+def test_queue_insert():
+    q = Q(3)
+    q.insert(1, 1.0)
+    q.insert(2, 0.5)
+    assert q.size() == 2
+    q.insert(3, 0.9)
+    assert q.size() == 3 and q.get(2)[0] == 1
+    q.insert(4, 2.0)  # dropped
+    assert q.size() == 3
+    assert [q.get(i)[0] for i in range(3)] == [2, 3, 1]
+
+
+def test_queue_visit():
+    q = Q(3)
+    q.insert(1, 1.0)
+    q.insert(2, 0.5)
+    assert not q.get(0)[2]
+    q.insert(3, 1.5)
+    assert q.has()
+    assert q.pop() == (2, 0.5) and q.get(0)[2] and q.has()
+    assert q.pop() == (1, 1.0) and q.get(1)[2] and q.has()
+    assert q.pop() == (3, 1.5) and q.get(2)[2] and not q.has()
+    assert q.pop() is None
+
+
+def test_queue_insert_on_full_queue():
+    q = Q(5)
+    for i, d in [(5, 0.5), (2, 0.2), (4, 0.4), (1, 0.1), (3, 0.3)]:
+        q.insert(i, d)
+    q.insert(6, 0.6)
+    assert q.get(4)[0] == 5 and q.size() == 5
+    q.insert(35, 0.35)
+    assert q.get(4)[0] == 4 and q.size() == 5
+
+
+def test_queue_ties_nan_and_cursor():
+    # queue.rs:130-171: lower-bound insertion puts a new item BEFORE equal distances; an item
+    # equal to the last of a full queue is accepted (only `last < new` rejects); NaN ignored;
+    # inserting ahead of the cursor moves the cursor back.
+    q = Q(3)
+    q.insert(1, 1.0)
+    q.insert(2, 1.0)
+    assert [q.get(i)[0] for i in range(2)] == [2, 1]
+    q.insert(3, float("nan"))
+    assert q.size() == 2
+    q.insert(4, 1.0)
+    q.insert(5, 1.0)  # full, last == new -> accepted, evicts last
+    assert [q.get(i)[0] for i in range(3)] == [5, 4, 2]
+    assert q.pop() == (5, 1.0)
+    q.insert(6, 0.5)
+    assert q.pop() == (6, 0.5)
+    q = Q(40)
+    rng = np.random.default_rng(42)
+    for i, d in enumerate(rng.uniform(-1, 1, 60).astype(np.float32)):
+        q.insert(i, float(d))
+    ds = [q.get(i)[1] for i in range(40)]
+    assert ds == sorted(ds)
+
+
+# ---------------------------------------------------------------- prune rule
+
+def test_update_occlude_factor_table():
+    # diskann/src/graph/config/mod.rs:1257-1315
+    f = O.lib().orc_update_occlude_factor
+    FMAX = float(np.finfo(np.float32).max)
+    for d_ik in [float(np.finfo(np.float32).min), -1.2, 0.0, 0.123, 50.0, FMAX]:
+        assert f(0, d_ik, 0.0, 1.0, 2.0) == FMAX
+    for alpha in [1.0, 1.1, 1.2, 1.3]:
+        assert f(0, 2.0, 1.0, 1.0, alpha) == 2.0
+        assert f(0, 2.0, 1.0, 2.0, alpha) == 2.0
+        assert f(0, 2.0, 1.0, 3.0, alpha) == 3.0
+    assert f(1, -2.0, -1.0, 0.0, 3.0) == 0.0
+    assert f(1, -3.0, -2.0, 0.0, 1.0) == 0.0
+    assert f(1, -3.0, -3.0, 0.0, 1.0) == 0.0
+    assert f(1, -3.0, -4.0, 0.0, 1.0) == np.float32(1.0) + np.float32(0.01)
+
+
+# ---------------------------------------------------------------- grid greedy search baselines
+
+def grid(dims, size):
+    """diskann/src/graph/test/synthetic.rs:102-348: lattice points (last coordinate fastest),
+    axis-neighbour adjacency in the order (-,+) per axis from the slowest axis, start point at
+    (size,...,size) linked to the last node."""
+    n = size ** dims
+    coords = np.stack(np.meshgrid(*[np.arange(size)] * dims, indexing="ij"), -1).reshape(n, dims)
+    data = np.concatenate([coords.astype(np.float32), np.full((1, dims), size, np.float32)])
+    adj = np.zeros((n + 1, 2 * dims + 1), np.uint32)
+    strides = [size ** (dims - 1 - a) for a in range(dims)]
+    for i in range(n):
+        lst = []
+        for a in range(dims):
+            if coords[i, a] > 0:
+                lst.append(i - strides[a])
+            if coords[i, a] < size - 1:
+                lst.append(i + strides[a])
+        adj[i, 0] = len(lst)
+        adj[i, 1:1 + len(lst)] = lst
+    adj[n, 0] = 1
+    adj[n, 1] = n - 1
+    return data, adj, n
+
+
+def test_grid_search_baselines():
+    g = json.load(open(os.path.join(GOLDEN, "grid_search.json")))
+    assert len(g["cases"]) == 18
+    for case in g["cases"]:
+        data, adj, n = grid(case["grid_dims"], case["grid_size"])
+        idx = O.Index(data, adj, n, 1, O.L2)
+        q = np.array([case["query"]], np.float32)
+        for fl in (O.SIMD, O.AVX2):
+            ids, dists, counts, cmps, hops = idx.search_batch(q, 10, 10, beam=case["beam_width"], flavour=fl)
+            assert counts[0] == case["num_results"], case
+            assert cmps[0] == case["comparisons"], (case, cmps[0])
+            assert hops[0] == case["hops"], (case, hops[0])
+            want = case["results"][:case["num_results"]]
+            assert [int(i) for i in ids[0][:counts[0]]] == [r[0] for r in want], case
+            assert [float(d) for d in dists[0][:counts[0]]] == [r[1] for r in want], case
+
+
+# ---------------------------------------------------------------- PQ closed-form table
+
+def seed_pivots(dim, chunks, n_pivots, start):
+    # pq/distance/test_utils.rs:117-158: pivot[p][chunk c][*] = S + p + c
+    off = O.pq_offsets(dim, chunks)
+    piv = np.zeros((n_pivots, dim), np.float32)
+    for p in range(n_pivots):
+        for c in range(chunks):
+            piv[p, int(off[c]):int(off[c + 1])] = start + p + c
+    return piv, off
+
+
+def expected_vector(code, off, start):
+    # test_utils.rs:93-111
+    v = []
+    for i, c in enumerate(code):
+        v += [start + float(i + int(c))] * int(off[i + 1] - off[i])
+    return np.array(v, np.float32)
+
+
+def test_pq_chunk_partition():
+    # diskann-quantization/src/views.rs:226-243 (+ test :528-545: 8/3 -> 3,3,2)
+    assert list(O.pq_offsets(8, 3)) == [0, 3, 6, 8]
+    assert list(O.pq_offsets(128, 32)) == list(range(0, 129, 4))
+    assert list(O.pq_offsets(10, 4)) == [0, 3, 6, 8, 10]
+
+
+@pytest.mark.parametrize("dim,chunks,n_pivots", [(17, 4, 7), (128, 32, 256), (96, 12, 256), (5, 5, 3)])
+def test_pq_closed_form_table(dim, chunks, n_pivots):
+    """test_utils.rs test_l2_inner / test_ip_inner / test_cosine_inner restated with numpy
+    seeds: table lookups vs full-precision distances to the reconstructed vector."""
+    rng = np.random.default_rng(dim * 1000 + chunks)
+    start = 2.0
+    piv, off = seed_pivots(dim, chunks, n_pivots, start)
+    L = O.lib()
+    for _ in range(8):
+        q = rng.normal(0, 1, dim).astype(np.float32)
+        codes = rng.integers(0, n_pivots, (16, chunks)).astype(np.uint8)
+        for metric, rel in [(O.L2, 1e-5), (O.INNER_PRODUCT, 2e-5), (O.COSINE, 2e-6), (O.COSINE_NORMALIZED, 1e-5)]:
+            out = np.zeros(16, np.float32)
+            L.orc_pq_query_distances(O.ptr(piv), n_pivots, dim, O.ptr(off), chunks, metric, O.ptr(q), O.ptr(codes),
+                                     16, O.ptr(out))
+            for i in range(16):
+                ev = expected_vector(codes[i], off, start)
+                m = O.L2 if metric == O.COSINE_NORMALIZED else metric  # dynamic.rs:80-85
+                want = float(O.distance(q, ev, m))
+                assert approx(float(out[i]), want, 1e-4, max(rel, 1e-4)), (metric, out[i], want)
+                # the direct (LUT-free) path and the LUT path agree to rounding
+                d = L.orc_pq_direct_distance(O.ptr(piv), dim, O.ptr(off), chunks, m, O.ptr(q), O.ptr(codes[i]))
+                assert approx(float(d), want, 1e-4, 1e-4)
+        # symmetric code x code distances == full-precision distance of the reconstructions
+        a, b = codes[0], codes[1]
+        for metric in (O.L2, O.INNER_PRODUCT, O.COSINE):
+            got = L.orc_pq_self_distance(O.ptr(piv), dim, O.ptr(off), chunks, metric, O.ptr(a), O.ptr(b))
+            want = float(O.distance(expected_vector(a, off, start), expected_vector(b, off, start), metric))
+            assert approx(float(got), want, 1e-4, 1e-4)
+
+
+def test_pq_lookup_is_sequential_chunk_order_sum():
+    # fixed_chunk_pq_table.rs:82-98: accum starts at 0.0 and adds lut[c][code[c]] in order
+    rng = np.random.default_rng(5)
+    lut = (rng.normal(size=(32, 256)) * 1e3).astype(np.float32)
+    code = rng.integers(0, 256, 32).astype(np.uint8)
+    acc = np.float32(0.0)
+    for c in range(32):
+        acc = np.float32(acc + lut[c, code[c]])
+    got = O.lib().orc_pq_lookup(O.ptr(code), 32, O.ptr(lut), 256)
+    assert np.float32(got) == acc
+
+
+def test_pq_encode_first_minimum_wins():
+    # product/tables/basic.rs:161-194: strict `<`, so the lowest pivot index among ties wins
+    dim, chunks = 8, 2
+    off = O.pq_offsets(dim, chunks)
+    piv = np.zeros((4, dim), np.float32)
+    piv[1] = 1.0
+    piv[2] = 1.0  # duplicate of pivot 1
+    piv[3] = 5.0
+    v = np.full(dim, 1.2, np.float32)
+    code = np.zeros(chunks, np.uint8)
+    assert O.lib().orc_pq_encode(O.ptr(piv), 4, dim, O.ptr(off), chunks, O.ptr(v), O.ptr(code)) == 0
+    assert list(code) == [1, 1]
+    v[:] = np.inf
+    assert O.lib().orc_pq_encode(O.ptr(piv), 4, dim, O.ptr(off), chunks, O.ptr(v), O.ptr(code)) == 1
+
+
+# ---------------------------------------------------------------- scalar quantization
+
+@pytest.mark.parametrize("nbits", [8, 4, 2, 1])
+def test_sq_compensated_distances_track_reconstruction(nbits):
+    """scalar/vectors.rs:509-... test_compensated_distance restated: X = a*X' + B; distances on
+    codes + compensation equal distances on reconstructions (f32 rounding tolerance)."""
+    rng = np.random.default_rng(nbits)
+    dim = 64
+    L = O.lib()
+    maxc = (1 << nbits) - 1
+    scale = np.float32(0.37)
+    a = scale / np.float32(maxc)
+    shift = rng.normal(0, 1, dim).astype(np.float32)
+    for _ in range(10):
+        xc = rng.integers(0, maxc + 1, dim).astype(np.uint8)
+        yc = rng.integers(0, maxc + 1, dim).astype(np.uint8)
+        X = (a * xc.astype(np.float32) + shift).astype(np.float32)
+        Y = (a * yc.astype(np.float32) + shift).astype(np.float32)
+        # compress the reconstruction: recovers the codes and yields the compensation
+        cx = np.zeros(dim, np.uint8)
+        cy = np.zeros(dim, np.uint8)
+        nan = C.c_int(0)
+        comp_x = L.orc_sq_compress(O.ptr(shift), scale, dim, nbits, O.ptr(X), O.ptr(cx), C.byref(nan))
+        comp_y = L.orc_sq_compress(O.ptr(shift), scale, dim, nbits, O.ptr(Y), O.ptr(cy), C.byref(nan))
+        assert (cx == xc).all() and (cy == yc).all() and nan.value == 0
+        ss = float(np.float32(scale) * np.float32(scale))
+        ssn = float((shift.astype(np.float64) ** 2).sum())
+        l2 = L.orc_sq_distance(O.L2, nbits, ss, ssn, O.ptr(cx), comp_x, O.ptr(cy), comp_y, dim)
+        ip = L.orc_sq_distance(O.INNER_PRODUCT, nbits, ss, ssn, O.ptr(cx), comp_x, O.ptr(cy), comp_y, dim)
+        want_l2 = float(((X.astype(np.float64) - Y) ** 2).sum())
+        want_ip = -float((X.astype(np.float64) * Y).sum())
+        assert abs(l2 - want_l2) <= 2e-4 * max(1.0, abs(want_l2))
+        assert abs(ip - want_ip) <= 2e-4 * max(1.0, abs(want_ip))
+
+
+def test_sq_compress_rounding_and_clamp():
+    # quantizer.rs:217: ((f - s) * inverse_scale).clamp(min, max).round(); round half away
+    shift = np.zeros(6, np.float32)
+    v = np.array([-3.0, 0.5, 1.5, 2.5, 254.5, 300.0], np.float32)
+    codes = np.zeros(6, np.uint8)
+    O.lib().orc_sq_compress(O.ptr(shift), 255.0, 6, 8, O.ptr(v), O.ptr(codes), None)
+    assert list(codes) == [0, 1, 2, 3, 255, 255]
+
+
+# ---------------------------------------------------------------- build + search sanity
+
+def test_oracle_build_and_search_reach_high_recall():
+    rng = np.random.default_rng(11)
+    n, d = 2000, 32
+    centers = rng.normal(size=(16, d)).astype(np.float32)
+    base = (centers[rng.integers(0, 16, n)] + 0.3 * rng.normal(size=(n, d))).astype(np.float32)
+    queries = (centers[rng.integers(0, 16, 50)] + 0.3 * rng.normal(size=(50, d))).astype(np.float32)
+    medoid = base[np.argmin(((base - base.mean(0)) ** 2).sum(1))]
+    vecs = np.concatenate([base, medoid[None]])
+    adj = O.build_graph(vecs, n, 1, O.L2, 16, 20, 40)
+    deg = adj[:, 0]
+    assert deg.max() <= 20 and deg[:n].min() >= 1
+    idx = O.Index(vecs, adj, n, 1, O.L2)
+    ids, dists, counts, cmps, hops = idx.search_batch(queries, 10, 40, threads=2)
+    gt, _ = O.bruteforce_knn(base, queries, O.L2, 10, threads=2)
+    assert O.recall(gt, ids, counts, 10, 10) > 0.95
+    assert (np.diff(dists, axis=1) >= 0).all()
+    # single-thread == multi-thread, SIMD emulation == AVX2
+    ids2, dists2, *_ = idx.search_batch(queries, 10, 40, flavour=O.SIMD, threads=1)
+    assert (ids == ids2).all() and (dists.view(np.uint32) == dists2.view(np.uint32)).all()
