@@ -1,0 +1,87 @@
+// dab_common.cuh — shared host-side plumbing for libdiskann_b200.so (index handle, error
+// reporting, launch accounting).  Compiled for sm_100a only.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/diskann_b200.h"
+
+namespace dab {
+
+constexpr uint32_t kNoId = 0xFFFFFFFFu;
+
+// thread-local error message (dab_last_error)
+char* error_buffer();
+int fail(int code, const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define DAB_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return ::dab::fail(_e == cudaErrorMemoryAllocation ? DAB_ERR_OUT_OF_MEMORY         \
+                                                               : DAB_ERR_CUDA,               \
+                               "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
+                               __FILE__, __LINE__);                                           \
+    } while (0)
+
+#define DAB_LAUNCHED() (::dab::g_launches.fetch_add(1, std::memory_order_relaxed))
+
+inline size_t elem_size(int dtype) {
+    switch (dtype) {
+        case DAB_F32: return 4;
+        case DAB_F16: return 2;
+        default: return 1;
+    }
+}
+inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+// A grow-only device (or pinned host) scratch buffer.
+struct Scratch {
+    void* p = nullptr;
+    size_t bytes = 0;
+    bool pinned_host = false;
+    int reserve(size_t n);
+    void release();
+};
+
+}  // namespace dab
+
+struct dab_index {
+    int dtype = 0, metric = 0;
+    uint32_t dim = 0;
+    uint64_t n_points = 0;
+    uint32_t n_start = 0;
+    uint32_t max_degree = 0;
+    int device = 0;
+    int sm_count = 148;
+
+    cudaStream_t stream = nullptr;      // stream in use
+    cudaStream_t own_stream = nullptr;  // library-created
+
+    // HBM-resident snapshot
+    uint8_t* d_vectors = nullptr;  // (n_points + n_start) rows, row_stride bytes apart
+    size_t row_stride = 0;         // round_up(dim * sizeof(T), 32): rows start on sector bounds
+    uint32_t* d_adj = nullptr;     // (n_points + n_start) rows of adj_stride words: [len, ids...]
+    uint32_t adj_stride = 0;       // round_up(max_degree + 1, 8) words (32 B multiple)
+    bool vectors_ready = false, graph_ready = false;
+
+    // product quantization
+    float* d_pivots = nullptr;     // [n_centers][dim]
+    uint32_t* d_offsets = nullptr; // [n_chunks + 1]
+    uint8_t* d_codes = nullptr;    // [n_total][n_chunks]
+    uint32_t pq_chunks = 0, pq_centers = 0;
+
+    // scratch (grow-only)
+    dab::Scratch s_queries, s_ids, s_out, s_out2, s_tables, s_counters, s_stats;
+    dab::Scratch h_stage;  // pinned host staging
+
+    uint64_t n_total() const { return n_points + n_start; }
+};

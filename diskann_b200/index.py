@@ -1,0 +1,239 @@
+"""Host-side mirror of the reference interface for the distance hot path, over the C ABI.
+
+Names follow the reference: `Metric` (diskann-vector/src/distance/metric.rs:8-20),
+`distance_comparer` (distance_provider.rs:44-46), the provider-level snapshot
+(`diskann_inmem::Provider`, diskann-inmem/src/provider.rs:71-131) and the batched
+`KNN::search` (diskann-benchmark-core/src/search/graph/knn.rs:208-238).  All compute happens
+in libdiskann_b200.so on the GPU; numpy is only the host container.
+"""
+import ctypes as C
+import enum
+
+import numpy as np
+
+from . import _lib
+from ._lib import DabError, check
+
+__all__ = ["Metric", "DType", "GpuIndex", "distance_comparer", "pair_distances", "DabError", "launch_count"]
+
+
+class Metric(enum.IntEnum):
+    """#[repr(C)] values of diskann_vector::distance::Metric."""
+    Cosine = 0
+    InnerProduct = 1
+    L2 = 2
+    CosineNormalized = 3
+
+
+class DType(enum.IntEnum):
+    f32 = 0
+    f16 = 1
+    i8 = 2
+    u8 = 3
+
+
+_NP = {DType.f32: np.float32, DType.f16: np.float16, DType.i8: np.int8, DType.u8: np.uint8}
+
+
+def dtype_of(arr):
+    try:
+        return {np.dtype(np.float32): DType.f32, np.dtype(np.float16): DType.f16,
+                np.dtype(np.int8): DType.i8, np.dtype(np.uint8): DType.u8}[arr.dtype]
+    except KeyError:
+        raise DabError(1, f"unsupported element type {arr.dtype}") from None
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def launch_count():
+    return int(_lib.lib().dab_launch_count())
+
+
+def pair_distances(x, y, metric, device=0):
+    """n independent distances x[i] . y[i] (Distance<T, U>::call for each pair)."""
+    x = np.ascontiguousarray(x)
+    y = np.ascontiguousarray(y)
+    if x.ndim != 2 or y.ndim != 2 or x.shape != y.shape:
+        raise DabError(1, f"expected two [n, dim] arrays of equal shape, got {x.shape} and {y.shape}")
+    out = np.empty(x.shape[0], np.float32)
+    check(_lib.lib().dab_pair_distances(int(dtype_of(x)), int(dtype_of(y)), int(metric), x.shape[1], _ptr(x), _ptr(y),
+                                        x.shape[0], _ptr(out), device))
+    return out
+
+
+def distance_comparer(metric, dim=None, device=0):
+    """T::distance_comparer(metric, Some(dim)) -> callable(x, y) -> f32.
+
+    Length mismatches raise (the providers' DistanceFunction panics, implementations.rs:105-130;
+    the inmem layer returns Err, layers/full.rs:203-213)."""
+
+    def call(x, y):
+        x = np.ascontiguousarray(x)
+        y = np.ascontiguousarray(y)
+        if x.ndim != 1 or x.shape != y.shape or (dim is not None and x.shape[0] != dim):
+            raise DabError(1, f"expected slices of length {dim} - instead got {x.shape} and {y.shape}")
+        return pair_distances(x[None, :], y[None, :], metric, device)[0]
+
+    return call
+
+
+class GpuIndex:
+    """Device-resident snapshot of an in-memory index: vectors + adjacency (+ PQ)."""
+
+    def __init__(self, dtype, metric, dim, n_points, n_start=1, max_degree=83, device=0):
+        self._h = C.c_void_p()
+        self.dtype, self.metric, self.dim = DType(dtype), Metric(metric), int(dim)
+        self.n_points, self.n_start, self.max_degree, self.device = int(n_points), int(n_start), int(max_degree), device
+        check(_lib.lib().dab_create(C.byref(self._h), int(dtype), int(metric), dim, n_points, n_start, max_degree, device))
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().dab_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def n_total(self):
+        return self.n_points + self.n_start
+
+    def set_stream(self, cuda_stream_ptr):
+        check(_lib.lib().dab_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    # -- uploads
+    def _rows(self, rows):
+        rows = np.ascontiguousarray(rows)
+        if rows.ndim != 2 or rows.shape[1] != self.dim or dtype_of(rows) != self.dtype:
+            raise DabError(1, f"expected [n, {self.dim}] rows of {self.dtype.name}, got {rows.shape} {rows.dtype}")
+        return rows
+
+    def upload_vectors(self, rows, first=0):
+        rows = self._rows(rows)
+        check(_lib.lib().dab_upload_vectors(self._h, _ptr(rows), first, rows.shape[0]))
+
+    def upload_vectors_device(self, dev_ptr, count, first=0):
+        check(_lib.lib().dab_upload_vectors_device(self._h, C.c_void_p(dev_ptr), first, count))
+
+    def upload_graph(self, adj, first=0):
+        adj = np.ascontiguousarray(adj, dtype=np.uint32)
+        if adj.ndim != 2:
+            raise DabError(1, "adjacency must be [n, stride] u32 with row[0] = degree")
+        check(_lib.lib().dab_upload_graph(self._h, _ptr(adj), adj.shape[1], first, adj.shape[0]))
+
+    def upload_graph_device(self, dev_ptr, src_stride, count, first=0):
+        check(_lib.lib().dab_upload_graph_device(self._h, C.c_void_p(dev_ptr), src_stride, first, count))
+
+    def download_graph(self, first=0, count=None):
+        count = self.n_total - first if count is None else count
+        adj = np.zeros((count, self.max_degree + 1), np.uint32)
+        check(_lib.lib().dab_download_graph(self._h, _ptr(adj), adj.shape[1], first, count))
+        return adj
+
+    def upload_pq(self, pivots, offsets, codes=None):
+        pivots = np.ascontiguousarray(pivots, np.float32)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        if pivots.ndim != 2 or pivots.shape[1] != self.dim:
+            raise DabError(1, f"pivots must be [n_centers, {self.dim}] f32")
+        if codes is not None:
+            codes = np.ascontiguousarray(codes, np.uint8)
+            if codes.shape != (self.n_total, len(offsets) - 1):
+                raise DabError(1, f"codes must be [{self.n_total}, {len(offsets) - 1}] u8, got {codes.shape}")
+        self.pq_chunks, self.pq_centers = len(offsets) - 1, pivots.shape[0]
+        check(_lib.lib().dab_upload_pq(self._h, _ptr(pivots), pivots.shape[0], _ptr(offsets), len(offsets) - 1, _ptr(codes)))
+
+    # -- distances
+    def _queries(self, queries):
+        queries = np.ascontiguousarray(queries)
+        if queries.ndim != 2 or queries.shape[1] != self.dim or dtype_of(queries) != self.dtype:
+            raise DabError(1, f"expected [nq, {self.dim}] queries of {self.dtype.name}, got {queries.shape} {queries.dtype}")
+        return queries
+
+    def distances(self, queries, ids):
+        """out[q][j] = QueryDistance(queries[q]).evaluate(row ids[q][j]) (expand_beam's distance stage)."""
+        queries = self._queries(queries)
+        ids = np.ascontiguousarray(ids, np.uint32)
+        if ids.ndim != 2 or ids.shape[0] != queries.shape[0]:
+            raise DabError(1, "ids must be [nq, c] u32")
+        out = np.empty(ids.shape, np.float32)
+        check(_lib.lib().dab_distances(self._h, _ptr(queries), queries.shape[0], _ptr(ids), ids.shape[1], _ptr(out)))
+        return out
+
+    def row_pair_distances(self, a, b):
+        a = np.ascontiguousarray(a, np.uint32)
+        b = np.ascontiguousarray(b, np.uint32)
+        if a.shape != b.shape or a.ndim != 1:
+            raise DabError(1, "a and b must be 1-d u32 arrays of equal length")
+        out = np.empty(a.shape[0], np.float32)
+        check(_lib.lib().dab_row_pair_distances(self._h, _ptr(a), _ptr(b), a.shape[0], _ptr(out)))
+        return out
+
+    def pairwise(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint32)
+        out = np.empty((ids.shape[0], ids.shape[0]), np.float32)
+        check(_lib.lib().dab_pairwise(self._h, _ptr(ids), ids.shape[0], _ptr(out)))
+        return out
+
+    # -- search
+    def search_batch(self, queries, k, l_search, beam_width=1):
+        """KNN::search for the whole batch: (ids [nq,k], dists [nq,k], counts, cmps, hops)."""
+        queries = self._queries(queries)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), np.uint32)
+        dists = np.empty((nq, k), np.float32)
+        counts = np.empty(nq, np.uint32)
+        cmps = np.empty(nq, np.uint32)
+        hops = np.empty(nq, np.uint32)
+        check(_lib.lib().dab_search_batch(self._h, _ptr(queries), nq, k, l_search, beam_width, _ptr(ids), _ptr(dists),
+                                          _ptr(counts), _ptr(cmps), _ptr(hops)))
+        return ids, dists, counts, cmps, hops
+
+    def search_batch_device(self, d_queries, nq, k, l_search, beam_width, d_ids, d_dists, d_counts=0, d_cmps=0, d_hops=0):
+        """Same with device pointers (integers); results stay in HBM."""
+        check(_lib.lib().dab_search_batch_device(self._h, C.c_void_p(d_queries), nq, k, l_search, beam_width,
+                                                 C.c_void_p(d_ids), C.c_void_p(d_dists), C.c_void_p(d_counts or None),
+                                                 C.c_void_p(d_cmps or None), C.c_void_p(d_hops or None)))
+
+    # -- PQ
+    def pq_populate_lut(self, queries, metric=None):
+        queries = np.ascontiguousarray(queries, np.float32)
+        out = np.empty((queries.shape[0], self.pq_chunks, self.pq_centers), np.float32)
+        check(_lib.lib().dab_pq_populate_lut(self._h, _ptr(queries), queries.shape[0],
+                                             int(self.metric if metric is None else metric), _ptr(out)))
+        return out
+
+    def pq_distances(self, queries, ids):
+        queries = np.ascontiguousarray(queries, np.float32)
+        ids = np.ascontiguousarray(ids, np.uint32)
+        out = np.empty(ids.shape, np.float32)
+        check(_lib.lib().dab_pq_distances(self._h, _ptr(queries), queries.shape[0], _ptr(ids), ids.shape[1], _ptr(out)))
+        return out
+
+    def pq_encode(self, vectors):
+        vectors = np.ascontiguousarray(vectors, np.float32)
+        out = np.empty((vectors.shape[0], self.pq_chunks), np.uint8)
+        check(_lib.lib().dab_pq_encode(self._h, _ptr(vectors), vectors.shape[0], _ptr(out)))
+        return out
+
+    # -- build-side reuse / ground truth
+    def build(self, pruned_degree, l_build, alpha=1.2, batch_size=0):
+        check(_lib.lib().dab_build(self._h, pruned_degree, l_build, alpha, batch_size))
+
+    def flat_knn(self, queries, k):
+        queries = self._queries(queries)
+        ids = np.empty((queries.shape[0], k), np.uint32)
+        dists = np.empty((queries.shape[0], k), np.float32)
+        check(_lib.lib().dab_flat_knn(self._h, _ptr(queries), queries.shape[0], k, _ptr(ids), _ptr(dists)))
+        return ids, dists

@@ -1,0 +1,187 @@
+/*
+ * diskann_b200.h — C ABI of the B200-native distance hot path for microsoft/DiskANN (DiskANN3).
+ *
+ * This is the drop-in boundary: a plain-C shared library
+ * (libdiskann_b200.so, sm_100a CUDA inside) whose entry points are what a Rust `-sys` crate
+ * for this path binds.  Conventions mirror the reference's only FFI precedent,
+ * diskann-garnet/src/lib.rs:262-630: opaque handle, (pointer, length) pairs, integer status,
+ * no unwinding across the boundary, caller owns every host buffer, the library owns device
+ * memory.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference checkout).
+ *
+ * Value conventions are the reference's (diskann-vector/src/distance/distance_provider.rs:
+ * 30-43, implementations.rs:217-404): L2 -> sum (x-y)^2 (no sqrt); InnerProduct -> -sum xy;
+ * Cosine -> 1 - cos (clamped); CosineNormalized -> 1 - sum xy (== Cosine for i8/u8).
+ * Float results are bit-identical to the reference's x86-64-v3 SIMD order; integer and PQ
+ * results are exact.
+ */
+#ifndef DISKANN_B200_H
+#define DISKANN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element types: diskann/src/utils/vector_repr.rs:117-190 (f32, f16, i8, u8) */
+enum { DAB_F32 = 0, DAB_F16 = 1, DAB_I8 = 2, DAB_U8 = 3 };
+
+/* diskann-vector/src/distance/metric.rs:8-20, #[repr(C)] values */
+enum { DAB_COSINE = 0, DAB_INNER_PRODUCT = 1, DAB_L2 = 2, DAB_COSINE_NORMALIZED = 3 };
+
+/* status codes (0 == ok); dab_last_error() has the message (maps to ANNError::message) */
+enum {
+    DAB_OK = 0,
+    DAB_ERR_INVALID_ARGUMENT = 1, /* bad dtype/metric/length: layers/full.rs:203-213, 306-314 */
+    DAB_ERR_CUDA = 2,
+    DAB_ERR_OUT_OF_MEMORY = 3,
+    DAB_ERR_VISITED_OVERFLOW = 4, /* per-query visited set exceeded its capacity (retried internally) */
+    DAB_ERR_NOT_READY = 5,        /* e.g. search before vectors/graph were uploaded */
+    DAB_ERR_NO_DEVICE = 6
+};
+
+typedef struct dab_index dab_index; /* opaque */
+
+/* ------------------------------------------------------------------ lifecycle */
+
+/* Replaces diskann_inmem::Provider::new(layer, config, start_points)
+ * (diskann-inmem/src/provider.rs:71-131) + layers::Full::<T>::new(dim, metric)
+ * (diskann-inmem/src/layers/full.rs:368-504) for the device-resident snapshot:
+ * n_points data rows (ids [0, n_points)) + n_start frozen start rows
+ * (ids [n_points, n_points + n_start)), adjacency rows of max_degree + 1 words. */
+int dab_create(dab_index** out, int dtype, int metric, uint32_t dim, uint64_t n_points,
+               uint32_t n_start, uint32_t max_degree, int device);
+void dab_destroy(dab_index* idx);
+
+/* thread-local message of the last failing call on this thread */
+const char* dab_last_error(void);
+
+/* Launch on the caller's CUDA stream (cudaStream_t passed as void*); NULL restores the
+ * library's own stream. */
+int dab_set_stream(dab_index* idx, void* cuda_stream);
+
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+uint64_t dab_launch_count(void);
+
+/* ------------------------------------------------------------------ data upload */
+
+/* layers::Set<T>::set(element, bytes) (diskann-inmem/src/layers/mod.rs:79-96) /
+ * Provider::set_element (provider.rs:341-372): dense row-major rows of dim elements, no
+ * tags.  `first` may address start rows (first >= n_points).  Host or device source. */
+int dab_upload_vectors(dab_index* idx, const void* rows, uint64_t first, uint64_t count);
+int dab_upload_vectors_device(dab_index* idx, const void* d_rows, uint64_t first, uint64_t count);
+
+/* Neighbors buffer (diskann-inmem/src/neighbors.rs:69-163): row = [len, id_0 .. id_{len-1}],
+ * src_stride words between source rows (>= max_degree + 1). */
+int dab_upload_graph(dab_index* idx, const uint32_t* adj, uint32_t src_stride, uint64_t first,
+                     uint64_t count);
+int dab_upload_graph_device(dab_index* idx, const uint32_t* d_adj, uint32_t src_stride,
+                            uint64_t first, uint64_t count);
+int dab_download_graph(dab_index* idx, uint32_t* adj, uint32_t dst_stride, uint64_t first,
+                       uint64_t count);
+
+/* FixedChunkPQTable::new(dim, pq_table, chunk_offsets)
+ * (diskann-providers/src/model/pq/fixed_chunk_pq_table.rs:104-135) + the compressed
+ * vectors of the quant store: pivots [n_centers][dim] f32, offsets [n_chunks + 1],
+ * codes [(n_points + n_start)][n_chunks] (may be NULL, then call dab_pq_encode_all). */
+int dab_upload_pq(dab_index* idx, const float* pivots, uint32_t n_centers,
+                  const uint64_t* offsets, uint32_t n_chunks, const uint8_t* codes);
+
+/* ------------------------------------------------------------------ (1) per-pair / per-query distances */
+
+/* DistanceProvider::distance_comparer(metric, dim) -> Distance<T,U>::call
+ * (diskann-vector/src/distance/distance_provider.rs:44-46, 86) and
+ * layers::Distance::evaluate(x, y) (diskann-inmem/src/layers/mod.rs:68-77): n independent
+ * pairs x[i] . y[i], host buffers, dense rows.  Supported (dtype_x, dtype_y): (f32,f32)
+ * (f16,f16) (f32,f16) (i8,i8) (u8,u8).  Stateless: no index needed. */
+int dab_pair_distances(int dtype_x, int dtype_y, int metric, uint32_t dim, const void* x,
+                       const void* y, uint64_t n, float* out, int device);
+
+/* SearchAccessor::expand_beam's distance stage batched over queries
+ * (diskann-inmem/src/provider.rs:436-479, 620-690; glue.rs:210-219):
+ * out[q][j] = QueryDistance(query q).evaluate(row ids[q][j]); ids == UINT32_MAX are skipped
+ * (out = NaN).  Queries have the index dtype (f16 queries are widened once,
+ * layers/full.rs:421-423). */
+int dab_distances(dab_index* idx, const void* queries, uint32_t nq, const uint32_t* ids,
+                  uint32_t c, float* out);
+int dab_distances_device(dab_index* idx, const void* d_queries, uint32_t nq,
+                         const uint32_t* d_ids, uint32_t c, float* d_out);
+
+/* PruneAccessor::fill + Distance: DistanceFunction<ElementRef, ElementRef>
+ * (diskann/src/graph/glue.rs:855-906; index.rs:2623-2625): data x data distances.
+ * out[i] = Distance<T,T>(row a[i], row b[i]). */
+int dab_row_pair_distances(dab_index* idx, const uint32_t* a, const uint32_t* b, uint64_t n,
+                           float* out);
+/* candidate x candidate block for robust_prune: out[i][j] = Distance<T,T>(ids[i], ids[j]) */
+int dab_pairwise(dab_index* idx, const uint32_t* ids, uint32_t n, float* out);
+
+/* ------------------------------------------------------------------ (3') batched greedy search */
+
+/* DiskANNIndex::search_internal + Knn::search + post-process for a whole query batch
+ * (diskann/src/graph/index.rs:1933-2000; graph/search/knn_search.rs:170-190;
+ * diskann-inmem/src/provider.rs:907-950), i.e. benchmark_core::search::graph::KNN::search
+ * (diskann-benchmark-core/src/search/graph/knn.rs:208-238) for every query at once.
+ * Results exclude start points; rows are padded with id UINT32_MAX / distance +inf;
+ * out_counts/out_cmps/out_hops may be NULL.  cmps/hops follow SearchStats
+ * (index.rs:1990-1991). */
+int dab_search_batch(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search,
+                     uint32_t beam_width, uint32_t* out_ids, float* out_dists,
+                     uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops);
+int dab_search_batch_device(dab_index* idx, const void* d_queries, uint32_t nq, uint32_t k,
+                            uint32_t l_search, uint32_t beam_width, uint32_t* d_out_ids,
+                            float* d_out_dists, uint32_t* d_out_counts, uint32_t* d_out_cmps,
+                            uint32_t* d_out_hops);
+
+/* ------------------------------------------------------------------ product quantization */
+
+/* FixedChunkPQTable::populate_chunk_distances / populate_chunk_inner_products
+ * (fixed_chunk_pq_table.rs:152-218): lut[q][chunk][center]; metric L2 or InnerProduct. */
+int dab_pq_populate_lut(dab_index* idx, const float* queries, uint32_t nq, int metric, float* out_lut);
+
+/* QueryComputer::evaluate_similarity over gathered codes
+ * (pq/distance/dynamic.rs:63-103; pq_dist_lookup_single, fixed_chunk_pq_table.rs:82-98;
+ * compute_pq_distance :617-670): out[q][j] for ids[q][j].  Queries are f32. */
+int dab_pq_distances(dab_index* idx, const float* queries, uint32_t nq, const uint32_t* ids,
+                     uint32_t c, float* out);
+
+/* BasicTable::compress_into (diskann-quantization/src/product/tables/basic.rs:161-194) for n
+ * host vectors (f32): codes [n][n_chunks].  Returns DAB_ERR_INVALID_ARGUMENT if a chunk's
+ * minimum distance is infinite/NaN (first offending row/chunk in the message). */
+int dab_pq_encode(dab_index* idx, const float* vectors, uint64_t n, uint8_t* out_codes);
+
+/* ------------------------------------------------------------------ scalar quantization */
+
+/* ScalarQuantizer::compress_into (diskann-quantization/src/scalar/quantizer.rs:190-239,
+ * 407-430): codes one per byte in [0, 2^nbits), compensation per vector. */
+int dab_sq_compress(int device, const float* shift, float scale, uint32_t dim, int nbits,
+                    const float* vectors, uint64_t n, uint8_t* out_codes, float* out_comp);
+
+/* CompensatedSquaredL2 / CompensatedIP / CompensatedCosineNormalized
+ * (scalar/vectors.rs:206-237, 310-376, 380-460) for n code pairs. */
+int dab_sq_distances(int device, int metric, int nbits, float scale_squared, float shift_square_norm,
+                     uint32_t dim, const uint8_t* x, const float* comp_x, const uint8_t* y,
+                     const float* comp_y, uint64_t n, float* out);
+
+/* ------------------------------------------------------------------ build-side reuse */
+
+/* Batched Vamana construction on the device (the rows SURVEY.md §8f.2 marks "next"):
+ * DiskANNIndex::multi_insert semantics (diskann/src/graph/index.rs:815) — batches of inserts
+ * searched with the same search kernel, pruned with robust_prune
+ * (graph/internal/prune.rs:106-259) and back-edges merged per destination.  Uses the
+ * uploaded vectors (including start rows) and overwrites the adjacency. */
+int dab_build(dab_index* idx, uint32_t pruned_degree, uint32_t l_build, float alpha,
+              uint32_t batch_size);
+
+/* exact k-NN by exhaustive scan (diskann/src/flat; ground truth for recall):
+ * out_ids [nq][k] ascending distance, ties by lower id. */
+int dab_flat_knn(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t* out_ids,
+                 float* out_dists);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,357 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle on the same seeded
+inputs.  Bar: bit-exact for every path (integer, PQ, and — because the kernels reproduce the
+reference's SIMD summation order — floating point too)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+METRICS = [O.L2, O.INNER_PRODUCT, O.COSINE, O.COSINE_NORMALIZED]
+PAIRS = [(np.float32, np.float32), (np.float16, np.float16), (np.float32, np.float16),
+         (np.int8, np.int8), (np.uint8, np.uint8)]
+
+
+@pytest.fixture(scope="module")
+def dab():
+    import diskann_b200
+    diskann_b200.lib()
+    return diskann_b200
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def same_bits(a, b):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return np.array_equal(bits(a)[~(np.isnan(a) & np.isnan(b))], bits(b)[~(np.isnan(a) & np.isnan(b))]) and \
+        np.array_equal(np.isnan(a), np.isnan(b))
+
+
+def fuzz(rng, dt, shape):
+    if dt in (np.float32, np.float16):
+        return rng.normal(0.0, 1.0, shape).astype(dt)
+    info = np.iinfo(dt)
+    return rng.integers(info.min, info.max + 1, shape).astype(dt)
+
+
+def corner(dt):
+    if dt in (np.float32, np.float16):
+        return [0.0, -5.0, 5.0, 10.0]
+    return [-128, 127, 0] if dt == np.int8 else [0, 255, 0]
+
+
+def clustered(rng, n, d, n_centers=32, spread=0.3):
+    centers = rng.normal(size=(n_centers, d)).astype(np.float32)
+    return (centers[rng.integers(0, n_centers, n)] + spread * rng.normal(size=(n, d))).astype(np.float32)
+
+
+# ---------------------------------------------------------------- per-pair distances
+
+def test_kat_l2_through_the_c_abi(dab):
+    g = json.load(open(os.path.join(GOLDEN, "kat_l2_f32_256.json")))
+    v = np.array(g["values"], np.float32)
+    out = dab.pair_distances(v[None, :256], v[None, 256:], dab.Metric.L2)
+    assert out[0] == np.float32(g["expected"])  # 429141.2 exactly, distance_provider.rs:744-828
+    f = dab.distance_comparer(dab.Metric.L2, 256)
+    assert f(v[:256], v[256:]) == np.float32(g["expected"])
+
+
+@pytest.mark.parametrize("dl,dr", PAIRS)
+def test_pair_distances_bit_exact_all_dims(dab, dl, dr):
+    """The reference's sweep (distance_provider.rs:551-606): every dim 0..64 + the specialised
+    and ragged sizes, corner broadcasts + fuzz, 4 metrics."""
+    rng = np.random.default_rng(1234)
+    for dim in list(range(1, 66)) + [95, 96, 97, 100, 127, 128, 129, 160, 255, 256, 384, 768, 1000]:
+        xs = [np.full(dim, a, dl) for a in corner(dl) for _ in corner(dr)]
+        ys = [np.full(dim, b, dr) for _ in corner(dl) for b in corner(dr)]
+        xs += [fuzz(rng, dl, dim) for _ in range(7)]
+        ys += [fuzz(rng, dr, dim) for _ in range(7)]
+        x, y = np.stack(xs), np.stack(ys)
+        for metric in METRICS:
+            got = dab.pair_distances(x, y, metric)
+            want = np.array([O.distance(a, b, metric, O.SIMD) for a, b in zip(x, y)], np.float32)
+            assert same_bits(got, want), (dim, metric, got, want)
+
+
+def test_pair_distances_special_values(dab):
+    a = np.full((1, 384), np.inf, np.float16)
+    assert math.isnan(dab.pair_distances(a, a, dab.Metric.L2)[0])  # distance_provider.rs:970-977
+    z = np.zeros((1, 37), np.float32)
+    o = np.ones((1, 37), np.float32)
+    assert dab.pair_distances(z, o, dab.Metric.Cosine)[0] == np.float32(1.0)  # zero norm -> similarity 0
+    # i32 accumulators hold the extreme broadcasts exactly
+    x = np.full((1, 256), -128, np.int8)
+    y = np.full((1, 256), 127, np.int8)
+    assert dab.pair_distances(x, y, dab.Metric.L2)[0] == np.float32(255 * 255 * 256)
+    u = np.full((1, 256), 255, np.uint8)
+    assert dab.pair_distances(u, u, dab.Metric.InnerProduct)[0] == np.float32(-255 * 255 * 256)
+
+
+def test_error_behaviour_matches_the_layer(dab):
+    # layers/full.rs:203-213, 306-314: length / type mismatch is an error, never a crash
+    with pytest.raises(dab.DabError):
+        dab.pair_distances(np.zeros((2, 4), np.float32), np.zeros((2, 5), np.float32), dab.Metric.L2)
+    with pytest.raises(dab.DabError):
+        dab.pair_distances(np.zeros((2, 4), np.int8), np.zeros((2, 4), np.uint8), dab.Metric.L2)
+    with pytest.raises(dab.DabError):
+        dab.pair_distances(np.zeros((2, 4), np.float64), np.zeros((2, 4), np.float64), dab.Metric.L2)
+    assert dab.pair_distances(np.zeros((0, 4), np.float32), np.zeros((0, 4), np.float32), dab.Metric.L2).shape == (0,)
+    with dab.GpuIndex(dab.DType.f32, dab.Metric.L2, 8, 10, 1, 4) as g:
+        with pytest.raises(dab.DabError):
+            g.upload_vectors(np.zeros((3, 7), np.float32))
+        with pytest.raises(dab.DabError):
+            g.upload_vectors(np.zeros((12, 8), np.float32))  # more rows than the index holds
+        with pytest.raises(dab.DabError) as e:
+            g.search_batch(np.zeros((1, 8), np.float32), 1, 4)
+        assert e.value.code == 5  # DAB_ERR_NOT_READY
+        bad = np.zeros((11, 5), np.uint32)
+        bad[0, 0] = 9  # degree > max_degree
+        with pytest.raises(dab.DabError):
+            g.upload_graph(bad)
+
+
+# ---------------------------------------------------------------- frontier distances (K1/K5 + K10)
+
+@pytest.mark.parametrize("dt,metric,dim", [
+    (np.float32, O.L2, 128), (np.float32, O.L2, 100), (np.float32, O.L2, 96), (np.float32, O.COSINE, 37),
+    (np.float16, O.INNER_PRODUCT, 768), (np.float16, O.L2, 100), (np.float16, O.COSINE_NORMALIZED, 64),
+    (np.int8, O.L2, 128), (np.int8, O.INNER_PRODUCT, 100), (np.uint8, O.L2, 128), (np.uint8, O.COSINE, 33),
+])
+def test_frontier_distances_bit_exact(dab, dt, metric, dim):
+    rng = np.random.default_rng(dim * 7 + metric)
+    n, nq, c = 3000, 40, 83
+    base = fuzz(rng, dt, (n + 1, dim))
+    queries = fuzz(rng, dt, (nq, dim))
+    ids = rng.integers(0, n + 1, (nq, c)).astype(np.uint32)
+    ids[0, 3] = 0xFFFFFFFF          # skipped slot
+    ids[1, :] = 0xFFFFFFFF          # empty (ragged) list
+    ids[2, 5] = n + 5               # out of bounds
+    with dab.GpuIndex(O.dtype_code(base), metric, dim, n, 1, 8) as g:
+        g.upload_vectors(base)
+        got = g.distances(queries, ids)
+        pa = rng.integers(0, n, 500).astype(np.uint32)
+        pb = rng.integers(0, n, 500).astype(np.uint32)
+        got_pairs = g.row_pair_distances(pa, pb)
+        sub = rng.integers(0, n, 17).astype(np.uint32)
+        got_block = g.pairwise(sub)
+    for qi in range(nq):
+        q = queries[qi].astype(np.float32) if dt == np.float16 else queries[qi]  # layers/full.rs:421-423
+        valid = ids[qi] <= n
+        want = O.distance_rows(q, base[np.where(valid, ids[qi], 0)], metric)
+        assert same_bits(got[qi][valid], want[valid]), (qi,)
+        assert np.isnan(got[qi][~valid]).all()
+    want_pairs = np.array([O.distance(base[a], base[b], metric) for a, b in zip(pa, pb)], np.float32)
+    assert same_bits(got_pairs, want_pairs)
+    want_block = np.array([[O.distance(base[a], base[b], metric) for b in sub] for a in sub], np.float32)
+    assert same_bits(got_block, want_block)
+
+
+# ---------------------------------------------------------------- greedy search
+
+def test_grid_search_baselines_on_gpu(dab):
+    """The reference's checked-in greedy-search baselines
+    (diskann/test/generated/graph/test/cases/grid_search/*.json) through dab_search_batch."""
+    from test_oracle_golden import grid
+    g = json.load(open(os.path.join(GOLDEN, "grid_search.json")))
+    for case in g["cases"]:
+        data, adj, n = grid(case["grid_dims"], case["grid_size"])
+        with dab.GpuIndex(dab.DType.f32, dab.Metric.L2, data.shape[1], n, 1, adj.shape[1] - 1) as gi:
+            gi.upload_vectors(data)
+            gi.upload_graph(adj)
+            ids, dists, counts, cmps, hops = gi.search_batch(np.array([case["query"]], np.float32), 10, 10,
+                                                             case["beam_width"])
+        assert counts[0] == case["num_results"] and cmps[0] == case["comparisons"] and hops[0] == case["hops"], case
+        want = case["results"][:case["num_results"]]
+        assert [int(i) for i in ids[0][:counts[0]]] == [r[0] for r in want], case
+        assert [float(d) for d in dists[0][:counts[0]]] == [r[1] for r in want], case
+
+
+def make_index(rng, dt, metric, n, d, R, L_build):
+    base = clustered(rng, n, d)
+    if dt == np.float16:
+        base = (base / np.linalg.norm(base, axis=1, keepdims=True)).astype(np.float16)
+    elif dt == np.int8:
+        base = np.clip(np.round(base * 40), -127, 127).astype(np.int8)
+    elif dt == np.uint8:
+        base = np.clip(np.round(base * 40 + 128), 0, 255).astype(np.uint8)
+    mean = base.astype(np.float32).mean(0)
+    medoid = base[np.argmin(((base.astype(np.float32) - mean) ** 2).sum(1))]
+    vecs = np.concatenate([base, medoid[None]])
+    maxdeg = int(R * 1.3)
+    adj = O.build_graph(vecs, n, 1, metric, R, maxdeg, L_build)
+    return vecs, adj, maxdeg
+
+
+SEARCH_CASES = [
+    (np.float32, O.L2, 128, 6000, 32, 50),
+    (np.float32, O.L2, 100, 3000, 16, 30),
+    (np.float32, O.COSINE, 48, 3000, 16, 30),
+    (np.float16, O.INNER_PRODUCT, 96, 3000, 16, 30),
+    (np.float16, O.L2, 64, 3000, 16, 30),
+    (np.int8, O.L2, 128, 4000, 24, 40),
+    (np.uint8, O.L2, 128, 3000, 16, 30),
+    (np.uint8, O.COSINE, 40, 2000, 16, 30),
+]
+
+
+@pytest.mark.parametrize("dt,metric,d,n,R,Lb", SEARCH_CASES)
+def test_search_batch_identical_to_oracle(dab, dt, metric, d, n, R, Lb):
+    """Same graph, same queries: ids, distances (bitwise), result counts, cmps and hops are all
+    identical to the oracle's search_internal for several (L, beam, k)."""
+    rng = np.random.default_rng(d * 31 + n)
+    vecs, adj, maxdeg = make_index(rng, dt, metric, n, d, R, Lb)
+    nq = 300
+    queries = vecs[rng.integers(0, n, nq)].astype(np.float32) + 0.1 * rng.normal(size=(nq, d)).astype(np.float32)
+    if dt in (np.int8, np.uint8):
+        info = np.iinfo(dt)
+        queries = np.clip(np.round(queries), info.min, info.max)
+    queries = queries.astype(dt)
+    oidx = O.Index(vecs, adj, n, 1, metric)
+    with dab.GpuIndex(O.dtype_code(vecs), metric, d, n, 1, maxdeg) as g:
+        g.upload_vectors(vecs)
+        g.upload_graph(adj)
+        assert np.array_equal(g.download_graph()[:, :adj.shape[1]], adj)
+        for (k, L, beam) in [(10, 10, 1), (10, 40, 1), (5, 100, 1), (10, 32, 2), (20, 33, 4), (1, 1, 1), (64, 20, 1)]:
+            got = g.search_batch(queries, k, L, beam)
+            want = oidx.search_batch(queries, k, L, beam=beam, threads=4)
+            for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, k, L, beam)
+
+
+def test_search_edge_cases(dab):
+    rng = np.random.default_rng(99)
+    n, d = 500, 16
+    vecs, adj, maxdeg = make_index(rng, np.float32, O.L2, n, d, 8, 20)
+    oidx = O.Index(vecs, adj, n, 1, O.L2)
+    with dab.GpuIndex(dab.DType.f32, dab.Metric.L2, d, n, 1, maxdeg) as g:
+        g.upload_vectors(vecs)
+        g.upload_graph(adj)
+        # empty batch
+        ids, dists, counts, cmps, hops = g.search_batch(np.zeros((0, d), np.float32), 10, 10)
+        assert ids.shape == (0, 10)
+        # k larger than anything reachable with L: padded with UINT32_MAX / +inf
+        q = vecs[:7]
+        got = g.search_batch(q, 50, 5)
+        want = oidx.search_batch(q, 50, 5)
+        assert np.array_equal(got[0], want[0]) and (got[2] <= 5).all()
+        assert (got[0][:, 5:] == 0xFFFFFFFF).all() and np.isinf(got[1][:, 5:]).all()
+        # a query with NaNs: every insert is ignored except ... all distances NaN -> no results
+        qn = np.full((1, d), np.nan, np.float32)
+        got = g.search_batch(qn, 10, 10)
+        want = oidx.search_batch(qn, 10, 10)
+        assert np.array_equal(got[0], want[0]) and got[2][0] == want[2][0] == 0
+        with pytest.raises(dab.DabError):
+            g.search_batch(q, 0, 10)
+        with pytest.raises(dab.DabError):
+            g.search_batch(q.astype(np.float16), 10, 10)
+
+
+def test_visited_table_overflow_is_retried_exactly(dab, monkeypatch):
+    """Force a tiny visited table: overflowing queries are re-run with a larger table and the
+    results stay identical to the oracle."""
+    rng = np.random.default_rng(5)
+    n, d = 5000, 32
+    vecs, adj, maxdeg = make_index(rng, np.float32, O.L2, n, d, 24, 40)
+    queries = clustered(rng, 200, d)
+    oidx = O.Index(vecs, adj, n, 1, O.L2)
+    want = oidx.search_batch(queries, 10, 60, threads=4)
+    monkeypatch.setenv("DAB_TEST_VISITED_LOG2", "10")
+    with dab.GpuIndex(dab.DType.f32, dab.Metric.L2, d, n, 1, maxdeg) as g:
+        g.upload_vectors(vecs)
+        g.upload_graph(adj)
+        got = g.search_batch(queries, 10, 60)
+    assert (want[3] > 768).any(), "the case must actually overflow a 1024-slot table"
+    for a, b in zip(got, want):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+# ---------------------------------------------------------------- product quantization
+
+def trained_pq(rng, base, chunks, centers=256):
+    """A quick k-means-free codebook: sampled rows as pivots (codebook quality is irrelevant
+    for arithmetic parity)."""
+    piv = base[rng.choice(base.shape[0], centers, replace=False)].astype(np.float32)
+    off = O.pq_offsets(base.shape[1], chunks)
+    return piv, off
+
+
+@pytest.mark.parametrize("metric,dim,chunks", [(O.L2, 128, 32), (O.INNER_PRODUCT, 128, 32), (O.COSINE_NORMALIZED, 96, 12),
+                                               (O.COSINE, 64, 8), (O.L2, 100, 7), (O.L2, 17, 17)])
+def test_pq_lut_adc_encode_bit_exact(dab, metric, dim, chunks):
+    rng = np.random.default_rng(dim + chunks)
+    n, nq, c = 2000, 16, 200
+    base = clustered(rng, n + 1, dim)
+    piv, off = trained_pq(rng, base, chunks)
+    L = O.lib()
+    with dab.GpuIndex(dab.DType.f32, metric, dim, n, 1, 8) as g:
+        g.upload_vectors(base)
+        g.upload_pq(piv, off)
+        codes = g.pq_encode(base)
+        want_codes = np.zeros_like(codes)
+        for i in range(n + 1):
+            assert L.orc_pq_encode(O.ptr(piv), 256, dim, O.ptr(off), chunks, O.ptr(base[i]), O.ptr(want_codes[i])) == 0
+        assert np.array_equal(codes, want_codes)
+        g.upload_pq(piv, off, codes)
+        queries = clustered(rng, nq, dim)
+        ids = rng.integers(0, n + 1, (nq, c)).astype(np.uint32)
+        ids[0, 0] = 0xFFFFFFFF
+        got = g.pq_distances(queries, ids)
+        if metric != O.COSINE:
+            lut = g.pq_populate_lut(queries)
+            want_lut = np.zeros((chunks, 256), np.float32)
+            for qi in range(nq):
+                L.orc_pq_populate_lut(O.ptr(piv), 256, dim, O.ptr(off), chunks,
+                                      O.INNER_PRODUCT if metric == O.INNER_PRODUCT else O.L2, O.ptr(queries[qi]), O.ptr(want_lut))
+                assert np.array_equal(bits(lut[qi]), bits(want_lut)), qi
+        for qi in range(nq):
+            valid = ids[qi] != 0xFFFFFFFF
+            sel = np.ascontiguousarray(codes[np.where(valid, ids[qi], 0)])
+            want = np.zeros(c, np.float32)
+            L.orc_pq_query_distances(O.ptr(piv), 256, dim, O.ptr(off), chunks, metric, O.ptr(queries[qi]), O.ptr(sel), c, O.ptr(want))
+            assert same_bits(got[qi][valid], want[valid]), qi
+            assert np.isnan(got[qi][~valid]).all()
+        # inf input -> error naming the row/chunk (basic.rs:187-189)
+        bad = base[:3].copy()
+        bad[1, 0] = np.inf
+        with pytest.raises(dab.DabError):
+            g.pq_encode(bad)
+
+
+# ---------------------------------------------------------------- scalar quantization
+
+@pytest.mark.parametrize("nbits", [8, 4, 2, 1])
+def test_sq_compress_and_distances_bit_exact(dab, nbits):
+    import ctypes as C
+    from diskann_b200 import _lib
+    rng = np.random.default_rng(nbits)
+    n, dim = 300, 100
+    vecs = clustered(rng, 2 * n, dim)
+    vecs[5, 7] = np.nan
+    shift = vecs[np.isfinite(vecs).all(1)].mean(0).astype(np.float32)
+    scale = np.float32(4.2)
+    codes = np.zeros((2 * n, dim), np.uint8)
+    comp = np.zeros(2 * n, np.float32)
+    _lib.check(_lib.lib().dab_sq_compress(0, O.ptr(shift), scale, dim, nbits, O.ptr(vecs), 2 * n, O.ptr(codes), O.ptr(comp)))
+    L = O.lib()
+    for i in range(2 * n):
+        wc = np.zeros(dim, np.uint8)
+        w = L.orc_sq_compress(O.ptr(shift), scale, dim, nbits, O.ptr(vecs[i]), O.ptr(wc), None)
+        assert np.array_equal(wc, codes[i]) and same_bits([w], [comp[i]]), i
+    ss = float(np.float32(scale) * np.float32(scale))
+    ssn = float(np.float32((shift.astype(np.float64) ** 2).sum()))
+    for metric in (O.L2, O.INNER_PRODUCT, O.COSINE_NORMALIZED):
+        out = np.zeros(n, np.float32)
+        x, y = np.ascontiguousarray(codes[:n]), np.ascontiguousarray(codes[n:])
+        cx, cy = np.ascontiguousarray(comp[:n]), np.ascontiguousarray(comp[n:])
+        _lib.check(_lib.lib().dab_sq_distances(0, metric, nbits, ss, ssn, dim, O.ptr(x), O.ptr(cx), O.ptr(y), O.ptr(cy), n, O.ptr(out)))
+        want = np.array([L.orc_sq_distance(metric, nbits, ss, ssn, O.ptr(x[i]), float(cx[i]), O.ptr(y[i]), float(cy[i]), dim)
+                         for i in range(n)], np.float32)
+        assert same_bits(out, want), metric
