@@ -228,6 +228,21 @@ class GpuIndex:
         return out
 
     # -- build-side reuse / ground truth
+    def robust_prune(self, pool_ids, pool_dists, pool_lens, locations, degree, alpha=1.2):
+        """robust_prune for a batch of pools -> (ids [n_pools, degree] padded UINT32_MAX, counts)."""
+        pool_ids = np.ascontiguousarray(pool_ids, np.uint32)
+        pool_dists = np.ascontiguousarray(pool_dists, np.float32)
+        pool_lens = np.ascontiguousarray(pool_lens, np.uint32)
+        locations = np.ascontiguousarray(locations, np.uint32)
+        if pool_ids.ndim != 2 or pool_ids.shape != pool_dists.shape or pool_lens.shape != (pool_ids.shape[0],) \
+                or locations.shape != pool_lens.shape:
+            raise DabError(1, "robust_prune: expected pool_ids/pool_dists [n_pools, cap], pool_lens/locations [n_pools]")
+        out = np.empty((pool_ids.shape[0], degree), np.uint32)
+        counts = np.empty(pool_ids.shape[0], np.uint32)
+        check(_lib.lib().dab_robust_prune(self._h, _ptr(pool_ids), _ptr(pool_dists), _ptr(pool_lens), _ptr(locations),
+                                          pool_ids.shape[0], pool_ids.shape[1], degree, alpha, _ptr(out), _ptr(counts)))
+        return out, counts
+
     def build(self, pruned_degree, l_build, alpha=1.2, batch_size=0):
         check(_lib.lib().dab_build(self._h, pruned_degree, l_build, alpha, batch_size))
 

@@ -168,6 +168,18 @@ int dab_sq_distances(int device, int metric, int nbits, float scale_squared, flo
 
 /* ------------------------------------------------------------------ build-side reuse */
 
+/* PruneAccessor::fill + robust_prune (diskann/src/graph/index.rs:2349-2380, 2565-2650;
+ * graph/internal/prune.rs:106-259; PruneKind graph/config/mod.rs:80-103) for n_pools
+ * independent candidate pools: pool p has pool_lens[p] (id, source distance) entries in
+ * pool_ids/pool_dists[p * pool_cap ...] (any order; sorted by distance then arrival order and
+ * truncated to max_occlusion_size = 750 like SortedNeighbors::new), locations[p] is the node
+ * being pruned (excluded from its own pool).  Candidate x candidate distances are
+ * Distance<T,T> over the uploaded rows.  out_ids [n_pools][degree] (padded UINT32_MAX). */
+int dab_robust_prune(dab_index* idx, const uint32_t* pool_ids, const float* pool_dists,
+                     const uint32_t* pool_lens, const uint32_t* locations, uint32_t n_pools,
+                     uint32_t pool_cap, uint32_t degree, float alpha, uint32_t* out_ids,
+                     uint32_t* out_counts);
+
 /* Batched Vamana construction on the device (the rows SURVEY.md §8f.2 marks "next"):
  * DiskANNIndex::multi_insert semantics (diskann/src/graph/index.rs:815) — batches of inserts
  * searched with the same search kernel, pruned with robust_prune
