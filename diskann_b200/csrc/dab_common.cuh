@@ -83,5 +83,11 @@ struct dab_index {
     dab::Scratch s_queries, s_ids, s_out, s_out2, s_tables, s_counters, s_stats;
     dab::Scratch h_stage;  // pinned host staging
 
+    // search-side state learned across calls
+    uint32_t hint_l = 0, hint_beam = 0, hint_visited = 0;  // largest visited set seen at (L, beam)
+    void* l2_window_ptr = nullptr;       // current persisting-L2 window (visited tables)
+    size_t l2_window_bytes = 0;
+    cudaStream_t l2_window_stream = nullptr;
+
     uint64_t n_total() const { return n_points + n_start; }
 };

@@ -54,7 +54,7 @@ struct SearchParams {
     uint32_t* out_hops;
     uint32_t* tables;
     uint32_t hcap_log2;
-    uint32_t* counters;           // [0] work counter, [1] overflow count
+    uint32_t* counters;           // [0] work counter, [1] overflow count, [2] max visited
     uint32_t* overflow_list;      // query indices whose visited table overflowed
     // optional record of expanded nodes (VisitedSearchRecord, used by the device build)
     uint32_t* rec_ids;
@@ -74,7 +74,10 @@ __device__ __forceinline__ bool visited_insert(uint32_t* table, uint32_t log2cap
     const uint32_t mask = (1u << log2cap) - 1u;
     uint32_t h = hash_id(id, log2cap);
     for (;;) {
-        uint32_t old = atomicCAS(table + h, kEmpty, id);
+        // plain L2 read first (L1 bypassed: the table is updated by L2 atomics): most probes hit
+        // an id that is already present and must not dirty the sector
+        uint32_t old = __ldcg(table + h);
+        if (old == kEmpty) old = atomicCAS(table + h, kEmpty, id);
         if (old == kEmpty) return true;
         if (old == id) return false;
         h = (h + 1) & mask;
@@ -319,6 +322,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) search_kernel(const SearchP
                 p.out_dists[(size_t)qidx * p.k + i] = __int_as_float(0x7F800000);
             }
             if (lane == 0) {
+                atomicMax(p.counters + 2, nvisited);
                 if (p.out_counts) p.out_counts[qidx] = count;
                 if (p.out_cmps) p.out_cmps[qidx] = cmps;
                 if (p.out_hops) p.out_hops[qidx] = hops;
@@ -330,10 +334,74 @@ __global__ void __launch_bounds__(kSearchWarps * 32) search_kernel(const SearchP
 
 // ------------------------------------------------------------------ host side
 
+// search_kernel_v2.cu
+struct SearchParamsV2 {
+    const uint8_t* vectors;
+    size_t row_stride;
+    const uint32_t* adj;
+    uint32_t adj_stride;
+    uint64_t n_points;
+    uint32_t n_start;
+    uint32_t dim;
+    uint32_t max_degree;
+    const void* queries;
+    const uint32_t* query_rows;
+    const uint32_t* query_list;
+    uint32_t n_work;
+    uint32_t k, cap, beam;
+    uint32_t* out_ids;
+    float* out_dists;
+    uint32_t* out_counts;
+    uint32_t* out_cmps;
+    uint32_t* out_hops;
+    uint32_t* tables;
+    uint32_t hcap_log2;
+    uint32_t* counters;
+    uint32_t* overflow_list;
+    uint32_t* rec_ids;
+    float* rec_dists;
+    uint32_t* rec_counts;
+    uint32_t rec_cap;
+    uint32_t warp_smem, off_q, off_cid, off_cd, off_beam, off_rows, off_bar;
+    uint32_t row_bytes, row_slot, stage_rows;
+};
+struct V2Launch {
+    void (*kern)(const SearchParamsV2);
+    size_t smem_block;
+    int grid;
+};
+int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchParamsV2& p, V2Launch& out);
+constexpr int kV2WarpsHost = 4;
+
 static uint32_t next_pow2_log2(uint64_t v) {
     uint32_t l = 0;
     while ((1ull << l) < v) ++l;
     return l;
+}
+
+// Keep the visited tables L2-resident: they are hit ~max_degree times per hop with random
+// 4-byte probes, while vector rows stream through.  cudaAccessPolicyWindow on the stream.
+static void pin_tables_in_l2(dab_index* idx, size_t bytes) {
+    if (idx->l2_window_ptr == idx->s_tables.p && idx->l2_window_bytes == bytes && idx->l2_window_stream == idx->stream) return;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, idx->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, idx->device);
+    if (max_persist <= 0 || max_window <= 0) return;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = idx->s_tables.p;
+    attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)max_window);
+    attr.accessPolicyWindow.hitRatio = bytes <= (size_t)max_persist ? 1.0f : (float)((double)max_persist / (double)bytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(idx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    idx->l2_window_ptr = idx->s_tables.p;
+    idx->l2_window_bytes = bytes;
+    idx->l2_window_stream = idx->stream;
 }
 
 template <typename K>
@@ -436,14 +504,53 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
 #undef PICK_INT
     if (rc) return rc;
 
+    // the latency-restructured kernel covers float rows with NA = 4 schemas; everything else
+    // runs the generic kernel above
+    SearchParamsV2 p2;
+    memset(&p2, 0, sizeof(p2));
+    V2Launch v2;
+    const bool use_v2 = v2_prepare(idx, l_search, beam, p2, v2) == 0;
+    if (use_v2) {
+        p2.vectors = p.vectors;
+        p2.row_stride = p.row_stride;
+        p2.adj = p.adj;
+        p2.adj_stride = p.adj_stride;
+        p2.n_points = p.n_points;
+        p2.n_start = p.n_start;
+        p2.dim = p.dim;
+        p2.max_degree = p.max_degree;
+        p2.queries = p.queries;
+        p2.query_rows = p.query_rows;
+        p2.k = p.k;
+        p2.cap = p.cap;
+        p2.beam = p.beam;
+        p2.out_ids = p.out_ids;
+        p2.out_dists = p.out_dists;
+        p2.out_counts = p.out_counts;
+        p2.out_cmps = p.out_cmps;
+        p2.out_hops = p.out_hops;
+        p2.rec_ids = p.rec_ids;
+        p2.rec_dists = p.rec_dists;
+        p2.rec_counts = p.rec_counts;
+        p2.rec_cap = p.rec_cap;
+        grid = v2.grid;
+    }
+
     // visited-table capacity: the reference's estimate (scratch.rs:186-192:
     // 1.1 * max_degree * 1.3 * L), never more than the index, at least 1024 slots
     double est = 1.1 * idx->max_degree * 1.3 * (double)l_search;
+    if (idx->hint_visited > 0 && l_search <= idx->hint_l && beam <= idx->hint_beam) {
+        // later batches: 1.5x the largest visited set seen at this (or a larger) L, at 75 % load
+        // (visited sets grow monotonically with L); queries that still overflow are re-run
+        // below with a larger table
+        const double seen = (double)idx->hint_visited * 1.5 / 0.75 + 64.0;
+        if (seen < est) est = seen;
+    }
     if (est > (double)idx->n_total() * 1.34) est = (double)idx->n_total() * 1.34;
     uint32_t hlog = std::max<uint32_t>(10, next_pow2_log2((uint64_t)est + 1));
     if (const char* t = getenv("DAB_TEST_VISITED_LOG2")) {  // tests force the overflow/retry path
         int v = atoi(t);
-        if (v >= 10 && v <= 30) hlog = (uint32_t)v;
+        if (v >= 8 && v <= 30) hlog = (uint32_t)v;
     }
 
     if ((rc = idx->s_counters.reserve(16 + (size_t)nq * 4))) return rc;
@@ -453,6 +560,8 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
     p.overflow_list = d_overflow;
     p.n_work = nq;
     p.query_list = nullptr;
+    p2.counters = d_counters;
+    p2.overflow_list = d_overflow;
     Scratch retry_list;  // holds the overflow list of the previous pass
 
     for (int pass = 0; pass < 6; ++pass) {
@@ -463,15 +572,32 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
         }
         p.tables = (uint32_t*)idx->s_tables.p;
         p.hcap_log2 = hlog;
+        pin_tables_in_l2(idx, ((size_t)warps << hlog) * 4);
         DAB_CUDA(cudaMemsetAsync(d_counters, 0, 16, idx->stream));
         int launch_grid = (int)std::min<uint64_t>((uint64_t)grid, ((uint64_t)p.n_work + kSearchWarps - 1) / kSearchWarps);
-        kern<<<launch_grid, kSearchWarps * 32, smem_block, idx->stream>>>(p);
+        if (use_v2) {
+            p2.tables = p.tables;
+            p2.hcap_log2 = hlog;
+            p2.query_list = p.query_list;
+            p2.n_work = p.n_work;
+            v2.kern<<<launch_grid, kV2WarpsHost * 32, v2.smem_block, idx->stream>>>(p2);
+        } else {
+            kern<<<launch_grid, kSearchWarps * 32, smem_block, idx->stream>>>(p);
+        }
         DAB_LAUNCHED();
         DAB_CUDA(cudaGetLastError());
-        uint32_t h_counters[2] = {0, 0};
-        DAB_CUDA(cudaMemcpyAsync(h_counters, d_counters, 8, cudaMemcpyDeviceToHost, idx->stream));
+        uint32_t h_counters[3] = {0, 0, 0};
+        DAB_CUDA(cudaMemcpyAsync(h_counters, d_counters, 12, cudaMemcpyDeviceToHost, idx->stream));
         DAB_CUDA(cudaStreamSynchronize(idx->stream));
         const uint32_t n_over = h_counters[1];
+        if (!rec_ids) {  // build-time searches run on a growing graph: do not learn from them
+            if (l_search != idx->hint_l || beam != idx->hint_beam) {
+                idx->hint_l = l_search;
+                idx->hint_beam = beam;
+                idx->hint_visited = 0;
+            }
+            idx->hint_visited = std::max(idx->hint_visited, h_counters[2]);
+        }
         if (n_over == 0) {
             retry_list.release();
             return DAB_OK;

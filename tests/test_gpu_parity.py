@@ -263,12 +263,12 @@ def test_visited_table_overflow_is_retried_exactly(dab, monkeypatch):
     queries = clustered(rng, 200, d)
     oidx = O.Index(vecs, adj, n, 1, O.L2)
     want = oidx.search_batch(queries, 10, 60, threads=4)
-    monkeypatch.setenv("DAB_TEST_VISITED_LOG2", "10")
+    monkeypatch.setenv("DAB_TEST_VISITED_LOG2", "8")
     with dab.GpuIndex(dab.DType.f32, dab.Metric.L2, d, n, 1, maxdeg) as g:
         g.upload_vectors(vecs)
         g.upload_graph(adj)
         got = g.search_batch(queries, 10, 60)
-    assert (want[3] > 768).any(), "the case must actually overflow a 1024-slot table"
+    assert (want[3] > 192).all(), "every query must actually overflow a 256-slot table (75 % load limit)"
     for a, b in zip(got, want):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
