@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdiskann_b200.so")
+LIB_PATH = os.environ.get("DAB_LIB_PATH") or os.path.join(_HERE, "libdiskann_b200.so")  # override: tuning builds
 
 # every symbol include/diskann_b200.h declares: name -> (restype, argtypes)
 _vp, _u32, _u64, _i, _f = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_float

@@ -355,15 +355,16 @@ struct SearchParamsV2 {
     uint32_t* out_cmps;
     uint32_t* out_hops;
     uint32_t* tables;
-    uint32_t hcap_log2;
+    uint32_t n_buckets;
     uint32_t* counters;
     uint32_t* overflow_list;
     uint32_t* rec_ids;
     float* rec_dists;
     uint32_t* rec_counts;
     uint32_t rec_cap;
-    uint32_t warp_smem, off_q, off_cid, off_cd, off_beam, off_rows, off_bar;
+    uint32_t warp_smem, off_q, off_qd, off_qi, off_cid, off_cd, off_beam, off_rows;
     uint32_t row_bytes, row_slot, stage_rows;
+    unsigned long long* phase_cycles;
 };
 struct V2Launch {
     void (*kern)(const SearchParamsV2);
@@ -543,14 +544,16 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
         // later batches: 1.5x the largest visited set seen at this (or a larger) L, at 75 % load
         // (visited sets grow monotonically with L); queries that still overflow are re-run
         // below with a larger table
-        const double seen = (double)idx->hint_visited * 1.5 / 0.75 + 64.0;
+        const double seen = ((double)idx->hint_visited * 1.15 + idx->max_degree) / (use_v2 ? 0.875 : 0.75) + 8.0;
         if (seen < est) est = seen;
     }
     if (est > (double)idx->n_total() * 1.34) est = (double)idx->n_total() * 1.34;
-    uint32_t hlog = std::max<uint32_t>(10, next_pow2_log2((uint64_t)est + 1));
+    // slots per warp: a power of two for the generic kernel, any multiple of 8 (32-byte buckets)
+    // for v2 so that the tables of all resident warps stay inside the L2
+    uint64_t slots = std::max<uint64_t>(256, (uint64_t)est + 1);
     if (const char* t = getenv("DAB_TEST_VISITED_LOG2")) {  // tests force the overflow/retry path
         int v = atoi(t);
-        if (v >= 8 && v <= 30) hlog = (uint32_t)v;
+        if (v >= 8 && v <= 30) slots = 1ull << v;
     }
 
     if ((rc = idx->s_counters.reserve(16 + (size_t)nq * 4))) return rc;
@@ -566,18 +569,28 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
 
     for (int pass = 0; pass < 6; ++pass) {
         const uint32_t warps = (uint32_t)grid * kSearchWarps;
-        if ((rc = idx->s_tables.reserve(((size_t)warps << hlog) * 4))) {
+        const uint32_t hlog = std::max<uint32_t>(use_v2 ? 8 : 10, next_pow2_log2(slots));
+        const uint32_t n_buckets = (uint32_t)((slots + 7) / 8);
+        const size_t words_per_warp = use_v2 ? (size_t)n_buckets * 8 : ((size_t)1 << hlog);
+        if ((rc = idx->s_tables.reserve((size_t)warps * words_per_warp * 4))) {
             retry_list.release();
             return rc;
         }
         p.tables = (uint32_t*)idx->s_tables.p;
         p.hcap_log2 = hlog;
-        pin_tables_in_l2(idx, ((size_t)warps << hlog) * 4);
+        pin_tables_in_l2(idx, (size_t)warps * words_per_warp * 4);
         DAB_CUDA(cudaMemsetAsync(d_counters, 0, 16, idx->stream));
         int launch_grid = (int)std::min<uint64_t>((uint64_t)grid, ((uint64_t)p.n_work + kSearchWarps - 1) / kSearchWarps);
         if (use_v2) {
+            p2.phase_cycles = nullptr;
+            if (getenv("DAB_PHASE_PROFILE")) {
+                static unsigned long long* d_phase = nullptr;
+                if (!d_phase) cudaMalloc(&d_phase, 64);
+                cudaMemsetAsync(d_phase, 0, 64, idx->stream);
+                p2.phase_cycles = d_phase;
+            }
             p2.tables = p.tables;
-            p2.hcap_log2 = hlog;
+            p2.n_buckets = n_buckets;
             p2.query_list = p.query_list;
             p2.n_work = p.n_work;
             v2.kern<<<launch_grid, kV2WarpsHost * 32, v2.smem_block, idx->stream>>>(p2);
@@ -590,6 +603,16 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
         DAB_CUDA(cudaMemcpyAsync(h_counters, d_counters, 12, cudaMemcpyDeviceToHost, idx->stream));
         DAB_CUDA(cudaStreamSynchronize(idx->stream));
         const uint32_t n_over = h_counters[1];
+        if (use_v2 && p2.phase_cycles) {
+            unsigned long long h_ph[8];
+            cudaMemcpy(h_ph, p2.phase_cycles, 64, cudaMemcpyDeviceToHost);
+            const char* names[8] = {"setup", "select", "adj+filter", "bulk-issue", "row-wait", "distance", "insert", "output"};
+            unsigned long long tot = 0;
+            for (int i = 0; i < 8; ++i) tot += h_ph[i];
+            fprintf(stderr, "[dab phase profile] nq=%u L=%u slots=%llu maxvisited=%u:", p.n_work, l_search, (unsigned long long)slots, h_counters[2]);
+            for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.1f%%", names[i], tot ? 100.0 * h_ph[i] / tot : 0.0);
+            fprintf(stderr, " | cycles/query=%.0f\n", (double)tot / p.n_work);
+        }
         if (!rec_ids) {  // build-time searches run on a growing graph: do not learn from them
             if (l_search != idx->hint_l || beam != idx->hint_beam) {
                 idx->hint_l = l_search;
@@ -614,8 +637,8 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
         retry_list = next;
         p.query_list = (const uint32_t*)retry_list.p;
         p.n_work = n_over;
-        hlog += 2;
-        if (((uint64_t)1 << hlog) > 4 * idx->n_total() + 4096) hlog = next_pow2_log2(2 * idx->n_total() + 2048);
+        slots *= 4;
+        if (slots > 4 * idx->n_total() + 4096) slots = 2 * idx->n_total() + 2048;
     }
     retry_list.release();
     return fail(DAB_ERR_VISITED_OVERFLOW, "search: visited set still overflowing after 6 passes");

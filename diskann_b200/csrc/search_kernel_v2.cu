@@ -48,7 +48,7 @@ struct SearchParamsV2 {
     uint32_t* out_cmps;
     uint32_t* out_hops;
     uint32_t* tables;
-    uint32_t hcap_log2;
+    uint32_t n_buckets;   // visited table: buckets of 8 ids (32 B) per warp, any count >= 16
     uint32_t* counters;
     uint32_t* overflow_list;
     uint32_t* rec_ids;
@@ -56,10 +56,11 @@ struct SearchParamsV2 {
     uint32_t* rec_counts;
     uint32_t rec_cap;
     // per-warp shared memory layout (bytes)
-    uint32_t warp_smem, off_q, off_cid, off_cd, off_beam, off_rows, off_bar;
+    uint32_t warp_smem, off_q, off_qd, off_qi, off_cid, off_cd, off_beam, off_rows;
     uint32_t row_bytes;   // bytes copied per row (multiple of 16)
     uint32_t row_slot;    // bytes between staged rows
     uint32_t stage_rows;  // rows staged per round (multiple of kGroup)
+    unsigned long long* phase_cycles;  // optional [8] per-phase cycle sums (profiling aid)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,115 +89,116 @@ __device__ __forceinline__ void bulk_row(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__device__ __forceinline__ uint32_t hash_id_v2(uint32_t id, uint32_t log2cap) { return (id * 0x9E3779B1u) >> (32u - log2cap); }
+__device__ __forceinline__ uint32_t bucket_of(uint32_t id, uint32_t n_buckets) { return __umulhi(id * 0x9E3779B1u, n_buckets); }
 
-// ---- register-resident sorted list, blocked layout: entry e lives in lane e / QR, reg e % QR
-template <int QR>
-struct RegQueue {
-    float d[QR];
-    uint32_t id[QR];  // bit 31 = visited flag
-};
+// ---- shared-memory sorted list with batched, rank-based merges ------------------------------
+// NeighborPriorityQueue::insert (queue.rs:130-171) applied to a whole round of candidates at
+// once.  Sequential lower-bound insertion with eviction of the tail is the same as keeping the
+// `cap` smallest elements under the total order (distance ascending, later-inserted first among
+// equal distances): a rejected / evicted element had >= cap elements ahead of it and can never
+// re-enter.  So each candidate's final index is
+//     #old(d < x) + #new((d_i < x) or (d_i == x and i later)),
+// each old entry moves right by #new(d_i <= d_old), and everything landing at >= cap is dropped.
+// NaN candidates are ignored; a full list pre-rejects `worst < x` exactly like the reference.
 
-template <int QR>
-__device__ __forceinline__ void rq_clear(RegQueue<QR>& q) {
-#pragma unroll
-    for (int r = 0; r < QR; ++r) {
-        q.d[r] = __int_as_float(0x7F800000);
-        q.id[r] = kEmptyV2;
+// first unvisited index in [from, lim), or lim
+__device__ __forceinline__ uint32_t first_unvisited(const uint32_t* qi, uint32_t from, uint32_t lim, int lane) {
+    for (uint32_t b = from & ~31u; b < lim; b += 32) {
+        const uint32_t i = b + lane;
+        const bool u = i >= from && i < lim && !(qi[i] & kFlagV2);
+        const unsigned m = __ballot_sync(kFull, u);
+        if (m) return b + __ffs(m) - 1;
     }
+    return lim;
 }
 
-// NeighborPriorityQueue::insert (queue.rs:130-171); warp-uniform (id, x); `size` uniform
-template <int QR>
-__device__ __forceinline__ void rq_insert(RegQueue<QR>& q, uint32_t cap, uint32_t& size, uint32_t id, float x, int lane) {
-    if (x != x) return;
-    if (size == cap) {
-        const uint32_t le = cap - 1;
-        float last = q.d[0];
-#pragma unroll
-        for (int r = 1; r < QR; ++r)
-            if ((int)(le % QR) == r) last = q.d[r];
-        last = __shfl_sync(kFull, last, (int)(le / QR));
-        if (last < x) return;
-    }
-    // lower bound = number of live entries with distance < x
-    int c = 0;
-#pragma unroll
-    for (int r = 0; r < QR; ++r) c += ((uint32_t)(lane * QR + r) < size && q.d[r] < x) ? 1 : 0;
-    const uint32_t pos = (uint32_t)__reduce_add_sync(kFull, c);
-    const float cd = __shfl_up_sync(kFull, q.d[QR - 1], 1);
-    const uint32_t ci = __shfl_up_sync(kFull, q.id[QR - 1], 1);
-#pragma unroll
-    for (int r = QR - 1; r >= 0; --r) {
-        const uint32_t e = (uint32_t)(lane * QR + r);
-        if (e > pos) {
-            q.d[r] = r > 0 ? q.d[r > 0 ? r - 1 : 0] : cd;
-            q.id[r] = r > 0 ? q.id[r > 0 ? r - 1 : 0] : ci;
-        } else if (e == pos) {
-            q.d[r] = x;
-            q.id[r] = id;
+// merge candidates c0 .. c0+m-1 (m <= 32; lane j owns candidate j) into the list
+template <int QT>
+__device__ __forceinline__ void merge_round(float* qd, uint32_t* qi, uint32_t cap, uint32_t& size, uint32_t& cursor_lo,
+                                            const uint32_t* cid, const float* cd, uint32_t c0, uint32_t m, int lane) {
+    const uint32_t j = (uint32_t)lane;
+    const float dj = j < m ? cd[c0 + j] : __int_as_float(0x7FC00000);
+    const uint32_t idj = j < m ? cid[c0 + j] : 0;
+    const float worst = size == cap ? qd[cap - 1] : __int_as_float(0x7F800000);
+    const bool valid = j < m && dj == dj && !(worst < dj);
+    const unsigned vm = __ballot_sync(kFull, valid);
+    if (!vm) return;
+    // lower bound among the old entries
+    uint32_t lo = 0, hi = size;
+    while (__any_sync(kFull, lo < hi)) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (lo < hi) {
+            if (qd[mid] < dj) lo = mid + 1;
+            else hi = mid;
         }
     }
-    if (size == cap) {
-        // the evicted tail moved to index cap: wipe it (falls off the end when cap == 32*QR)
+    // old entries into registers (striped: entry t*32 + lane)
+    float od[QT];
+    uint32_t oi[QT], sh[QT];
 #pragma unroll
-        for (int r = 0; r < QR; ++r)
-            if ((uint32_t)(lane * QR + r) == cap) {
-                q.d[r] = __int_as_float(0x7F800000);
-                q.id[r] = kEmptyV2;
-            }
-    } else {
-        ++size;
+    for (int t = 0; t < QT; ++t) {
+        const uint32_t e = (uint32_t)t * 32 + lane;
+        od[t] = e < size ? qd[e] : __int_as_float(0x7F800000);
+        oi[t] = e < size ? qi[e] : kEmptyV2;
+        sh[t] = 0;
     }
-}
-
-// closest_notvisited (queue.rs:297-313): marks and returns the first unvisited entry below
-// `lim`, or kEmptyV2; *dist receives its distance
-template <int QR>
-__device__ __forceinline__ uint32_t rq_pop(RegQueue<QR>& q, uint32_t lim, float* dist, int lane) {
-    int first = QR;
+    uint32_t rn = 0;
+    unsigned it = vm;
+    while (it) {
+        const int i = __ffs(it) - 1;
+        it &= it - 1;
+        const float di = __shfl_sync(kFull, dj, i);
+        rn += (di < dj || (di == dj && (uint32_t)i > j)) ? 1u : 0u;
 #pragma unroll
-    for (int r = QR - 1; r >= 0; --r)
-        if ((uint32_t)(lane * QR + r) < lim && !(q.id[r] & kFlagV2)) first = r;
-    const unsigned m = __ballot_sync(kFull, first < QR);
-    if (!m) return kEmptyV2;
-    const int src = __ffs(m) - 1;
-    uint32_t id = 0;
-    float d = 0.0f;
+        for (int t = 0; t < QT; ++t) sh[t] += di <= od[t] ? 1u : 0u;
+    }
+    const uint32_t pos = lo + rn;
+    const bool keep_new = valid && pos < cap;
+    __syncwarp();
 #pragma unroll
-    for (int r = 0; r < QR; ++r)
-        if (first == r) {
-            id = q.id[r];
-            d = q.d[r];
-            if (lane == src) q.id[r] = id | kFlagV2;
+    for (int t = 0; t < QT; ++t) {
+        const uint32_t e = (uint32_t)t * 32 + lane;
+        const uint32_t ne = e + sh[t];
+        if (e < size && sh[t] != 0 && ne < cap) {
+            qd[ne] = od[t];
+            qi[ne] = oi[t];
         }
-    *dist = __shfl_sync(kFull, d, src);
-    return __shfl_sync(kFull, id, src);
+    }
+    if (keep_new) {
+        qd[pos] = dj;
+        qi[pos] = idj;
+    }
+    size = min(cap, size + (uint32_t)__popc(vm));
+    cursor_lo = min(cursor_lo, __reduce_min_sync(kFull, keep_new ? pos : 0xFFFFFFFFu));
+    __syncwarp();
 }
 
-// first unvisited entry below lim without marking (for the adjacency prefetch)
-template <int QR>
-__device__ __forceinline__ uint32_t rq_peek(const RegQueue<QR>& q, uint32_t lim, int lane) {
-    int first = QR;
+// ---- exact visited set: bucketed open addressing, 8 ids per 32-byte bucket ------------------
+// One probe = one 32 B sector: returns true when `id` was newly inserted (HashSet::insert).
+__device__ __forceinline__ bool bucket_insert(uint32_t* table, uint32_t n_buckets, uint32_t b, uint4 lo4, uint4 hi4, uint32_t id) {
+    for (;;) {
+        uint32_t s[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+        bool found = false;
+        int empty = -1;
 #pragma unroll
-    for (int r = QR - 1; r >= 0; --r)
-        if ((uint32_t)(lane * QR + r) < lim && !(q.id[r] & kFlagV2)) first = r;
-    const unsigned m = __ballot_sync(kFull, first < QR);
-    if (!m) return kEmptyV2;
-    const int src = __ffs(m) - 1;
-    uint32_t id = 0;
-#pragma unroll
-    for (int r = 0; r < QR; ++r)
-        if (first == r) id = q.id[r];
-    return __shfl_sync(kFull, id, src);
-}
-
-template <int QR>
-__device__ __forceinline__ bool rq_has_unvisited(const RegQueue<QR>& q, uint32_t lim, int lane) {
-    bool any = false;
-#pragma unroll
-    for (int r = 0; r < QR; ++r) any |= (uint32_t)(lane * QR + r) < lim && !(q.id[r] & kFlagV2);
-    return __any_sync(kFull, any);
+        for (int k = 7; k >= 0; --k) {
+            found |= s[k] == id;
+            if (s[k] == kEmptyV2) empty = k;
+        }
+        if (found) return false;
+        uint32_t* bp = table + (size_t)b * 8;
+        if (empty >= 0) {
+            const uint32_t old = atomicCAS(bp + empty, kEmptyV2, id);
+            if (old == kEmptyV2) return true;
+            if (old == id) return false;
+            // another lane of this warp took the slot: re-read the bucket
+        } else {
+            b = b + 1 == n_buckets ? 0 : b + 1;
+            bp = table + (size_t)b * 8;
+        }
+        lo4 = __ldcg(reinterpret_cast<const uint4*>(bp));
+        hi4 = __ldcg(reinterpret_cast<const uint4*>(bp) + 1);
+    }
 }
 
 // transpose-butterfly stage over M live values (see flat_kernels.cu)
@@ -259,28 +261,29 @@ __device__ __forceinline__ float group_distance(const float* __restrict__ q, con
     return a;
 }
 
-template <typename TD, int KIND, int POST, int QR>
-__global__ void __launch_bounds__(kV2Warps * 32) search_kernel_v2(const SearchParamsV2 p) {
+template <typename TD, int KIND, int POST, int QT>
+#ifndef DAB_V2_MIN_CTAS
+#define DAB_V2_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_v2(const SearchParamsV2 p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint8_t* base = smem + (size_t)wib * p.warp_smem;
     float* qf = reinterpret_cast<float*>(base + p.off_q);
+    float* qd = reinterpret_cast<float*>(base + p.off_qd);
+    uint32_t* qi = reinterpret_cast<uint32_t*>(base + p.off_qi);
     uint32_t* cid = reinterpret_cast<uint32_t*>(base + p.off_cid);
     float* cd = reinterpret_cast<float*>(base + p.off_cd);
     uint32_t* beam_ids = reinterpret_cast<uint32_t*>(base + p.off_beam);
     uint8_t* rows = base + p.off_rows;
-    const uint32_t bar = smem_u32(base + p.off_bar);
     const uint32_t rows_a = smem_u32(rows);
 
     const uint32_t warp_slot = blockIdx.x * kV2Warps + wib;
-    uint32_t* table = p.tables + ((size_t)warp_slot << p.hcap_log2);
-    const uint32_t hcap = 1u << p.hcap_log2, hmask = hcap - 1;
-    const uint32_t hlimit = hcap - (hcap >> 2);
+    const uint32_t nbk = p.n_buckets;
+    uint32_t* table = p.tables + (size_t)warp_slot * nbk * 8;
+    const uint32_t hlimit = nbk * 7;  // 87.5 % load: 8-way buckets stay short
     const uint64_t n_total = p.n_points + p.n_start;
     const int dim = (int)p.dim;
-    uint32_t phase = 0;
-    if (lane == 0) mbar_init(bar);
-    __syncwarp();
 
     for (;;) {
         uint32_t w = 0;
@@ -289,6 +292,21 @@ __global__ void __launch_bounds__(kV2Warps * 32) search_kernel_v2(const SearchPa
         if (w >= p.n_work) break;
         const uint32_t qidx = p.query_list ? p.query_list[w] : w;
 
+#ifdef DAB_PHASE_PROFILE_BUILD
+        long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tmark = clock64();
+#define DAB_PHASE(i)                         \
+    do {                                     \
+        if (p.phase_cycles) {                \
+            const long long _n = clock64();  \
+            tph[i] += _n - tmark;            \
+            tmark = _n;                      \
+        }                                    \
+    } while (0)
+#else
+#define DAB_PHASE(i) do { } while (0)
+#endif
+
         __syncwarp();
         {
             const TD* s = p.query_rows ? reinterpret_cast<const TD*>(p.vectors + (size_t)p.query_rows[qidx] * p.row_stride)
@@ -296,24 +314,30 @@ __global__ void __launch_bounds__(kV2Warps * 32) search_kernel_v2(const SearchPa
             for (int e = lane; e < dim; e += 32) qf[e] = to_f32(s[e]);
             uint4 e4 = make_uint4(kEmptyV2, kEmptyV2, kEmptyV2, kEmptyV2);
             uint4* t4 = reinterpret_cast<uint4*>(table);
-            for (uint32_t i = lane; i < (hcap >> 2); i += 32) t4[i] = e4;
+            for (uint32_t i = lane; i < nbk * 2; i += 32) t4[i] = e4;
         }
         __syncwarp();
+        DAB_PHASE(0);  // query staging + table clear
 
-        RegQueue<QR> best;
-        rq_clear(best);
-        uint32_t size = 0, cmps = 0, hops = 0, nvisited = 0, nrec = 0;
+        uint32_t size = 0, cursor_lo = 0, cmps = 0, hops = 0, nvisited = 0, nrec = 0;
         bool overflow = false;
 
-        // stages `n` candidate rows (ids in cid[c0..)) and computes their distances into cd[]
+        // stage `n` candidate rows (ids cid[c0..)) with per-lane 16 B async copies (one warp
+        // instruction moves 512 B of a row) and compute their distances into cd[]
         auto distances = [&](uint32_t c0, uint32_t n) {
-            if (lane == 0) mbar_expect(bar, n * p.row_bytes);
+            const uint32_t myid = (uint32_t)lane < n ? cid[c0 + lane] : 0;  // n <= stage_rows <= 32
+#pragma unroll 4
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint8_t* src = p.vectors + (size_t)__shfl_sync(kFull, myid, j) * p.row_stride;
+                for (uint32_t off = lane * 16; off < p.row_bytes; off += 512)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rows_a + j * p.row_slot + off), "l"(src + off)
+                                 : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            DAB_PHASE(3);  // issue of the row copies
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
-            if ((uint32_t)lane < n) bulk_row(rows_a + lane * p.row_slot, p.vectors + (size_t)cid[c0 + lane] * p.row_stride, p.row_bytes, bar);
-            for (uint32_t j = 32 + lane; j < n; j += 32)
-                bulk_row(rows_a + j * p.row_slot, p.vectors + (size_t)cid[c0 + j] * p.row_stride, p.row_bytes, bar);
-            mbar_wait(bar, phase);
-            phase ^= 1;
+            DAB_PHASE(4);  // waiting for the rows
             for (uint32_t g0 = 0; g0 < n; g0 += kGroup) {
                 const float r = group_distance<TD, KIND>(qf, rows + (size_t)g0 * p.row_slot, p.row_slot, dim, lane);
                 const uint32_t u = (((lane >> 3) & 1) << 2) | (((lane >> 4) & 1) << 1) | ((lane >> 2) & 1);
@@ -322,50 +346,52 @@ __global__ void __launch_bounds__(kV2Warps * 32) search_kernel_v2(const SearchPa
             __syncwarp();
         };
 
-        // ---- start points
-        for (uint32_t s0 = 0; s0 < p.n_start; s0 += p.stage_rows) {
-            const uint32_t n = min(p.stage_rows, p.n_start - s0);
-            for (uint32_t j = lane; j < n; j += 32) {
-                const uint32_t id = (uint32_t)p.n_points + s0 + j;
-                cid[j] = id;
-                uint32_t h = hash_id_v2(id, p.hcap_log2);
-                for (;;) {
-                    uint32_t old = atomicCAS(table + h, kEmptyV2, id);
-                    if (old == kEmptyV2 || old == id) break;
-                    h = (h + 1) & hmask;
-                }
+        // ---- start points (SearchAccessor::start_point_distances, provider.rs:406-433)
+        for (uint32_t s0 = 0; s0 < p.n_start; s0 += 32) {
+            const uint32_t n = min(32u, p.n_start - s0);
+            if ((uint32_t)lane < n) {
+                const uint32_t id = (uint32_t)p.n_points + s0 + lane;
+                cid[lane] = id;
+                const uint32_t b = bucket_of(id, nbk);
+                const uint4* bp = reinterpret_cast<const uint4*>(table + (size_t)b * 8);
+                bucket_insert(table, nbk, b, __ldcg(bp), __ldcg(bp + 1), id);
             }
             __syncwarp();
-            distances(0, n);
-            for (uint32_t j = 0; j < n; ++j) rq_insert(best, p.cap, size, cid[j], cd[j], lane);
+            for (uint32_t c0 = 0; c0 < n; c0 += p.stage_rows) distances(c0, min(p.stage_rows, n - c0));
+            merge_round<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, 0, n, lane);
             nvisited += n;
             cmps += n;
-            __syncwarp();
         }
 
-        // ---- greedy loop
-        while (rq_has_unvisited(best, min(p.cap, size), lane)) {
+        // ---- greedy loop (index.rs:1961-1992)
+        for (;;) {
+            const uint32_t lim = min(p.cap, size);
             uint32_t nb = 0;
-            while (nb < p.beam) {
-                float nd;
-                const uint32_t id = rq_pop(best, min(p.cap, size), &nd, lane);
-                if (id == kEmptyV2) break;
+            while (nb < p.beam) {  // closest_notvisited x beam_width (queue.rs:297-313)
+                const uint32_t idx = first_unvisited(qi, cursor_lo, lim, lane);
+                if (idx >= lim) break;
+                const uint32_t id = qi[idx];
+                __syncwarp();
                 if (lane == 0) {
+                    qi[idx] = id | kFlagV2;
                     beam_ids[nb] = id;
                     if (p.rec_ids && nrec < p.rec_cap) {
                         p.rec_ids[(size_t)qidx * p.rec_cap + nrec] = id;
-                        p.rec_dists[(size_t)qidx * p.rec_cap + nrec] = nd;
+                        p.rec_dists[(size_t)qidx * p.rec_cap + nrec] = qd[idx];
                     }
                 }
+                cursor_lo = idx + 1;
                 ++nrec;
                 ++nb;
+                __syncwarp();
             }
-            __syncwarp();
+            if (nb == 0) break;
             {
                 // speculative: the next hop most likely expands the now-first unvisited entry
-                const uint32_t nxt = rq_peek(best, min(p.cap, size), lane);
-                if (nxt != kEmptyV2 && lane < 3) prefetch_l2(p.adj + (size_t)nxt * p.adj_stride + lane * 32);
+                const uint32_t nxt = first_unvisited(qi, cursor_lo, lim, lane);
+                if (nxt < lim && lane < 3) prefetch_l2(p.adj + (size_t)(qi[nxt] & ~kFlagV2) * p.adj_stride + lane * 32);
             }
+            DAB_PHASE(1);  // selection + prefetch
 
             uint32_t ncand = 0;
             for (uint32_t b = 0; b < nb; ++b) {
@@ -376,58 +402,41 @@ __global__ void __launch_bounds__(kV2Warps * 32) search_kernel_v2(const SearchPa
                 wd[1] = 32 + lane < p.adj_stride ? __ldg(row + 32 + lane) : kEmptyV2;
                 wd[2] = 64 + lane < p.adj_stride ? __ldg(row + 64 + lane) : kEmptyV2;
                 const uint32_t deg = min(__shfl_sync(kFull, wd[0], 0), p.max_degree);
-                // first probes of all three chunks in flight together
+                // bucket probes of all three chunks in flight together
                 bool valid[3];
-                uint32_t h[3], seen[3];
+                uint32_t bk[3];
+                uint4 lo4[3], hi4[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const uint32_t j = c * 32 + lane;
                     valid[c] = j >= 1 && j <= deg;
-                    h[c] = hash_id_v2(wd[c], p.hcap_log2);
-                    seen[c] = valid[c] ? __ldcg(table + h[c]) : wd[c];
+                    bk[c] = bucket_of(wd[c], nbk);
+                    if (valid[c]) {
+                        const uint4* bp = reinterpret_cast<const uint4*>(table + (size_t)bk[c] * 8);
+                        lo4[c] = __ldcg(bp);
+                        hi4[c] = __ldcg(bp + 1);
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    if ((uint32_t)c * 32 > deg) break;
                     bool inserted = false;
-                    if (valid[c]) {
-                        uint32_t old = seen[c], hh = h[c];
-                        for (;;) {
-                            if (old == kEmptyV2) old = atomicCAS(table + hh, kEmptyV2, wd[c]);
-                            if (old == kEmptyV2) {
-                                inserted = true;
-                                break;
-                            }
-                            if (old == wd[c]) break;
-                            hh = (hh + 1) & hmask;
-                            old = __ldcg(table + hh);
-                        }
-                    }
-                    const bool isnew = inserted && wd[c] < n_total;
+                    if (valid[c]) inserted = bucket_insert(table, nbk, bk[c], lo4[c], hi4[c], wd[c]);
+                    const bool isnew = inserted && wd[c] < n_total;  // is_in_bounds
                     const unsigned mi = __ballot_sync(kFull, inserted);
                     const unsigned mn = __ballot_sync(kFull, isnew);
                     if (isnew) cid[ncand + __popc(mn & ((1u << lane) - 1u))] = wd[c];
                     ncand += __popc(mn);
                     nvisited += __popc(mi);
                 }
-                // adjacency rows longer than 95 neighbours (max_degree > 95): remaining chunks
+                // adjacency rows longer than 95 neighbours: remaining chunks
                 for (uint32_t c0 = 96; c0 < deg + 1; c0 += 32) {
                     const uint32_t j = c0 + lane;
                     const uint32_t word = j < p.adj_stride ? __ldg(row + j) : kEmptyV2;
-                    const bool v = j <= deg;
                     bool inserted = false;
-                    if (v) {
-                        uint32_t hh = hash_id_v2(word, p.hcap_log2);
-                        for (;;) {
-                            uint32_t old = __ldcg(table + hh);
-                            if (old == kEmptyV2) old = atomicCAS(table + hh, kEmptyV2, word);
-                            if (old == kEmptyV2) {
-                                inserted = true;
-                                break;
-                            }
-                            if (old == word) break;
-                            hh = (hh + 1) & hmask;
-                        }
+                    if (j <= deg) {
+                        const uint32_t b2 = bucket_of(word, nbk);
+                        const uint4* bp = reinterpret_cast<const uint4*>(table + (size_t)b2 * 8);
+                        inserted = bucket_insert(table, nbk, b2, __ldcg(bp), __ldcg(bp + 1), word);
                     }
                     const bool isnew = inserted && word < n_total;
                     const unsigned mi = __ballot_sync(kFull, inserted);
@@ -436,36 +445,21 @@ __global__ void __launch_bounds__(kV2Warps * 32) search_kernel_v2(const SearchPa
                     ncand += __popc(mn);
                     nvisited += __popc(mi);
                 }
-                if (nvisited + p.max_degree + 32 > hlimit) overflow = true;
+                if (nvisited + p.max_degree > hlimit) overflow = true;
             }
             if (overflow) break;
             __syncwarp();
+            DAB_PHASE(2);  // adjacency fetch + visited filter
 
             for (uint32_t c0 = 0; c0 < ncand; c0 += p.stage_rows) distances(c0, min(p.stage_rows, ncand - c0));
+            DAB_PHASE(5);  // distance arithmetic
 
-            // best.insert in adjacency order; candidates that cannot enter a full list are skipped
-            for (uint32_t c0 = 0; c0 < ncand; c0 += 32) {
-                const uint32_t j = c0 + lane;
-                const float dj = j < ncand ? cd[j] : __int_as_float(0x7FC00000);
-                const uint32_t ij = j < ncand ? cid[j] : 0;
-                float worst = __int_as_float(0x7F800000);
-                if (size == p.cap) {
-                    const uint32_t le = p.cap - 1;
-                    float t = best.d[0];
-#pragma unroll
-                    for (int r = 1; r < QR; ++r)
-                        if ((int)(le % QR) == r) t = best.d[r];
-                    worst = __shfl_sync(kFull, t, (int)(le / QR));
-                }
-                unsigned m = __ballot_sync(kFull, j < ncand && !(worst < dj));
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    rq_insert(best, p.cap, size, __shfl_sync(kFull, ij, src), __shfl_sync(kFull, dj, src), lane);
-                }
-            }
+            // best.insert for every neighbour in adjacency order (index.rs:1986-1988)
+            for (uint32_t c0 = 0; c0 < ncand; c0 += 32)
+                merge_round<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, c0, min(32u, ncand - c0), lane);
             cmps += ncand;
             hops += nb;
+            DAB_PHASE(6);  // inserts
         }
 
         if (overflow) {
@@ -476,37 +470,21 @@ __global__ void __launch_bounds__(kV2Warps * 32) search_kernel_v2(const SearchPa
             continue;
         }
 
-        // ---- post-process: drop start points, first k
+        // ---- post-process: drop start points, first k (provider.rs:907-950)
         {
             const uint32_t n = min(p.cap, size);
             uint32_t count = 0;
-            // entries are blocked per lane (index order = lane-major): exclusive prefix of the
-            // kept flags over (lane, r) gives each kept entry its output position
-            int keptc = 0;
-            bool keep[QR];
-#pragma unroll
-            for (int r = 0; r < QR; ++r) {
-                const uint32_t e = (uint32_t)(lane * QR + r);
-                keep[r] = e < n && (best.id[r] & ~kFlagV2) < p.n_points;
-                keptc += keep[r] ? 1 : 0;
-            }
-            int incl = keptc;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(kFull, incl, o);
-                if (lane >= o) incl += t;
-            }
-            uint32_t pos = (uint32_t)(incl - keptc);
-            count = (uint32_t)__shfl_sync(kFull, incl, 31);
-#pragma unroll
-            for (int r = 0; r < QR; ++r) {
-                if (keep[r]) {
-                    if (pos < p.k) {
-                        p.out_ids[(size_t)qidx * p.k + pos] = best.id[r] & ~kFlagV2;
-                        p.out_dists[(size_t)qidx * p.k + pos] = best.d[r];
-                    }
-                    ++pos;
+            for (uint32_t b = 0; b < n && count < p.k; b += 32) {
+                const uint32_t i = b + lane;
+                const uint32_t id = i < n ? (qi[i] & ~kFlagV2) : kEmptyV2;
+                const bool keep = i < n && id < p.n_points;
+                const unsigned m = __ballot_sync(kFull, keep);
+                const uint32_t pos = count + __popc(m & ((1u << lane) - 1u));
+                if (keep && pos < p.k) {
+                    p.out_ids[(size_t)qidx * p.k + pos] = id;
+                    p.out_dists[(size_t)qidx * p.k + pos] = qd[i];
                 }
+                count += __popc(m);
             }
             count = min(count, p.k);
             for (uint32_t i = count + lane; i < p.k; i += 32) {
@@ -521,6 +499,12 @@ __global__ void __launch_bounds__(kV2Warps * 32) search_kernel_v2(const SearchPa
                 if (p.rec_counts) p.rec_counts[qidx] = min(nrec, p.rec_cap);
             }
         }
+        DAB_PHASE(7);  // output
+#ifdef DAB_PHASE_PROFILE_BUILD
+        if (p.phase_cycles && lane == 0)
+            for (int i = 0; i < 8; ++i) atomicAdd(p.phase_cycles + i, (unsigned long long)tph[i]);
+#endif
+#undef DAB_PHASE
     }
 }
 
@@ -542,7 +526,7 @@ int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchPar
     if (cap > 256 || idx->max_degree > 1000) return 1;
     const uint32_t row_bytes = (uint32_t)round_up((size_t)idx->dim * elem_size(idx->dtype), 16);
     if (row_bytes > idx->row_stride) return 1;
-    const uint32_t row_slot = row_bytes + 16;  // +16 B: rows start on different banks
+    const uint32_t row_slot = row_bytes;
     size_t off = 0;
     p.off_q = (uint32_t)off;
     off += round_up((size_t)idx->dim * 4, 16);
@@ -553,8 +537,11 @@ int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchPar
     off += round_up(std::max<size_t>(ncand_max, idx->n_start) * 4, 16);
     p.off_beam = (uint32_t)off;
     off += round_up((size_t)beam * 4, 16);
-    p.off_bar = (uint32_t)off;
-    off += 16;
+    const size_t cap_pad = round_up(cap, 32) + 32;
+    p.off_qd = (uint32_t)off;
+    off += cap_pad * 4;
+    p.off_qi = (uint32_t)off;
+    off += cap_pad * 4;
     off = round_up(off, 128);
     p.off_rows = (uint32_t)off;
     const size_t fixed = off;
@@ -593,6 +580,10 @@ int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchPar
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, out.kern, kV2Warps * 32, out.smem_block) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         return 1;
+    }
+    if (const char* t = getenv("DAB_V2_CTAS_PER_SM")) {  // tuning aid
+        const int v = atoi(t);
+        if (v >= 1 && v < per_sm) per_sm = v;
     }
     out.grid = per_sm * idx->sm_count;
     return 0;
