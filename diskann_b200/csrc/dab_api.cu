@@ -105,7 +105,7 @@ int dab_create(dab_index** out, int dtype, int metric, uint32_t dim, uint64_t n_
     idx->stream = idx->own_stream;
     const uint64_t total = idx->n_total();
     e = cudaMalloc(&idx->d_vectors, total * idx->row_stride);
-    if (e == cudaSuccess) e = cudaMalloc(&idx->d_adj, total * (size_t)idx->adj_stride * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&idx->d_adj, total * (size_t)idx->adj_stride * 4 + 512);  // +slack: kernels read whole 128 B lines of the last row
     if (e != cudaSuccess) {
         dab_destroy(idx);
         return fail(DAB_ERR_OUT_OF_MEMORY, "dab_create: device allocation failed: %s", cudaGetErrorString(e));
