@@ -372,45 +372,10 @@ struct V2Launch {
     int grid;
 };
 int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchParamsV2& p, V2Launch& out);
-constexpr int kV2WarpsHost = 4;
-
-// search_kernel_team.cu
-struct SearchParamsTeam {
-    const uint8_t* vectors;
-    size_t row_stride;
-    const uint32_t* adj;
-    uint32_t adj_stride;
-    uint64_t n_points;
-    uint32_t n_start;
-    uint32_t dim;
-    uint32_t max_degree;
-    const void* queries;
-    const uint32_t* query_rows;
-    const uint32_t* query_list;
-    uint32_t n_work;
-    uint32_t k, cap;
-    uint32_t* out_ids;
-    float* out_dists;
-    uint32_t* out_counts;
-    uint32_t* out_cmps;
-    uint32_t* out_hops;
-    uint32_t* tables;
-    uint32_t n_buckets;
-    uint32_t* counters;
-    uint32_t* overflow_list;
-    uint32_t* rec_ids;
-    float* rec_dists;
-    uint32_t* rec_counts;
-    uint32_t rec_cap;
-    uint32_t team_smem, off_q, off_qd, off_qi, off_cid, off_cd;
-};
-struct TeamLaunch {
-    void (*kern)(const SearchParamsTeam);
-    size_t smem_block;
-    int grid;
-};
-int team_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchParamsTeam& p, TeamLaunch& out);
-constexpr int kTeamWarpsHost = 2, kTeamsPerWarpHost = 4;
+#ifndef DAB_V2_WARPS
+#define DAB_V2_WARPS 1
+#endif
+constexpr int kV2WarpsHost = DAB_V2_WARPS;
 
 static uint32_t next_pow2_log2(uint64_t v) {
     uint32_t l = 0;
@@ -548,34 +513,7 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
     SearchParamsV2 p2;
     memset(&p2, 0, sizeof(p2));
     V2Launch v2;
-    SearchParamsTeam p3;
-    memset(&p3, 0, sizeof(p3));
-    TeamLaunch tl;
-    const bool use_team = team_prepare(idx, l_search, beam, p3, tl) == 0;
-    if (use_team) {
-        p3.vectors = p.vectors;
-        p3.row_stride = p.row_stride;
-        p3.adj = p.adj;
-        p3.adj_stride = p.adj_stride;
-        p3.n_points = p.n_points;
-        p3.n_start = p.n_start;
-        p3.dim = p.dim;
-        p3.max_degree = p.max_degree;
-        p3.queries = p.queries;
-        p3.query_rows = p.query_rows;
-        p3.k = p.k;
-        p3.cap = p.cap;
-        p3.out_ids = p.out_ids;
-        p3.out_dists = p.out_dists;
-        p3.out_counts = p.out_counts;
-        p3.out_cmps = p.out_cmps;
-        p3.out_hops = p.out_hops;
-        p3.rec_ids = p.rec_ids;
-        p3.rec_dists = p.rec_dists;
-        p3.rec_counts = p.rec_counts;
-        p3.rec_cap = p.rec_cap;
-    }
-    const bool use_v2 = !use_team && v2_prepare(idx, l_search, beam, p2, v2) == 0;
+    const bool use_v2 = v2_prepare(idx, l_search, beam, p2, v2) == 0;
     if (use_v2) {
         p2.vectors = p.vectors;
         p2.row_stride = p.row_stride;
@@ -609,7 +547,7 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
         // later batches: 1.5x the largest visited set seen at this (or a larger) L, at 75 % load
         // (visited sets grow monotonically with L); queries that still overflow are re-run
         // below with a larger table
-        const double seen = ((double)idx->hint_visited * 1.15 + idx->max_degree) / (use_v2 || use_team ? 0.875 : 0.75) + 8.0;
+        const double seen = ((double)idx->hint_visited * 1.15 + idx->max_degree) / (use_v2 ? 0.875 : 0.75) + 8.0;
         if (seen < est) est = seen;
     }
     if (est > (double)idx->n_total() * 1.34) est = (double)idx->n_total() * 1.34;
@@ -633,11 +571,10 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
     Scratch retry_list;  // holds the overflow list of the previous pass
 
     for (int pass = 0; pass < 6; ++pass) {
-        // number of per-query table slots resident at once (teams or warps)
-        const uint32_t warps = use_team ? (uint32_t)tl.grid * kTeamWarpsHost * kTeamsPerWarpHost : (uint32_t)grid * kSearchWarps;
-        const uint32_t hlog = std::max<uint32_t>(use_v2 || use_team ? 8 : 10, next_pow2_log2(slots));
+        const uint32_t warps = (uint32_t)grid * (use_v2 ? kV2WarpsHost : kSearchWarps);
+        const uint32_t hlog = std::max<uint32_t>(use_v2 ? 8 : 10, next_pow2_log2(slots));
         const uint32_t n_buckets = (uint32_t)((slots + 7) / 8);
-        const size_t words_per_warp = use_v2 || use_team ? (size_t)n_buckets * 8 : ((size_t)1 << hlog);
+        const size_t words_per_warp = use_v2 ? (size_t)n_buckets * 8 : ((size_t)1 << hlog);
         if ((rc = idx->s_tables.reserve((size_t)warps * words_per_warp * 4))) {
             retry_list.release();
             return rc;
@@ -647,17 +584,14 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
         pin_tables_in_l2(idx, (size_t)warps * words_per_warp * 4);
         DAB_CUDA(cudaMemsetAsync(d_counters, 0, 16, idx->stream));
         int launch_grid = (int)std::min<uint64_t>((uint64_t)grid, ((uint64_t)p.n_work + kSearchWarps - 1) / kSearchWarps);
-        if (use_team) {
-            p3.counters = d_counters;
-            p3.overflow_list = d_overflow;
-            p3.tables = p.tables;
-            p3.n_buckets = n_buckets;
-            p3.query_list = p.query_list;
-            p3.n_work = p.n_work;
-            const uint32_t q_per_cta = kTeamWarpsHost * kTeamsPerWarpHost;
-            const int team_grid = (int)std::min<uint64_t>((uint64_t)tl.grid, ((uint64_t)p.n_work + q_per_cta - 1) / q_per_cta);
-            tl.kern<<<team_grid, kTeamWarpsHost * 32, tl.smem_block, idx->stream>>>(p3);
-        } else if (use_v2) {
+        if (use_v2) {
+            // one warp per query, persistent: size the grid so every resident warp runs the same
+            // number of queries (10K queries on 3108 slots would otherwise pay for 4 full rounds
+            // with the last one 22 % full)
+            const uint64_t max_warps = (uint64_t)grid * kV2WarpsHost;
+            const uint64_t rounds = (p.n_work + max_warps - 1) / max_warps;
+            const uint64_t need = (p.n_work + rounds - 1) / rounds;
+            launch_grid = (int)((need + kV2WarpsHost - 1) / kV2WarpsHost);
             p2.phase_cycles = nullptr;
             if (getenv("DAB_PHASE_PROFILE")) {
                 static unsigned long long* d_phase = nullptr;

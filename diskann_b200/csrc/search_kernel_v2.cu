@@ -23,7 +23,10 @@
 
 namespace dab {
 
-constexpr int kV2Warps = 4;
+#ifndef DAB_V2_WARPS
+#define DAB_V2_WARPS 1
+#endif
+constexpr int kV2Warps = DAB_V2_WARPS;  // warps per CTA (each warp owns a query)
 constexpr uint32_t kEmptyV2 = 0xFFFFFFFFu;
 constexpr uint32_t kFlagV2 = 0x80000000u;
 constexpr int kGroup = 8;  // rows reduced together
@@ -263,7 +266,7 @@ __device__ __forceinline__ float group_distance(const float* __restrict__ q, con
 
 template <typename TD, int KIND, int POST, int QT>
 #ifndef DAB_V2_MIN_CTAS
-#define DAB_V2_MIN_CTAS 5
+#define DAB_V2_MIN_CTAS 21
 #endif
 __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_v2(const SearchParamsV2 p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -546,7 +549,12 @@ int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchPar
     p.off_rows = (uint32_t)off;
     const size_t fixed = off;
     // rows staged per round: as many as fit ~6 KB per warp, a multiple of the reduce group
-    uint32_t stage = (uint32_t)std::max<size_t>(kGroup, (6144 / row_slot) / kGroup * kGroup);
+    size_t stage_bytes = 6144;
+    if (const char* t = getenv("DAB_V2_STAGE_BYTES")) {  // tuning aid
+        const long v = atol(t);
+        if (v >= 1024 && v <= 65536) stage_bytes = (size_t)v;
+    }
+    uint32_t stage = (uint32_t)std::max<size_t>(kGroup, (stage_bytes / row_slot) / kGroup * kGroup);
     stage = std::min<uint32_t>(stage, 32);
     p.stage_rows = stage;
     p.row_bytes = row_bytes;
