@@ -34,6 +34,7 @@ SYMBOLS = {
     "dab_pq_populate_lut": (_i, [_vp, _vp, _u32, _i, _vp]),
     "dab_pq_distances": (_i, [_vp, _vp, _u32, _vp, _u32, _vp]),
     "dab_pq_encode": (_i, [_vp, _vp, _u64, _vp]),
+    "dab_search_batch_pq": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "dab_sq_compress": (_i, [_i, _vp, _f, _u32, _i, _vp, _u64, _vp, _vp]),
     "dab_sq_distances": (_i, [_i, _i, _i, _f, _f, _u32, _vp, _vp, _vp, _vp, _u64, _vp]),
     "dab_robust_prune": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _f, _vp, _vp]),

@@ -1,0 +1,124 @@
+// search_common.cuh — device helpers shared by the warp-per-query search kernels: the exact
+// bucketed visited set and the batched rank-merge of the sorted candidate list.
+#pragma once
+
+#include "distance_device.cuh"
+
+namespace dab {
+
+constexpr uint32_t kEmptyV2 = 0xFFFFFFFFu;
+constexpr uint32_t kFlagV2 = 0x80000000u;
+
+__device__ __forceinline__ uint32_t bucket_of(uint32_t id, uint32_t n_buckets) { return __umulhi(id * 0x9E3779B1u, n_buckets); }
+
+// ---- shared-memory sorted list with batched, rank-based merges ------------------------------
+// NeighborPriorityQueue::insert (queue.rs:130-171) applied to a whole round of candidates at
+// once.  Sequential lower-bound insertion with eviction of the tail is the same as keeping the
+// `cap` smallest elements under the total order (distance ascending, later-inserted first among
+// equal distances): a rejected / evicted element had >= cap elements ahead of it and can never
+// re-enter.  So each candidate's final index is
+//     #old(d < x) + #new((d_i < x) or (d_i == x and i later)),
+// each old entry moves right by #new(d_i <= d_old), and everything landing at >= cap is dropped.
+// NaN candidates are ignored; a full list pre-rejects `worst < x` exactly like the reference.
+
+// first unvisited index in [from, lim), or lim
+__device__ __forceinline__ uint32_t first_unvisited(const uint32_t* qi, uint32_t from, uint32_t lim, int lane) {
+    for (uint32_t b = from & ~31u; b < lim; b += 32) {
+        const uint32_t i = b + lane;
+        const bool u = i >= from && i < lim && !(qi[i] & kFlagV2);
+        const unsigned m = __ballot_sync(kFull, u);
+        if (m) return b + __ffs(m) - 1;
+    }
+    return lim;
+}
+
+// merge candidates c0 .. c0+m-1 (m <= 32; lane j owns candidate j) into the list
+template <int QT>
+__device__ __forceinline__ void merge_round(float* qd, uint32_t* qi, uint32_t cap, uint32_t& size, uint32_t& cursor_lo,
+                                            const uint32_t* cid, const float* cd, uint32_t c0, uint32_t m, int lane) {
+    const uint32_t j = (uint32_t)lane;
+    const float dj = j < m ? cd[c0 + j] : __int_as_float(0x7FC00000);
+    const uint32_t idj = j < m ? cid[c0 + j] : 0;
+    const float worst = size == cap ? qd[cap - 1] : __int_as_float(0x7F800000);
+    const bool valid = j < m && dj == dj && !(worst < dj);
+    const unsigned vm = __ballot_sync(kFull, valid);
+    if (!vm) return;
+    // lower bound among the old entries
+    uint32_t lo = 0, hi = size;
+    while (__any_sync(kFull, lo < hi)) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (lo < hi) {
+            if (qd[mid] < dj) lo = mid + 1;
+            else hi = mid;
+        }
+    }
+    // old entries into registers (striped: entry t*32 + lane)
+    float od[QT];
+    uint32_t oi[QT], sh[QT];
+#pragma unroll
+    for (int t = 0; t < QT; ++t) {
+        const uint32_t e = (uint32_t)t * 32 + lane;
+        od[t] = e < size ? qd[e] : __int_as_float(0x7F800000);
+        oi[t] = e < size ? qi[e] : kEmptyV2;
+        sh[t] = 0;
+    }
+    uint32_t rn = 0;
+    unsigned it = vm;
+    while (it) {
+        const int i = __ffs(it) - 1;
+        it &= it - 1;
+        const float di = __shfl_sync(kFull, dj, i);
+        rn += (di < dj || (di == dj && (uint32_t)i > j)) ? 1u : 0u;
+#pragma unroll
+        for (int t = 0; t < QT; ++t) sh[t] += di <= od[t] ? 1u : 0u;
+    }
+    const uint32_t pos = lo + rn;
+    const bool keep_new = valid && pos < cap;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < QT; ++t) {
+        const uint32_t e = (uint32_t)t * 32 + lane;
+        const uint32_t ne = e + sh[t];
+        if (e < size && sh[t] != 0 && ne < cap) {
+            qd[ne] = od[t];
+            qi[ne] = oi[t];
+        }
+    }
+    if (keep_new) {
+        qd[pos] = dj;
+        qi[pos] = idj;
+    }
+    size = min(cap, size + (uint32_t)__popc(vm));
+    cursor_lo = min(cursor_lo, __reduce_min_sync(kFull, keep_new ? pos : 0xFFFFFFFFu));
+    __syncwarp();
+}
+
+// ---- exact visited set: bucketed open addressing, 8 ids per 32-byte bucket ------------------
+// One probe = one 32 B sector: returns true when `id` was newly inserted (HashSet::insert).
+__device__ __forceinline__ bool bucket_insert(uint32_t* table, uint32_t n_buckets, uint32_t b, uint4 lo4, uint4 hi4, uint32_t id) {
+    for (;;) {
+        uint32_t s[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+        bool found = false;
+        int empty = -1;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            found |= s[k] == id;
+            if (s[k] == kEmptyV2) empty = k;
+        }
+        if (found) return false;
+        uint32_t* bp = table + (size_t)b * 8;
+        if (empty >= 0) {
+            const uint32_t old = atomicCAS(bp + empty, kEmptyV2, id);
+            if (old == kEmptyV2) return true;
+            if (old == id) return false;
+            // another lane of this warp took the slot: re-read the bucket
+        } else {
+            b = b + 1 == n_buckets ? 0 : b + 1;
+            bp = table + (size_t)b * 8;
+        }
+        lo4 = __ldcg(reinterpret_cast<const uint4*>(bp));
+        hi4 = __ldcg(reinterpret_cast<const uint4*>(bp) + 1);
+    }
+}
+
+}  // namespace dab

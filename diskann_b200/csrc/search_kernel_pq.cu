@@ -1,0 +1,388 @@
+// search_kernel_pq.cu — batched greedy search whose traversal distances are PQ ADC lookups.
+//
+// Restates the providers' quant accessor (diskann-providers/src/model/graph/provider/async_/
+// inmem/product.rs:311-340: expand_beam with `computer.evaluate_similarity(aux_vectors[i])`)
+// around the same search_internal loop (diskann/src/graph/index.rs:1933-2000):
+//   * QueryComputer::new (pq/distance/dynamic.rs:63-87): L2 and CosineNormalized -> TableL2,
+//     InnerProduct -> TableIP (entries are -dot); the query is converted to f32 first;
+//   * the warp builds its query's table once (n_chunks x n_centers f32, entries in the
+//     reference's SIMD order for the chunk length, fixed_chunk_pq_table.rs:152-187) into a
+//     per-warp global scratch that stays in L2;
+//   * per hop every lane owns one surviving neighbour: coalesced 16 B code loads, one table
+//     gather per chunk, and the sum is accumulated in chunk order from 0.0
+//     (pq_dist_lookup_single, fixed_chunk_pq_table.rs:82-98) -> bit-identical ADC distances;
+//   * visited set, sorted list and post-processing are the shared exact helpers.
+// No tensor cores: LUT gather + byte loads, HBM traffic is n_chunks code bytes per candidate.
+#include "dab_common.cuh"
+#include "quant_device.cuh"
+#include "search_common.cuh"
+
+#include <algorithm>
+
+namespace dab {
+
+constexpr int kPqWarps = 4;
+
+struct SearchParamsPq {
+    const uint8_t* vectors;  // only for the f32 view of the query rows in build-free search: unused
+    const uint32_t* adj;
+    uint32_t adj_stride;
+    uint64_t n_points;
+    uint32_t n_start;
+    uint32_t dim;
+    uint32_t max_degree;
+    int dtype;
+    const void* queries;
+    const uint32_t* query_list;
+    uint32_t n_work;
+    uint32_t k, cap, beam;
+    const float* pivots;
+    const uint32_t* offsets;
+    const uint8_t* codes;
+    uint32_t n_chunks, n_centers;
+    int ip_table;  // 1: TableIP (entries -dot), 0: TableL2
+    float* luts;   // [warps][n_chunks * n_centers]
+    uint32_t* out_ids;
+    float* out_dists;
+    uint32_t* out_counts;
+    uint32_t* out_cmps;
+    uint32_t* out_hops;
+    uint32_t* tables;
+    uint32_t n_buckets;
+    uint32_t* counters;
+    uint32_t* overflow_list;
+    uint32_t warp_smem, off_q, off_qd, off_qi, off_cid, off_cd, off_beam;
+};
+
+template <int QT>
+__global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchParamsPq p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint8_t* base = smem + (size_t)wib * p.warp_smem;
+    float* qf = reinterpret_cast<float*>(base + p.off_q);
+    float* qd = reinterpret_cast<float*>(base + p.off_qd);
+    uint32_t* qi = reinterpret_cast<uint32_t*>(base + p.off_qi);
+    uint32_t* cid = reinterpret_cast<uint32_t*>(base + p.off_cid);
+    float* cd = reinterpret_cast<float*>(base + p.off_cd);
+    uint32_t* beam_ids = reinterpret_cast<uint32_t*>(base + p.off_beam);
+
+    const uint32_t warp_slot = blockIdx.x * kPqWarps + wib;
+    const uint32_t nbk = p.n_buckets;
+    uint32_t* table = p.tables + (size_t)warp_slot * nbk * 8;
+    const uint32_t hlimit = nbk * 7;
+    const uint64_t n_total = p.n_points + p.n_start;
+    const uint32_t entries = p.n_chunks * p.n_centers;
+    float* lut = p.luts + (size_t)warp_slot * entries;
+    const int dim = (int)p.dim;
+
+    // ADC distances of candidates cid[0..n) -> cd[]: one lane per candidate
+    auto adc = [&](uint32_t n) {
+        for (uint32_t c0 = 0; c0 < n; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            if (c < n) {
+                const uint8_t* code = p.codes + (size_t)cid[c] * p.n_chunks;
+                float accum = 0.0f;
+                uint32_t ch = 0;
+                if ((p.n_chunks & 15u) == 0) {
+                    for (; ch < p.n_chunks; ch += 16) {
+                        const uint4 w = __ldg(reinterpret_cast<const uint4*>(code + ch));
+                        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+                        float v[16];
+#pragma unroll
+                        for (int k2 = 0; k2 < 16; ++k2)
+                            v[k2] = __ldcg(lut + (ch + k2) * p.n_centers + ((ws[k2 >> 2] >> ((k2 & 3) * 8)) & 0xFFu));
+#pragma unroll
+                        for (int k2 = 0; k2 < 16; ++k2) accum = __fadd_rn(accum, v[k2]);
+                    }
+                } else {
+                    for (; ch < p.n_chunks; ++ch) accum = __fadd_rn(accum, __ldcg(lut + ch * p.n_centers + __ldg(code + ch)));
+                }
+                cd[c] = accum;
+            }
+        }
+        __syncwarp();
+    };
+
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(p.counters, 1u);
+        w = __shfl_sync(kFull, w, 0);
+        if (w >= p.n_work) break;
+        const uint32_t qidx = p.query_list ? p.query_list[w] : w;
+
+        // ---- query -> f32 (T: Into<f32>), table build, visited clear
+        __syncwarp();
+        for (int e = lane; e < dim; e += 32) {
+            float v;
+            switch (p.dtype) {
+                case DAB_F32: v = reinterpret_cast<const float*>(p.queries)[(size_t)qidx * dim + e]; break;
+                case DAB_F16: v = __half2float(reinterpret_cast<const __half*>(p.queries)[(size_t)qidx * dim + e]); break;
+                case DAB_I8: v = (float)reinterpret_cast<const int8_t*>(p.queries)[(size_t)qidx * dim + e]; break;
+                default: v = (float)reinterpret_cast<const uint8_t*>(p.queries)[(size_t)qidx * dim + e]; break;
+            }
+            qf[e] = v;
+        }
+        {
+            const uint4 e4 = make_uint4(kEmptyV2, kEmptyV2, kEmptyV2, kEmptyV2);
+            uint4* t4 = reinterpret_cast<uint4*>(table);
+            for (uint32_t i = lane; i < nbk * 2; i += 32) t4[i] = e4;
+        }
+        __syncwarp();
+        for (uint32_t t = lane; t < entries; t += 32) {
+            const uint32_t chunk = t / p.n_centers, center = t % p.n_centers;
+            const uint32_t start = p.offsets[chunk], stop = p.offsets[chunk + 1];
+            const float* piv = p.pivots + (size_t)center * dim + start;
+            float v;
+            if (p.ip_table) v = -thread_simd_l2ip<KIND_IP>(qf + start, piv, (int)(stop - start));
+            else v = thread_simd_l2ip<KIND_L2>(qf + start, piv, (int)(stop - start));
+            __stcg(lut + t, v);
+        }
+        __syncwarp();
+
+        uint32_t size = 0, cursor_lo = 0, cmps = 0, hops = 0, nvisited = 0;
+        bool overflow = false;
+
+        // ---- start points
+        for (uint32_t s0 = 0; s0 < p.n_start; s0 += 32) {
+            const uint32_t n = min(32u, p.n_start - s0);
+            if ((uint32_t)lane < n) {
+                const uint32_t id = (uint32_t)p.n_points + s0 + lane;
+                cid[lane] = id;
+                const uint32_t b = bucket_of(id, nbk);
+                const uint4* bp = reinterpret_cast<const uint4*>(table + (size_t)b * 8);
+                bucket_insert(table, nbk, b, __ldcg(bp), __ldcg(bp + 1), id);
+            }
+            __syncwarp();
+            adc(n);
+            merge_round<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, 0, n, lane);
+            nvisited += n;
+            cmps += n;
+        }
+
+        // ---- greedy loop
+        for (;;) {
+            const uint32_t lim = min(p.cap, size);
+            uint32_t nb = 0;
+            while (nb < p.beam) {
+                const uint32_t idx = first_unvisited(qi, cursor_lo, lim, lane);
+                if (idx >= lim) break;
+                const uint32_t id = qi[idx];
+                __syncwarp();
+                if (lane == 0) {
+                    qi[idx] = id | kFlagV2;
+                    beam_ids[nb] = id;
+                }
+                cursor_lo = idx + 1;
+                ++nb;
+                __syncwarp();
+            }
+            if (nb == 0) break;
+            uint32_t ncand = 0;
+            for (uint32_t b = 0; b < nb; ++b) {
+                const uint32_t node = beam_ids[b];
+                const uint32_t* row = p.adj + (size_t)node * p.adj_stride;
+                const uint32_t deg = min(__ldg(row), p.max_degree);
+                for (uint32_t c0 = 0; c0 < deg + 1; c0 += 32) {
+                    const uint32_t j = c0 + lane;
+                    const uint32_t word = j < p.adj_stride ? __ldg(row + j) : kEmptyV2;
+                    bool inserted = false;
+                    if (j >= 1 && j <= deg) {
+                        const uint32_t b2 = bucket_of(word, nbk);
+                        const uint4* bp = reinterpret_cast<const uint4*>(table + (size_t)b2 * 8);
+                        inserted = bucket_insert(table, nbk, b2, __ldcg(bp), __ldcg(bp + 1), word);
+                    }
+                    const bool isnew = inserted && word < n_total;
+                    const unsigned mi = __ballot_sync(kFull, inserted);
+                    const unsigned mn = __ballot_sync(kFull, isnew);
+                    if (isnew) cid[ncand + __popc(mn & ((1u << lane) - 1u))] = word;
+                    ncand += __popc(mn);
+                    nvisited += __popc(mi);
+                }
+                if (nvisited + p.max_degree > hlimit) overflow = true;
+            }
+            if (overflow) break;
+            __syncwarp();
+            adc(ncand);
+            for (uint32_t c0 = 0; c0 < ncand; c0 += 32)
+                merge_round<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, c0, min(32u, ncand - c0), lane);
+            cmps += ncand;
+            hops += nb;
+        }
+
+        if (overflow) {
+            if (lane == 0) {
+                const uint32_t o = atomicAdd(p.counters + 1, 1u);
+                p.overflow_list[o] = qidx;
+            }
+            continue;
+        }
+        {
+            const uint32_t n = min(p.cap, size);
+            uint32_t count = 0;
+            for (uint32_t b = 0; b < n && count < p.k; b += 32) {
+                const uint32_t i = b + lane;
+                const uint32_t id = i < n ? (qi[i] & ~kFlagV2) : kEmptyV2;
+                const bool keep = i < n && id < p.n_points;
+                const unsigned m = __ballot_sync(kFull, keep);
+                const uint32_t pos = count + __popc(m & ((1u << lane) - 1u));
+                if (keep && pos < p.k) {
+                    p.out_ids[(size_t)qidx * p.k + pos] = id;
+                    p.out_dists[(size_t)qidx * p.k + pos] = qd[i];
+                }
+                count += __popc(m);
+            }
+            count = min(count, p.k);
+            for (uint32_t i = count + lane; i < p.k; i += 32) {
+                p.out_ids[(size_t)qidx * p.k + i] = kEmptyV2;
+                p.out_dists[(size_t)qidx * p.k + i] = __int_as_float(0x7F800000);
+            }
+            if (lane == 0) {
+                atomicMax(p.counters + 2, nvisited);
+                if (p.out_counts) p.out_counts[qidx] = count;
+                if (p.out_cmps) p.out_cmps[qidx] = cmps;
+                if (p.out_hops) p.out_hops[qidx] = hops;
+            }
+        }
+    }
+}
+
+static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam,
+                         uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cmps, uint32_t* d_hops) {
+    if (!idx->graph_ready) return fail(DAB_ERR_NOT_READY, "dab_search_batch_pq: graph must be uploaded first");
+    if (!idx->d_pivots || !idx->d_codes) return fail(DAB_ERR_NOT_READY, "dab_search_batch_pq: dab_upload_pq (with codes) has not been called");
+    if (k == 0 || l_search == 0 || beam == 0 || beam > 64) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: bad k / l_search / beam_width");
+    if (idx->metric == DAB_COSINE)
+        return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: Metric::Cosine traverses with DirectCosine (no table); use dab_pq_distances");
+    const uint32_t cap = l_search + idx->n_start;
+    if (cap > 256) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: L + #start must be <= 256");
+    SearchParamsPq p;
+    memset(&p, 0, sizeof(p));
+    p.adj = idx->d_adj;
+    p.adj_stride = idx->adj_stride;
+    p.n_points = idx->n_points;
+    p.n_start = idx->n_start;
+    p.dim = idx->dim;
+    p.max_degree = idx->max_degree;
+    p.dtype = idx->dtype;
+    p.queries = d_queries;
+    p.k = k;
+    p.cap = cap;
+    p.beam = beam;
+    p.pivots = idx->d_pivots;
+    p.offsets = idx->d_offsets;
+    p.codes = idx->d_codes;
+    p.n_chunks = idx->pq_chunks;
+    p.n_centers = idx->pq_centers;
+    p.ip_table = idx->metric == DAB_INNER_PRODUCT ? 1 : 0;  // L2 and CosineNormalized use TableL2 (dynamic.rs:80-85)
+    p.out_ids = d_ids;
+    p.out_dists = d_dists;
+    p.out_counts = d_counts;
+    p.out_cmps = d_cmps;
+    p.out_hops = d_hops;
+
+    size_t off = 0;
+    p.off_q = 0;
+    off += round_up((size_t)idx->dim * 4, 16);
+    const size_t cap_pad = round_up(cap, 32) + 32;
+    p.off_qd = (uint32_t)off;
+    off += cap_pad * 4;
+    p.off_qi = (uint32_t)off;
+    off += cap_pad * 4;
+    const size_t ncand_max = std::max<size_t>((size_t)beam * idx->max_degree, idx->n_start);
+    p.off_cid = (uint32_t)off;
+    off += round_up(ncand_max * 4, 16);
+    p.off_cd = (uint32_t)off;
+    off += round_up(ncand_max * 4, 16);
+    p.off_beam = (uint32_t)off;
+    off += round_up((size_t)beam * 4, 16);
+    p.warp_smem = (uint32_t)round_up(off, 16);
+    const size_t smem_block = (size_t)p.warp_smem * kPqWarps;
+    if (smem_block > 200 * 1024) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: configuration needs %zu B shared memory per CTA", smem_block);
+    void (*kern)(const SearchParamsPq) = cap <= 128 ? search_kernel_pq<4> : search_kernel_pq<8>;
+    DAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block));
+    int per_sm = 0;
+    DAB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPqWarps * 32, smem_block));
+    if (per_sm < 1) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: kernel does not fit");
+    per_sm = std::min(per_sm, 6);  // keeps the per-warp tables (32 KB each at 32 x 256) inside the L2
+    const int grid = (int)std::min<uint64_t>((uint64_t)per_sm * idx->sm_count, ((uint64_t)nq + kPqWarps - 1) / kPqWarps);
+    const uint32_t warps = (uint32_t)grid * kPqWarps;
+
+    uint64_t slots = std::max<uint64_t>(256, (uint64_t)(1.1 * idx->max_degree * 1.3 * (double)l_search) + 1);
+    if (slots > 2 * idx->n_total() + 2048) slots = 2 * idx->n_total() + 2048;
+    int rc;
+    if ((rc = idx->s_counters.reserve(16 + (size_t)nq * 4))) return rc;
+    uint32_t* d_counters = (uint32_t*)idx->s_counters.p;
+    p.counters = d_counters;
+    p.overflow_list = d_counters + 4;
+    const size_t lut_bytes = (size_t)warps * idx->pq_chunks * idx->pq_centers * 4;
+    if ((rc = idx->s_out2.reserve(lut_bytes))) return rc;
+    p.luts = (float*)idx->s_out2.p;
+    p.n_work = nq;
+    Scratch retry;
+    for (int pass = 0; pass < 6; ++pass) {
+        p.n_buckets = (uint32_t)((slots + 7) / 8);
+        if ((rc = idx->s_tables.reserve((size_t)warps * p.n_buckets * 32))) {
+            retry.release();
+            return rc;
+        }
+        p.tables = (uint32_t*)idx->s_tables.p;
+        DAB_CUDA(cudaMemsetAsync(d_counters, 0, 16, idx->stream));
+        kern<<<grid, kPqWarps * 32, smem_block, idx->stream>>>(p);
+        DAB_LAUNCHED();
+        DAB_CUDA(cudaGetLastError());
+        uint32_t h[3] = {0, 0, 0};
+        DAB_CUDA(cudaMemcpyAsync(h, d_counters, 12, cudaMemcpyDeviceToHost, idx->stream));
+        DAB_CUDA(cudaStreamSynchronize(idx->stream));
+        if (h[1] == 0) {
+            retry.release();
+            return DAB_OK;
+        }
+        Scratch next;
+        if ((rc = next.reserve((size_t)h[1] * 4))) {
+            retry.release();
+            return rc;
+        }
+        DAB_CUDA(cudaMemcpy(next.p, d_counters + 4, (size_t)h[1] * 4, cudaMemcpyDeviceToDevice));
+        retry.release();
+        retry = next;
+        p.query_list = (const uint32_t*)retry.p;
+        p.n_work = h[1];
+        slots *= 4;
+    }
+    retry.release();
+    return fail(DAB_ERR_VISITED_OVERFLOW, "dab_search_batch_pq: visited set still overflowing after 6 passes");
+}
+
+}  // namespace dab
+
+using namespace dab;
+
+extern "C" int dab_search_batch_pq(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search,
+                                   uint32_t beam_width, uint32_t* out_ids, float* out_dists, uint32_t* out_counts,
+                                   uint32_t* out_cmps, uint32_t* out_hops) {
+    if (!idx) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: idx is NULL");
+    if (nq == 0) return DAB_OK;
+    if (!queries || !out_ids || !out_dists) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: NULL argument");
+    if (k == 0) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: k must be > 0");
+    DAB_CUDA(cudaSetDevice(idx->device));
+    const size_t qbytes = (size_t)nq * idx->dim * elem_size(idx->dtype);
+    const size_t rbytes = (size_t)nq * k * 4;
+    int rc;
+    if ((rc = idx->s_queries.reserve(qbytes))) return rc;
+    if ((rc = idx->s_out.reserve(2 * rbytes))) return rc;
+    if ((rc = idx->s_stats.reserve((size_t)nq * 12))) return rc;
+    uint32_t* d_ids = (uint32_t*)idx->s_out.p;
+    float* d_dists = (float*)((uint8_t*)idx->s_out.p + rbytes);
+    uint32_t* d_counts = (uint32_t*)idx->s_stats.p;
+    uint32_t* d_cmps = d_counts + nq;
+    uint32_t* d_hops = d_cmps + nq;
+    DAB_CUDA(cudaMemcpyAsync(idx->s_queries.p, queries, qbytes, cudaMemcpyHostToDevice, idx->stream));
+    if ((rc = run_search_pq(idx, idx->s_queries.p, nq, k, l_search, beam_width, d_ids, d_dists, d_counts, d_cmps, d_hops))) return rc;
+    DAB_CUDA(cudaMemcpyAsync(out_ids, d_ids, rbytes, cudaMemcpyDeviceToHost, idx->stream));
+    DAB_CUDA(cudaMemcpyAsync(out_dists, d_dists, rbytes, cudaMemcpyDeviceToHost, idx->stream));
+    if (out_counts) DAB_CUDA(cudaMemcpyAsync(out_counts, d_counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, idx->stream));
+    if (out_cmps) DAB_CUDA(cudaMemcpyAsync(out_cmps, d_cmps, (size_t)nq * 4, cudaMemcpyDeviceToHost, idx->stream));
+    if (out_hops) DAB_CUDA(cudaMemcpyAsync(out_hops, d_hops, (size_t)nq * 4, cudaMemcpyDeviceToHost, idx->stream));
+    DAB_CUDA(cudaStreamSynchronize(idx->stream));
+    return DAB_OK;
+}

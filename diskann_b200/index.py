@@ -221,6 +221,19 @@ class GpuIndex:
         check(_lib.lib().dab_pq_distances(self._h, _ptr(queries), queries.shape[0], _ptr(ids), ids.shape[1], _ptr(out)))
         return out
 
+    def search_batch_pq(self, queries, k, l_search, beam_width=1):
+        """KNN::search with PQ ADC traversal distances (providers' QuantAccessor)."""
+        queries = self._queries(queries)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), np.uint32)
+        dists = np.empty((nq, k), np.float32)
+        counts = np.empty(nq, np.uint32)
+        cmps = np.empty(nq, np.uint32)
+        hops = np.empty(nq, np.uint32)
+        check(_lib.lib().dab_search_batch_pq(self._h, _ptr(queries), nq, k, l_search, beam_width, _ptr(ids), _ptr(dists),
+                                             _ptr(counts), _ptr(cmps), _ptr(hops)))
+        return ids, dists, counts, cmps, hops
+
     def pq_encode(self, vectors):
         vectors = np.ascontiguousarray(vectors, np.float32)
         out = np.empty((vectors.shape[0], self.pq_chunks), np.uint8)

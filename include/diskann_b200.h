@@ -148,6 +148,18 @@ int dab_pq_populate_lut(dab_index* idx, const float* queries, uint32_t nq, int m
 int dab_pq_distances(dab_index* idx, const float* queries, uint32_t nq, const uint32_t* ids,
                      uint32_t c, float* out);
 
+/* The providers' PQ traversal: QuantAccessor::expand_beam with
+ * `computer.evaluate_similarity(aux_vectors[i])`
+ * (diskann-providers/src/model/graph/provider/async_/inmem/product.rs:311-340) inside
+ * search_internal — dab_search_batch with every traversal distance an ADC lookup over the
+ * uploaded codes (start points included).  Queries have the index dtype and are converted to
+ * f32 (T: Into<f32>); L2 / CosineNormalized use TableL2, InnerProduct TableIP; Metric::Cosine
+ * (DirectCosine, no table) is rejected here — use dab_pq_distances.  No rerank: distances
+ * returned are the ADC values. */
+int dab_search_batch_pq(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search,
+                        uint32_t beam_width, uint32_t* out_ids, float* out_dists,
+                        uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops);
+
 /* BasicTable::compress_into (diskann-quantization/src/product/tables/basic.rs:161-194) for n
  * host vectors (f32): codes [n][n_chunks].  Returns DAB_ERR_INVALID_ARGUMENT if a chunk's
  * minimum distance is infinite/NaN (first offending row/chunk in the message). */

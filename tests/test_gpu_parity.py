@@ -469,3 +469,57 @@ def test_device_build_graph_is_valid_and_searchable(dab, dt, metric, dim, n):
     rec = O.recall(gt_ids, got[0], got[2], 10, 10)
     # reference-quality graph: compare with the oracle's sequential build on a subset size
     assert rec > 0.95, rec
+
+
+# ---------------------------------------------------------------- PQ traversal (C4 shape) and C3 shape
+
+@pytest.mark.parametrize("dt,metric,d,chunks", [(np.int8, O.L2, 128, 32), (np.float32, O.L2, 96, 12), (np.float32, O.INNER_PRODUCT, 64, 16),
+                                                (np.uint8, O.COSINE_NORMALIZED, 40, 7)])
+def test_pq_traversal_search_identical_to_oracle(dab, dt, metric, d, chunks):
+    """dab_search_batch_pq: greedy search whose traversal distances are ADC lookups over the codes
+    (providers' QuantAccessor, product.rs:311-340) == the oracle's search with pq_codes set."""
+    rng = np.random.default_rng(d + chunks)
+    n = 4000
+    vecs, adj, maxdeg = make_index(rng, dt, O.L2 if metric == O.COSINE_NORMALIZED else metric, n, d, 24, 40)
+    f32 = vecs.astype(np.float32)
+    piv = f32[rng.choice(n, 256, replace=False)]
+    off = O.pq_offsets(d, chunks)
+    L = O.lib()
+    codes = np.zeros((n + 1, chunks), np.uint8)
+    for i in range(n + 1):
+        assert L.orc_pq_encode(O.ptr(piv), 256, d, O.ptr(off), chunks, O.ptr(f32[i]), O.ptr(codes[i])) == 0
+    nq = 200
+    queries = vecs[rng.integers(0, n, nq)].copy()
+    oidx = O.Index(vecs, adj, n, 1, metric, pq=(piv, off, codes))
+    with dab.GpuIndex(O.dtype_code(vecs), metric, d, n, 1, maxdeg) as g:
+        g.upload_vectors(vecs)
+        g.upload_graph(adj)
+        g.upload_pq(piv, off, codes)
+        for (k, Ls, beam) in [(10, 30, 1), (5, 64, 2), (10, 150, 1)]:
+            got = g.search_batch_pq(queries, k, Ls, beam)
+            want = oidx.search_batch(queries, k, Ls, beam=beam, threads=4)
+            for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, k, Ls, beam)
+    with dab.GpuIndex(dab.DType.f32, dab.Metric.Cosine, d, n, 1, maxdeg) as g:
+        g.upload_vectors(f32)
+        g.upload_graph(adj)
+        g.upload_pq(piv, off, codes)
+        with pytest.raises(dab.DabError):
+            g.search_batch_pq(f32[:2], 5, 10)  # DirectCosine has no table: rejected loudly
+
+
+def test_search_c3_shape_f16_768_inner_product(dab):
+    """BASELINE config C3 shape (768-d f16, inner product) at test size through the v2 kernel."""
+    rng = np.random.default_rng(768)
+    n, d = 3000, 768
+    vecs, adj, maxdeg = make_index(rng, np.float16, O.INNER_PRODUCT, n, d, 32, 50)
+    queries = vecs[rng.integers(0, n, 64)].copy()
+    oidx = O.Index(vecs, adj, n, 1, O.INNER_PRODUCT)
+    with dab.GpuIndex(dab.DType.f16, dab.Metric.InnerProduct, d, n, 1, maxdeg) as g:
+        g.upload_vectors(vecs)
+        g.upload_graph(adj)
+        for (k, Ls) in [(10, 100), (10, 200)]:
+            got = g.search_batch(queries, k, Ls, 1)
+            want = oidx.search_batch(queries, k, Ls, threads=4)
+            for a, b in zip(got, want):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
