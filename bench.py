@@ -138,6 +138,7 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = WORKLOADS[args.workload]
     n, dim, nq, R = cfg["n"], cfg["dim"], cfg["nq"], cfg["R"]
@@ -153,7 +154,10 @@ def run_gpu(args):
     g = dab.GpuIndex(dab.DType.f32, dab.Metric.L2, dim, n, 1, md, device=local)
     g.upload_vectors(base)
     g.upload_vectors(medoid[None, :], first=n)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch and the library, so the CUDA events below are
+    # recorded on the stream the kernels are launched on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     g.set_stream(stream.cuda_stream)
 
     # index: built once on rank 0 with the device build, replicated with one NCCL broadcast
