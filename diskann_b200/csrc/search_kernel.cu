@@ -22,6 +22,7 @@
 // bytes for ~2-3 flop/element — no tensor cores.
 #include "dab_common.cuh"
 #include "distance_device.cuh"
+#include "search_v2.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -335,47 +336,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) search_kernel(const SearchP
 // ------------------------------------------------------------------ host side
 
 // search_kernel_v2.cu
-struct SearchParamsV2 {
-    const uint8_t* vectors;
-    size_t row_stride;
-    const uint32_t* adj;
-    uint32_t adj_stride;
-    uint64_t n_points;
-    uint32_t n_start;
-    uint32_t dim;
-    uint32_t max_degree;
-    const void* queries;
-    const uint32_t* query_rows;
-    const uint32_t* query_list;
-    uint32_t n_work;
-    uint32_t k, cap, beam;
-    uint32_t* out_ids;
-    float* out_dists;
-    uint32_t* out_counts;
-    uint32_t* out_cmps;
-    uint32_t* out_hops;
-    uint32_t* tables;
-    uint32_t n_buckets;
-    uint32_t* counters;
-    uint32_t* overflow_list;
-    uint32_t* rec_ids;
-    float* rec_dists;
-    uint32_t* rec_counts;
-    uint32_t rec_cap;
-    uint32_t warp_smem, off_q, off_qd, off_qi, off_cid, off_cd, off_beam, off_rows;
-    uint32_t row_bytes, row_slot, stage_rows;
-    unsigned long long* phase_cycles;
-};
-struct V2Launch {
-    void (*kern)(const SearchParamsV2);
-    size_t smem_block;
-    int grid;
-};
-int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchParamsV2& p, V2Launch& out);
-#ifndef DAB_V2_WARPS
-#define DAB_V2_WARPS 1
-#endif
-constexpr int kV2WarpsHost = DAB_V2_WARPS;
+constexpr int kV2WarpsHost = kV2Warps;
 
 static uint32_t next_pow2_log2(uint64_t v) {
     uint32_t l = 0;
@@ -387,6 +348,7 @@ static uint32_t next_pow2_log2(uint64_t v) {
 // 4-byte probes, while vector rows stream through.  cudaAccessPolicyWindow on the stream.
 static void pin_tables_in_l2(dab_index* idx, size_t bytes) {
     if (idx->l2_window_ptr == idx->s_tables.p && idx->l2_window_bytes == bytes && idx->l2_window_stream == idx->stream) return;
+    if (getenv("DAB_NO_L2_WINDOW")) return;  // tuning aid
     int max_persist = 0, max_window = 0;
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, idx->device);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, idx->device);

@@ -122,11 +122,7 @@ __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchPa
             }
             qf[e] = v;
         }
-        {
-            const uint4 e4 = make_uint4(kEmptyV2, kEmptyV2, kEmptyV2, kEmptyV2);
-            uint4* t4 = reinterpret_cast<uint4*>(table);
-            for (uint32_t i = lane; i < nbk * 2; i += 32) t4[i] = e4;
-        }
+        for (uint32_t i = lane; i < nbk; i += 32) store_empty_bucket(table + (size_t)i * 8);
         __syncwarp();
         for (uint32_t t = lane; t < entries; t += 32) {
             const uint32_t chunk = t / p.n_centers, center = t % p.n_centers;
@@ -149,8 +145,9 @@ __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchPa
                 const uint32_t id = (uint32_t)p.n_points + s0 + lane;
                 cid[lane] = id;
                 const uint32_t b = bucket_of(id, nbk);
-                const uint4* bp = reinterpret_cast<const uint4*>(table + (size_t)b * 8);
-                bucket_insert(table, nbk, b, __ldcg(bp), __ldcg(bp + 1), id);
+                uint32_t bs[8];
+                load_bucket(table + (size_t)b * 8, bs);
+                bucket_insert(table, nbk, b, bs, id);
             }
             __syncwarp();
             adc(n);
@@ -188,8 +185,9 @@ __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchPa
                     bool inserted = false;
                     if (j >= 1 && j <= deg) {
                         const uint32_t b2 = bucket_of(word, nbk);
-                        const uint4* bp = reinterpret_cast<const uint4*>(table + (size_t)b2 * 8);
-                        inserted = bucket_insert(table, nbk, b2, __ldcg(bp), __ldcg(bp + 1), word);
+                        uint32_t bs[8];
+                        load_bucket(table + (size_t)b2 * 8, bs);
+                        inserted = bucket_insert(table, nbk, b2, bs, word);
                     }
                     const bool isnew = inserted && word < n_total;
                     const unsigned mi = __ballot_sync(kFull, inserted);

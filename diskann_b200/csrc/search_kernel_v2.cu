@@ -6,7 +6,8 @@
 // results; what changes is how many dependent memory round trips a hop costs:
 //
 //   * rows of the surviving candidates of a hop are staged in shared memory with cp.async
-//     (16 B per lane: one warp instruction moves a 512 B row, no registers tied up), a stage of
+//     (16 B per lane, eight lanes per row: one warp instruction moves 128 B of four rows and no
+//     lane needs another lane's address; no registers tied up), a stage of
 //     rows in flight at once (a TMA bulk-copy variant was measured slower: UBLKCP takes
 //     warp-uniform operands, so per-row copies serialise);
 //   * distances are computed from shared memory (lane s <-> SIMD slot s, conflict-free) for 8
@@ -19,52 +20,23 @@
 #include "dab_common.cuh"
 #include "distance_device.cuh"
 #include "search_common.cuh"
+#include "search_v2.cuh"
 
 #include <algorithm>
 #include <cstdlib>
 
 namespace dab {
 
-#ifndef DAB_V2_WARPS
-#define DAB_V2_WARPS 1
-#endif
-constexpr int kV2Warps = DAB_V2_WARPS;  // warps per CTA (each warp owns a query)
 constexpr int kGroup = 8;  // rows reduced together
-
-struct SearchParamsV2 {
-    const uint8_t* vectors;
-    size_t row_stride;
-    const uint32_t* adj;
-    uint32_t adj_stride;
-    uint64_t n_points;
-    uint32_t n_start;
-    uint32_t dim;
-    uint32_t max_degree;
-    const void* queries;
-    const uint32_t* query_rows;
-    const uint32_t* query_list;
-    uint32_t n_work;
-    uint32_t k, cap, beam;
-    uint32_t* out_ids;
-    float* out_dists;
-    uint32_t* out_counts;
-    uint32_t* out_cmps;
-    uint32_t* out_hops;
-    uint32_t* tables;
-    uint32_t n_buckets;   // visited table: buckets of 8 ids (32 B) per warp, any count >= 16
-    uint32_t* counters;
-    uint32_t* overflow_list;
-    uint32_t* rec_ids;
-    float* rec_dists;
-    uint32_t* rec_counts;
-    uint32_t rec_cap;
-    // per-warp shared memory layout (bytes)
-    uint32_t warp_smem, off_q, off_qd, off_qi, off_cid, off_cd, off_beam, off_rows;
-    uint32_t row_bytes;   // bytes copied per row (multiple of 16)
-    uint32_t row_slot;    // bytes between staged rows
-    uint32_t stage_rows;  // rows staged per round (multiple of kGroup)
-    unsigned long long* phase_cycles;  // optional [8] per-phase cycle sums (profiling aid)
-};
+#ifndef DAB_V2_COPY8
+#define DAB_V2_COPY8 1     // row copies: eight lanes per row (0: whole warp per row)
+#endif
+#ifndef DAB_V2_ADJ_SMEM
+#define DAB_V2_ADJ_SMEM 1  // speculative adjacency row into shared memory (0: L2 prefetch)
+#endif
+#ifndef DAB_V2_F32X2
+#define DAB_V2_F32X2 1     // packed FADD2 / FFMA2 distance arithmetic
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -82,15 +54,52 @@ __device__ __forceinline__ void bfly8(float (&v)[kGroup], int lane, int bit) {
     }
 }
 
+// Packed f32x2 arithmetic (FADD2 / FFMA2 on sm_100): each half is an IEEE round-to-nearest
+// operation, so a pair of rows advances with one instruction and the same bits as two scalar ones.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+template <int KIND>
+__device__ __forceinline__ uint64_t step2(uint64_t acc, uint64_t x2, uint64_t y2) {
+    if (KIND == KIND_L2) {
+        uint64_t c2;
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c2) : "l"(x2), "l"(y2));
+        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(acc) : "l"(c2), "l"(acc));
+    } else {
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(acc) : "l"(x2), "l"(y2), "l"(acc));
+    }
+    return acc;
+}
+
 // distances of 8 staged rows (shared memory) against the query (shared memory, f32); returns on
 // every lane the value of row u = ((lane>>3)&1)<<2 | ((lane>>4)&1)<<1 | ((lane>>2)&1)
 template <typename TD, int KIND>
 __device__ __forceinline__ float group_distance(const float* __restrict__ q, const uint8_t* __restrict__ rows,
                                                 uint32_t row_slot, int dim, int lane) {
+    const int full8 = dim & ~7, rem = dim & 7;
     float v[kGroup];
+#if DAB_V2_F32X2
+    uint64_t v2[kGroup / 2];
+#pragma unroll
+    for (int g = 0; g < kGroup / 2; ++g) v2[g] = 0ull;
+    for (int e = lane; e < full8; e += 32) {
+        const float x = q[e];
+        const uint64_t x2 = pack2(x, x);
+#pragma unroll
+        for (int g = 0; g < kGroup / 2; ++g) {
+            const float y0 = to_f32(reinterpret_cast<const TD*>(rows + (size_t)(2 * g) * row_slot)[e]);
+            const float y1 = to_f32(reinterpret_cast<const TD*>(rows + (size_t)(2 * g + 1) * row_slot)[e]);
+            v2[g] = step2<KIND>(v2[g], x2, pack2(y0, y1));
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < kGroup / 2; ++g) unpack2(v2[g], v[2 * g], v[2 * g + 1]);
+#else
 #pragma unroll
     for (int g = 0; g < kGroup; ++g) v[g] = 0.0f;
-    const int full8 = dim & ~7, rem = dim & 7;
     for (int e = lane; e < full8; e += 32) {
         const float x = q[e];
 #pragma unroll
@@ -104,6 +113,7 @@ __device__ __forceinline__ float group_distance(const float* __restrict__ q, con
             }
         }
     }
+#endif
     bfly8<8>(v, lane, 8);
     bfly8<4>(v, lane, 16);
     if (rem) {
@@ -146,6 +156,8 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
     uint32_t* beam_ids = reinterpret_cast<uint32_t*>(base + p.off_beam);
     uint8_t* rows = base + p.off_rows;
     const uint32_t rows_a = smem_u32(rows);
+    uint32_t* adjbuf = reinterpret_cast<uint32_t*>(base + p.off_adj);
+    const uint32_t adjbuf_a = smem_u32(adjbuf);
 
     const uint32_t warp_slot = blockIdx.x * kV2Warps + wib;
     const uint32_t nbk = p.n_buckets;
@@ -153,6 +165,12 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
     const uint32_t hlimit = nbk * 7;  // 87.5 % load: 8-way buckets stay short
     const uint64_t n_total = p.n_points + p.n_start;
     const int dim = (int)p.dim;
+#if DAB_L2_HINTS
+    // vector rows stream through L2 (a row is read once per query): evict them first so the
+    // visited tables, which are re-probed every hop, stay resident
+    uint64_t row_policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(row_policy));
+#endif
 
     for (;;) {
         uint32_t w = 0;
@@ -181,26 +199,37 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
             const TD* s = p.query_rows ? reinterpret_cast<const TD*>(p.vectors + (size_t)p.query_rows[qidx] * p.row_stride)
                                        : reinterpret_cast<const TD*>(p.queries) + (size_t)qidx * dim;
             for (int e = lane; e < dim; e += 32) qf[e] = to_f32(s[e]);
-            uint4 e4 = make_uint4(kEmptyV2, kEmptyV2, kEmptyV2, kEmptyV2);
-            uint4* t4 = reinterpret_cast<uint4*>(table);
-            for (uint32_t i = lane; i < nbk * 2; i += 32) t4[i] = e4;
+            for (uint32_t i = lane; i < nbk; i += 32) store_empty_bucket(table + (size_t)i * 8);
         }
         __syncwarp();
         DAB_PHASE(0);  // query staging + table clear
 
         uint32_t size = 0, cursor_lo = 0, cmps = 0, hops = 0, nvisited = 0, nrec = 0;
+        uint32_t pred = kEmptyV2;  // node whose adjacency row sits in adjbuf
         bool overflow = false;
 
         // stage `n` candidate rows (ids cid[c0..)) with per-lane 16 B async copies (one warp
         // instruction moves 512 B of a row) and compute their distances into cd[]
         auto distances = [&](uint32_t c0, uint32_t n) {
-            const uint32_t myid = (uint32_t)lane < n ? cid[c0 + lane] : 0;  // n <= stage_rows <= 32
-#pragma unroll 4
-            for (uint32_t j = 0; j < n; ++j) {
-                const uint8_t* src = p.vectors + (size_t)__shfl_sync(kFull, myid, j) * p.row_stride;
-                for (uint32_t off = lane * 16; off < p.row_bytes; off += 512)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rows_a + j * p.row_slot + off), "l"(src + off)
+            // eight lanes per row, 16 B each: one warp instruction moves 128 B of four different
+            // rows, and every lane forms its own source address (no cross-lane traffic)
+#if DAB_V2_COPY8
+            const uint32_t sub = (uint32_t)lane >> 3, nsub = 4, off0 = ((uint32_t)lane & 7u) * 16u, offs = 128;
+#else
+            const uint32_t sub = 0, nsub = 1, off0 = (uint32_t)lane * 16u, offs = 512;
+#endif
+            for (uint32_t j = sub; j < n; j += nsub) {
+                const uint8_t* src = p.vectors + (size_t)cid[c0 + j] * p.row_stride;
+                const uint32_t dst = rows_a + j * p.row_slot;
+                for (uint32_t off = off0; off < p.row_bytes; off += offs) {
+#if DAB_L2_HINTS
+                    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + off), "l"(src + off),
+                                 "l"(row_policy)
                                  : "memory");
+#else
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(src + off) : "memory");
+#endif
+                }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             DAB_PHASE(3);  // issue of the row copies
@@ -222,8 +251,9 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                 const uint32_t id = (uint32_t)p.n_points + s0 + lane;
                 cid[lane] = id;
                 const uint32_t b = bucket_of(id, nbk);
-                const uint4* bp = reinterpret_cast<const uint4*>(table + (size_t)b * 8);
-                bucket_insert(table, nbk, b, __ldcg(bp), __ldcg(bp + 1), id);
+                uint32_t bs[8];
+                load_bucket(table + (size_t)b * 8, bs);
+                bucket_insert(table, nbk, b, bs, id);
             }
             __syncwarp();
             for (uint32_t c0 = 0; c0 < n; c0 += p.stage_rows) distances(c0, min(p.stage_rows, n - c0));
@@ -255,41 +285,65 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                 __syncwarp();
             }
             if (nb == 0) break;
-            {
-                // speculative: the next hop most likely expands the now-first unvisited entry
-                const uint32_t nxt = first_unvisited(qi, cursor_lo, lim, lane);
-                if (nxt < lim && lane < 3) prefetch_l2(p.adj + (size_t)(qi[nxt] & ~kFlagV2) * p.adj_stride + lane * 32);
-            }
-            DAB_PHASE(1);  // selection + prefetch
+            DAB_PHASE(1);  // selection
 
             uint32_t ncand = 0;
             for (uint32_t b = 0; b < nb; ++b) {
                 const uint32_t node = beam_ids[b];
                 const uint32_t* row = p.adj + (size_t)node * p.adj_stride;
                 uint32_t wd[3];
-                wd[0] = __ldg(row + lane);
-                wd[1] = 32 + lane < p.adj_stride ? __ldg(row + 32 + lane) : kEmptyV2;
-                wd[2] = 64 + lane < p.adj_stride ? __ldg(row + 64 + lane) : kEmptyV2;
+                if (b == 0 && p.adj_words) {
+                    // the speculative copy of the previous hop has long landed; it must be
+                    // drained before the buffer is read or re-targeted
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                }
+                if (b == 0 && node == pred) {
+                    wd[0] = adjbuf[lane];
+                    wd[1] = 32 + lane < p.adj_words ? adjbuf[32 + lane] : kEmptyV2;
+                    wd[2] = 64 + lane < p.adj_words ? adjbuf[64 + lane] : kEmptyV2;
+                    __syncwarp();
+                } else {
+                    wd[0] = __ldg(row + lane);
+                    wd[1] = 32 + lane < p.adj_stride ? __ldg(row + 32 + lane) : kEmptyV2;
+                    wd[2] = 64 + lane < p.adj_stride ? __ldg(row + 64 + lane) : kEmptyV2;
+                }
+                if (b == 0) {
+                    // speculative: the next hop most likely expands the now-first unvisited entry;
+                    // fetch its adjacency row into shared memory (or at least into L2) while
+                    // this hop runs
+                    const uint32_t nxt = first_unvisited(qi, cursor_lo, lim, lane);
+                    pred = kEmptyV2;
+                    if (nxt < lim) {
+                        const uint32_t nid = qi[nxt] & ~kFlagV2;
+                        const uint32_t* nrow = p.adj + (size_t)nid * p.adj_stride;
+                        if (p.adj_words) {
+                            pred = nid;
+                            if ((uint32_t)lane * 4 < p.adj_words)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(adjbuf_a + lane * 16), "l"(nrow + lane * 4)
+                                             : "memory");
+                            asm volatile("cp.async.commit_group;" ::: "memory");
+                        } else if (lane < 3) {
+                            prefetch_l2(nrow + lane * 32);
+                        }
+                    }
+                }
                 const uint32_t deg = min(__shfl_sync(kFull, wd[0], 0), p.max_degree);
                 // bucket probes of all three chunks in flight together
                 bool valid[3];
                 uint32_t bk[3];
-                uint4 lo4[3], hi4[3];
+                uint32_t bs[3][8];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const uint32_t j = c * 32 + lane;
                     valid[c] = j >= 1 && j <= deg;
                     bk[c] = bucket_of(wd[c], nbk);
-                    if (valid[c]) {
-                        const uint4* bp = reinterpret_cast<const uint4*>(table + (size_t)bk[c] * 8);
-                        lo4[c] = __ldcg(bp);
-                        hi4[c] = __ldcg(bp + 1);
-                    }
+                    if (valid[c]) load_bucket(table + (size_t)bk[c] * 8, bs[c]);
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     bool inserted = false;
-                    if (valid[c]) inserted = bucket_insert(table, nbk, bk[c], lo4[c], hi4[c], wd[c]);
+                    if (valid[c]) inserted = bucket_insert(table, nbk, bk[c], bs[c], wd[c]);
                     const bool isnew = inserted && wd[c] < n_total;  // is_in_bounds
                     const unsigned mi = __ballot_sync(kFull, inserted);
                     const unsigned mn = __ballot_sync(kFull, isnew);
@@ -304,8 +358,9 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                     bool inserted = false;
                     if (j <= deg) {
                         const uint32_t b2 = bucket_of(word, nbk);
-                        const uint4* bp = reinterpret_cast<const uint4*>(table + (size_t)b2 * 8);
-                        inserted = bucket_insert(table, nbk, b2, __ldcg(bp), __ldcg(bp + 1), word);
+                        uint32_t bs2[8];
+                        load_bucket(table + (size_t)b2 * 8, bs2);
+                        inserted = bucket_insert(table, nbk, b2, bs2, word);
                     }
                     const bool isnew = inserted && word < n_total;
                     const unsigned mi = __ballot_sync(kFull, inserted);
@@ -378,12 +433,6 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
 }
 
 // ------------------------------------------------------------------ host side
-struct V2Launch {
-    void (*kern)(const SearchParamsV2);
-    size_t smem_block;
-    int grid;
-};
-
 // Returns 1 when this configuration is not covered by v2 (caller falls back to v1), 0 on
 // success with `out` filled, or a negative DAB error code.
 int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchParamsV2& p, V2Launch& out) {
@@ -406,7 +455,11 @@ int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchPar
     off += round_up(std::max<size_t>(ncand_max, idx->n_start) * 4, 16);
     p.off_beam = (uint32_t)off;
     off += round_up((size_t)beam * 4, 16);
-    const size_t cap_pad = round_up(cap, 32) + 32;
+    // speculative adjacency buffer: the first <= 96 words of a row, 16-byte granules
+    p.adj_words = DAB_V2_ADJ_SMEM && idx->adj_stride % 4 == 0 ? (uint32_t)std::min<size_t>(idx->adj_stride, 96) : 0;
+    p.off_adj = (uint32_t)off;
+    off += (size_t)p.adj_words * 4;
+    const size_t cap_pad = round_up(cap, 4);
     p.off_qd = (uint32_t)off;
     off += cap_pad * 4;
     p.off_qi = (uint32_t)off;
