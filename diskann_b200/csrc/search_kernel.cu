@@ -346,16 +346,29 @@ static uint32_t next_pow2_log2(uint64_t v) {
 
 // Keep the visited tables L2-resident: they are hit ~max_degree times per hop with random
 // 4-byte probes, while vector rows stream through.  cudaAccessPolicyWindow on the stream.
+// The generic kernel keeps its tables L2-resident with a persisting access-policy window on the
+// stream; search_kernel_v2 marks its table accesses evict_last / row copies evict_first per
+// instruction instead (search_common.cuh) and runs measurably slower with the window on top, so
+// the window is dropped (`bytes == 0`) whenever v2 is dispatched.
 static void pin_tables_in_l2(dab_index* idx, size_t bytes) {
-    if (idx->l2_window_ptr == idx->s_tables.p && idx->l2_window_bytes == bytes && idx->l2_window_stream == idx->stream) return;
-    if (getenv("DAB_NO_L2_WINDOW")) return;  // tuning aid
+    void* want = bytes ? idx->s_tables.p : nullptr;
+    if (idx->l2_window_ptr == want && idx->l2_window_bytes == bytes && (bytes == 0 || idx->l2_window_stream == idx->stream)) return;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (bytes == 0) {
+        attr.accessPolicyWindow.num_bytes = 0;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        if (cudaStreamSetAttribute(idx->l2_window_stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+        idx->l2_window_ptr = nullptr;
+        idx->l2_window_bytes = 0;
+        return;
+    }
     int max_persist = 0, max_window = 0;
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, idx->device);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, idx->device);
     if (max_persist <= 0 || max_window <= 0) return;
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
-    cudaStreamAttrValue attr;
-    memset(&attr, 0, sizeof(attr));
     attr.accessPolicyWindow.base_ptr = idx->s_tables.p;
     attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)max_window);
     attr.accessPolicyWindow.hitRatio = bytes <= (size_t)max_persist ? 1.0f : (float)((double)max_persist / (double)bytes);
@@ -543,7 +556,7 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
         }
         p.tables = (uint32_t*)idx->s_tables.p;
         p.hcap_log2 = hlog;
-        pin_tables_in_l2(idx, (size_t)warps * words_per_warp * 4);
+        pin_tables_in_l2(idx, use_v2 ? 0 : (size_t)warps * words_per_warp * 4);
         DAB_CUDA(cudaMemsetAsync(d_counters, 0, 16, idx->stream));
         int launch_grid = (int)std::min<uint64_t>((uint64_t)grid, ((uint64_t)p.n_work + kSearchWarps - 1) / kSearchWarps);
         if (use_v2) {

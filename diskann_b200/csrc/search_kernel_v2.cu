@@ -218,17 +218,25 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
 #else
             const uint32_t sub = 0, nsub = 1, off0 = (uint32_t)lane * 16u, offs = 512;
 #endif
-            for (uint32_t j = sub; j < n; j += nsub) {
-                const uint8_t* src = p.vectors + (size_t)cid[c0 + j] * p.row_stride;
-                const uint32_t dst = rows_a + j * p.row_slot;
-                for (uint32_t off = off0; off < p.row_bytes; off += offs) {
+            auto copy16 = [&](uint32_t dst, const uint8_t* src) {
 #if DAB_L2_HINTS
-                    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + off), "l"(src + off),
-                                 "l"(row_policy)
-                                 : "memory");
+                asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(row_policy) : "memory");
 #else
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(src + off) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 #endif
+            };
+            if (p.row_bytes == 4 * offs) {  // 128-d f32 / 256-d f16 rows: fixed trip count, immediate offsets
+                for (uint32_t j = sub; j < n; j += nsub) {
+                    const uint8_t* src = p.vectors + (size_t)cid[c0 + j] * p.row_stride + off0;
+                    const uint32_t dst = rows_a + j * p.row_slot + off0;
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k) copy16(dst + k * offs, src + k * offs);
+                }
+            } else {
+                for (uint32_t j = sub; j < n; j += nsub) {
+                    const uint8_t* src = p.vectors + (size_t)cid[c0 + j] * p.row_stride;
+                    const uint32_t dst = rows_a + j * p.row_slot;
+                    for (uint32_t off = off0; off < p.row_bytes; off += offs) copy16(dst + off, src + off);
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
