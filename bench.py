@@ -138,7 +138,7 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL logs, stdout stays the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = WORKLOADS[args.workload]
     n, dim, nq, R = cfg["n"], cfg["dim"], cfg["nq"], cfg["R"]
@@ -306,7 +306,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": nq * K * 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "kernel": "search_kernel<float,4,L2>",
+                         "traffic": ncu_traffic(), "kernel": "search_kernel_v2<float,L2,QT=4>",
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "note": "achieved = algorithmic bytes (cmps*520 + hops*336 + 512 + k*8 per query, run's own counters) "
                                  "/ CUDA-event step time on this rank"},
@@ -380,14 +380,18 @@ def run_reference(args):
     g.build(R, cfg["l_build"], ALPHA)
     adj = g.download_graph()
     gt_ids, _ = g.flat_knn(queries, K)
-    l_search = args.l_search
-    if not l_search:
-        for L in L_SWEEP:
-            ids, _, counts, _, _ = g.search_batch(queries, K, L, 1)
-            hits = sum(len(set(gt_ids[i].tolist()) & set(ids[i, :counts[i]].tolist())) for i in range(nq))
-            l_search = L
-            if hits / (nq * K) >= TARGET_RECALL:
-                break
+    # the same L as the GPU arm: BASELINE.json configs[1] names L_search=100; a larger L only if
+    # that misses the recall target (the search is deterministic, so the device sweep decides)
+    l_search = args.l_search or cfg.get("l_search", 100)
+    min_l = None
+    for L in L_SWEEP:
+        ids, _, counts, _, _ = g.search_batch(queries, K, L, 1)
+        hits = sum(len(set(gt_ids[i].tolist()) & set(ids[i, :counts[i]].tolist())) for i in range(nq))
+        min_l = L
+        if hits / (nq * K) >= TARGET_RECALL:
+            break
+    if min_l > l_search and not args.l_search:
+        l_search = min_l
     g.close()
     O, oidx = cpu_search_setup(base, medoid, adj, n)
     threads = O.lib().orc_hardware_threads()
@@ -405,7 +409,7 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": args.workload, "n_points": n, "dim": dim, "queries": nq, "l_search": l_search, "k": K,
                    "recall_at_10": round(O.recall(gt_ids, ids, counts, K, K), 5), "mean_cmps": float(cmps.mean()),
-                   "mean_hops": float(hops.mean())},
+                   "mean_hops": float(hops.mean()), "min_l_for_target_recall": min_l},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                          "sample": f"each step = the full {nq}-query batch on {threads} threads (contiguous partitions)"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -71,7 +71,9 @@ __device__ __forceinline__ float combine_acc(float a) {
 // must call this together.  `slot` = lane index inside the team.  q: query elements
 // (shared or global memory), rows[u]: global rows.  Returns the mathematical value
 // (pre post-op) of row u in out[u] on every lane of the team.
-template <int NA, int KIND, int U, typename TQ, typename TD>
+// EU: unroll factor of the element loop — EU * U independent row loads in flight per lane (the
+// pure gather kernels need the memory-level parallelism; the search kernels keep registers).
+template <int NA, int KIND, int U, int EU = 1, typename TQ, typename TD>
 __device__ __forceinline__ void team_float_multi(const TQ* __restrict__ q,
                                                  const TD* const (&rows)[U], int dim, int slot,
                                                  float (&out)[U]) {
@@ -82,6 +84,7 @@ __device__ __forceinline__ void team_float_multi(const TQ* __restrict__ q,
         float nx = 0.0f, ny[U], xy[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) ny[u] = xy[u] = 0.0f;
+#pragma unroll(EU)
         for (int e = slot; e < full8; e += S) {
             float x = to_f32(q[e]);
             float y[U];
@@ -118,6 +121,7 @@ __device__ __forceinline__ void team_float_multi(const TQ* __restrict__ q,
         float acc[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) acc[u] = 0.0f;
+#pragma unroll(EU)
         for (int e = slot; e < full8; e += S) {
             float x = to_f32(q[e]);
             float y[U];

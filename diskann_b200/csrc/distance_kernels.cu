@@ -100,7 +100,7 @@ frontier_float_kernel(const TQG* __restrict__ queries, uint32_t nq, const uint32
                 rows[u] = reinterpret_cast<const TD*>(vectors + (size_t)(ok[u] ? id : 0) * row_stride);
             }
             float r[U];
-            team_float_multi<NA, KIND, U>(q, rows, dim, slot, r);
+            team_float_multi<NA, KIND, U, 4>(q, rows, dim, slot, r);
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (slot == 0 && jj[u] < jend) out[(size_t)qi * c + jj[u]] = ok[u] ? post_op<POST>(r[u]) : __int_as_float(0x7FC00000);
