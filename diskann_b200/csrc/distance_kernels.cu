@@ -108,6 +108,119 @@ frontier_float_kernel(const TQG* __restrict__ queries, uint32_t nq, const uint32
     }
 }
 
+// Wide-load variant for the NA = 4 schemas (L2 / InnerProduct / CosineNormalized over f32 or
+// f16 rows against an f32 query): every lane reads 16 contiguous bytes of its row per step
+// (8 f16 = all eight slots of one accumulator; 4 f32 = half of them) and runs those slots'
+// sequential FMA chains itself, so a row needs only 4 (f16) or 8 (f32) lanes and a warp works on
+// 8 or 4 rows at once with LDG.128 instead of 2- / 4-byte loads.  Same association as
+// team_float_multi: block k of 8 elements goes to accumulator k mod 4, accumulators are combined
+// (s0+s1)+(s2+s3) with xor-shuffles, the zero-filled remainder is applied to the combined
+// vector, then sum_tree ((x0+x4)+(x2+x6))+((x1+x5)+(x3+x7)).
+template <typename TQG, typename TD, int KIND, int POST>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+frontier_wide_kernel(const TQG* __restrict__ queries, uint32_t nq, const uint32_t* __restrict__ ids, uint32_t c,
+                     const uint8_t* __restrict__ vectors, size_t row_stride, uint64_t n_total, int dim, int qstride,
+                     float* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int EPL = 16 / (int)sizeof(TD);  // elements per 16-byte load: 8 (f16) or 4 (f32)
+    constexpr int LPR = 32 / EPL;              // lanes per row: 4 or 8
+    constexpr int ROWS = EPL;                  // rows per warp pass: 8 or 4
+    constexpr int HALVES = 8 / EPL;            // lanes sharing one accumulator: 1 or 2
+    constexpr int TILE = 32;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int team = lane / LPR, tl = lane % LPR;
+    const int a = tl / HALVES, h = tl % HALVES;
+    float* q = reinterpret_cast<float*>(smem) + (size_t)wib * qstride;
+    const int nb8 = dim >> 3, full8 = dim & ~7, rem = dim & 7;
+    const uint32_t tiles_per_q = (c + TILE - 1) / TILE;
+    const uint64_t total_tiles = (uint64_t)nq * tiles_per_q;
+    const uint64_t nwarps = (uint64_t)gridDim.x * kWarpsPerBlock;
+    for (uint64_t t = (uint64_t)blockIdx.x * kWarpsPerBlock + wib; t < total_tiles; t += nwarps) {
+        const uint32_t qi = (uint32_t)(t / tiles_per_q);
+        const uint32_t j0 = (uint32_t)(t % tiles_per_q) * TILE;
+        __syncwarp();
+        for (int e = lane; e < qstride; e += 32) q[e] = e < dim ? to_f32(queries[(size_t)qi * dim + e]) : 0.0f;
+        __syncwarp();
+        const uint32_t jend = min(j0 + TILE, c);
+        for (uint32_t j = j0; j < jend; j += ROWS) {
+            const uint32_t jj = j + team;
+            const uint32_t id = jj < jend ? ids[(size_t)qi * c + jj] : kNoId;
+            const bool ok = id != kNoId && id < n_total;
+            const uint8_t* row = vectors + (size_t)(ok ? id : 0) * row_stride;
+            float acc[EPL];
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) acc[i] = 0.0f;
+#pragma unroll 4
+            for (int k = a; k < nb8; k += 4) {
+                const int e0 = 8 * k + EPL * h;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + (size_t)e0 * sizeof(TD)));
+                float y[EPL];
+                if constexpr (sizeof(TD) == 2) {
+                    const __half2* hp = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = __half22float2(hp[i]);
+                        y[2 * i] = f.x;
+                        y[2 * i + 1] = f.y;
+                    }
+                } else {
+                    y[0] = __uint_as_float(v.x), y[1] = __uint_as_float(v.y), y[2] = __uint_as_float(v.z), y[3] = __uint_as_float(v.w);
+                }
+#pragma unroll
+                for (int i = 0; i < EPL; i += 4) {
+                    const float4 x = *reinterpret_cast<const float4*>(q + e0 + i);
+                    const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (KIND == KIND_L2) {
+                            const float d = __fsub_rn(xs[u], y[i + u]);
+                            acc[i + u] = __fmaf_rn(d, d, acc[i + u]);
+                        } else {
+                            acc[i + u] = __fmaf_rn(xs[u], y[i + u], acc[i + u]);
+                        }
+                    }
+                }
+            }
+            // (s0 + s1) + (s2 + s3), slot-wise
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                acc[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], HALVES));
+                acc[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], 2 * HALVES));
+            }
+            if (rem) {  // zero-filled tail on the combined vector (simd.rs:733-744)
+                const TD* tail = reinterpret_cast<const TD*>(row) + full8;
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) {
+                    const int l = EPL * h + i;
+                    const float x = l < rem ? q[full8 + l] : 0.0f;
+                    const float yv = l < rem ? ldg_elem(tail + l) : 0.0f;
+                    if (KIND == KIND_L2) {
+                        const float d = __fsub_rn(x, yv);
+                        acc[i] = __fmaf_rn(d, d, acc[i]);
+                    } else {
+                        acc[i] = __fmaf_rn(x, yv, acc[i]);
+                    }
+                }
+            }
+            float r;
+            if constexpr (HALVES == 1) {
+                r = __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[4]), __fadd_rn(acc[2], acc[6])),
+                              __fadd_rn(__fadd_rn(acc[1], acc[5]), __fadd_rn(acc[3], acc[7])));
+            } else {
+                float tsum[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    // x_i + x_{i+4}: the partner lane holds the other half of the slots
+                    const float other = __shfl_xor_sync(kFull, acc[i], 1);
+                    tsum[i] = h == 0 ? __fadd_rn(acc[i], other) : __fadd_rn(other, acc[i]);
+                }
+                r = __fadd_rn(__fadd_rn(tsum[0], tsum[2]), __fadd_rn(tsum[1], tsum[3]));
+            }
+            if (tl == 0 && jj < jend) out[(size_t)qi * c + jj] = ok ? post_op<POST>(r) : __int_as_float(0x7FC00000);
+        }
+    }
+}
+
 template <bool SIGNED, int KIND, int POST, int U>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 frontier_int_kernel(const uint8_t* __restrict__ queries, uint32_t nq, const uint32_t* __restrict__ ids, uint32_t c,
@@ -273,6 +386,33 @@ int launch_frontier(const dab_index* idx, const void* d_queries, uint32_t nq, co
     if (smem > 200 * 1024) return fail(DAB_ERR_INVALID_ARGUMENT, "dim %d too large for the frontier kernel", dim);
     cudaStream_t st = idx->stream;
     constexpr int U = 4;
+    // NA = 4 schemas over f32 / f16 rows: the wide-load kernel (16 B per lane)
+    const bool wide = plan.kind != KIND_COS && (idx->dtype == DAB_F32 || idx->dtype == DAB_F16) && idx->row_stride % 16 == 0 &&
+                      !getenv("DAB_FRONTIER_NARROW");  // env: tuning aid, forces the 4-byte-load kernel
+    if (wide) {
+        const int qstride = (dim + 3) & ~3;
+        const size_t wsmem = (size_t)kWarpsPerBlock * qstride * 4;
+#define LW(TQ, TDD, K, P)                                                                                          \
+    do {                                                                                                          \
+        auto kern = frontier_wide_kernel<TQ, TDD, K, P>;                                                          \
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);                      \
+        kern<<<grid, block, wsmem, st>>>((const TQ*)d_queries, nq, d_ids, c, idx->d_vectors, idx->row_stride,      \
+                                         idx->n_total(), dim, qstride, d_out);                                    \
+    } while (0)
+        if (idx->dtype == DAB_F32) {
+            if (plan.kind == KIND_L2) LW(float, float, KIND_L2, POST_ID);
+            else if (plan.post == POST_NEG) LW(float, float, KIND_IP, POST_NEG);
+            else LW(float, float, KIND_IP, POST_ONE_MINUS);
+        } else {
+            if (plan.kind == KIND_L2) LW(__half, __half, KIND_L2, POST_ID);
+            else if (plan.post == POST_NEG) LW(__half, __half, KIND_IP, POST_NEG);
+            else LW(__half, __half, KIND_IP, POST_ONE_MINUS);
+        }
+#undef LW
+        DAB_LAUNCHED();
+        DAB_CUDA(cudaGetLastError());
+        return DAB_OK;
+    }
 #define ARGS nq, d_ids, c, idx->d_vectors, idx->row_stride, idx->n_total(), dim, d_out
     if (idx->dtype == DAB_F32) {
 #define L(K, P)                                                                                                   \

@@ -124,6 +124,8 @@ def test_error_behaviour_matches_the_layer(dab):
     (np.float32, O.L2, 128), (np.float32, O.L2, 100), (np.float32, O.L2, 96), (np.float32, O.COSINE, 37),
     (np.float16, O.INNER_PRODUCT, 768), (np.float16, O.L2, 100), (np.float16, O.COSINE_NORMALIZED, 64),
     (np.int8, O.L2, 128), (np.int8, O.INNER_PRODUCT, 100), (np.uint8, O.L2, 128), (np.uint8, O.COSINE, 33),
+    # wide-load kernel corners: fewer than four 8-blocks, no full block at all, leftover blocks + tail
+    (np.float32, O.INNER_PRODUCT, 17), (np.float16, O.L2, 7), (np.float32, O.COSINE_NORMALIZED, 43), (np.float16, O.INNER_PRODUCT, 61),
 ])
 def test_frontier_distances_bit_exact(dab, dt, metric, dim):
     rng = np.random.default_rng(dim * 7 + metric)
