@@ -274,6 +274,27 @@ def run_gpu(args):
     assert np.array_equal(ids_dev, h_ids.numpy().view(np.uint32)), "device-resident and host C-ABI results differ"
     recall = recall_of(ids_dev, counts)
 
+    # informative only: the same device-resident step at the smallest L of the sweep that already
+    # meets the recall target (rank 0, after every collective of the timed runs)
+    at_min_l = None
+    if rank == 0 and min_l and min_l != l_search:
+        def step_min():
+            g.search_batch_device(d_q.data_ptr(), nq, K, min_l, 1, d_ids.data_ptr(), d_dists.data_ptr(),
+                                  d_counts.data_ptr(), d_cmps.data_ptr(), d_hops.data_ptr())
+        for _ in range(max(3, args.warmup)):
+            step_min()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_min()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_min = e0.elapsed_time(e1) / args.steps
+        r_min = recall_of(d_ids.cpu().numpy().view(np.uint32), d_counts.cpu().numpy().view(np.uint32))
+        at_min_l = {"l_search": min_l, "recall_at_10": round(r_min, 5), "ms_per_step": ms_min,
+                    "queries_per_s_this_gpu": nq / (ms_min / 1e3)}
+
     ms_step = ms_dev / args.steps
     total_q = nq * world
     value = total_q / (ms_step / 1e3)
@@ -300,7 +321,7 @@ def run_gpu(args):
                        "l2_policy": f"no flush: index {(n * dim * 4 + (n + 1) * 4 * (md + 1)) / 1e6:.0f} MB >> 126 MB L2 and "
                                     "each step gathers ~GBs of random rows",
                        "setup_s": {"data": round(t_data, 1), "build": round(t_build, 1), "ground_truth": round(t_gt, 2)},
-                       "min_l_for_target_recall": min_l, "l_sweep": sweep},
+                       "min_l_for_target_recall": min_l, "l_sweep": sweep, "at_min_l": at_min_l},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
                     "d2h_bytes_per_step": nq * K * 8, "ms_per_step": ms_e2e / args.steps},

@@ -15,8 +15,11 @@
 //     (xor 8, 16, [remainder], 4, 2, 1) — 9 shuffles per 8 rows;
 //   * the sorted candidate list lives in shared memory and a whole round of candidates is merged
 //     at once by rank (search_common.cuh), equivalent to the reference's sequential inserts;
-//   * all visited-set probes of an adjacency row are issued together; the adjacency row of the
-//     next-best unvisited candidate is prefetched into L2 while the current hop runs.
+//   * all visited-set probes of an adjacency row are issued together (one 256-bit evict_last
+//     load per 8-id bucket); the adjacency row of the next-best unvisited candidate is copied
+//     into shared memory while the current hop runs, so the next hop usually starts without a
+//     global round trip;
+//   * the distance arithmetic advances two rows per instruction (packed f32x2 FADD2 / FFMA2).
 #include "dab_common.cuh"
 #include "distance_device.cuh"
 #include "search_common.cuh"

@@ -1,0 +1,30 @@
+"""debug aid: one small pass over every kernel family, sized to run under
+`compute-sanitizer --tool memcheck` (or racecheck / initcheck) in about a minute."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import diskann_b200 as dab
+
+rng = np.random.default_rng(0)
+for dt, ddt, metric, d in ((np.float32, dab.DType.f32, dab.Metric.L2, 100), (np.float16, dab.DType.f16, dab.Metric.InnerProduct, 61),
+                           (np.int8, dab.DType.i8, dab.Metric.L2, 33)):
+    n = 3000
+    base = (rng.normal(size=(n + 1, d)) * (30 if dt == np.int8 else 1)).astype(dt)
+    with dab.GpuIndex(ddt, metric, d, n, 1, 41) as g:
+        g.upload_vectors(base)
+        g.build(32, 64, 1.2)                                     # search (records) + prune + back-edge kernels
+        adj = g.download_graph()
+        ids = rng.integers(0, n + 1, (50, 83)).astype(np.uint32)
+        ids[0, :5] = 0xFFFFFFFF
+        out = g.distances(base[:50], ids)                        # frontier kernels (wide for f32 / f16)
+        pairs = g.row_pair_distances(ids[1, :40], ids[2, :40])
+        block = g.pairwise(ids[3, :17])
+        got = g.search_batch(base[:64], 5, 64, 1)                # search_kernel_v2 / generic
+        got4 = g.search_batch(base[:64], 5, 40, 4)
+        knn = g.flat_knn(base[:16], 5)
+        print(dt.__name__, "deg max", int(adj[:, 0].max()), "search ok", int(got[2].min()), int(got4[2].min()),
+              "finite", bool(np.isfinite(out[1:]).all() and np.isfinite(pairs).all() and np.isfinite(block).all()), knn[0].shape)
+print("sanitize_check done")
