@@ -339,7 +339,7 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(result))
+        emit(result)
 
 
 # ------------------------------------------------------------------------------------------ CPU arms
@@ -392,7 +392,7 @@ def run_reference(args):
     queries = make_data(cfg, SEED_QUERY, nq, centers)
     medoid = base[np.argmin(((base - base.mean(0, dtype=np.float64).astype(np.float32)) ** 2).sum(1))]
     if not has_gpu:
-        print(json.dumps({"impl": "reference", "unavailable": "no GPU to prepare the 1M-point graph input for the CPU arm"}))
+        emit({"impl": "reference", "unavailable": "no GPU to prepare the 1M-point graph input for the CPU arm"})
         return
     import diskann_b200 as dab
     g = dab.GpuIndex(dab.DType.f32, dab.Metric.L2, dim, n, 1, md)
@@ -423,7 +423,7 @@ def run_reference(args):
         ids, _, counts, cmps, hops = oidx.search_batch(queries, K, l_search, threads=threads)
     dt = (time.perf_counter() - t0) / args.steps
     qps = nq / dt
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "QPS @ recall@10>=0.95, 1Mx128 f32 L2 (Vamana R=64 greedy search, batch 10K)",
         "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -434,7 +434,26 @@ def run_reference(args):
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                          "sample": f"each step = the full {nq}-query batch on {threads} threads (contiguous partitions)"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries loaded later (NCCL prints its version
+    banner there) write to file descriptor 1 directly, so fd 1 is pointed at stderr for the rest
+    of the process and the JSON line goes to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 def main():
@@ -450,6 +469,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
