@@ -8,8 +8,11 @@
 #include <cstring>
 #include <limits>
 #include <thread>
-#include <unordered_set>
 #include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 namespace {
 
@@ -129,14 +132,94 @@ struct Visit {
     float dist;
 };
 
+// The reference's visited set is a hashbrown HashSet<u32> created with the capacity estimate of
+// scratch.rs:186-192 and kept in the pooled search scratch (cleared, not reallocated, between
+// queries).  Same behaviour here: flat open addressing, 7/8 load factor, doubling growth.
+struct VisitedSet {
+    static constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+    std::vector<uint32_t> slots;
+    size_t count = 0;
+    bool has_empty_key = false;  // the one id that collides with the empty marker
+    uint32_t shift = 28;
+
+    void reset(size_t expected) {
+        size_t cap = 16;
+        while (cap * 7 / 8 < expected) cap <<= 1;
+        if (slots.size() != cap) slots.assign(cap, kEmpty);
+        else std::fill(slots.begin(), slots.end(), kEmpty);
+        set_shift();
+        count = 0;
+        has_empty_key = false;
+    }
+    void set_shift() {
+        uint32_t lg = 0;
+        while (((size_t)1 << lg) < slots.size()) ++lg;
+        shift = 32 - lg;
+    }
+    void grow() {
+        std::vector<uint32_t> old;
+        old.swap(slots);
+        slots.assign(old.size() * 2, kEmpty);
+        set_shift();
+        for (uint32_t v : old)
+            if (v != kEmpty) place(v);
+    }
+    void place(uint32_t id) {
+        const size_t mask = slots.size() - 1;
+        size_t h = (size_t)((id * 0x9E3779B1u) >> shift);
+        while (slots[h] != kEmpty) h = (h + 1) & mask;
+        slots[h] = id;
+    }
+    // HashSet::insert: true when the id was not present
+    bool insert(uint32_t id) {
+        if (id == kEmpty) {
+            const bool fresh = !has_empty_key;
+            has_empty_key = true;
+            return fresh;
+        }
+        const size_t mask = slots.size() - 1;
+        size_t h = (size_t)((id * 0x9E3779B1u) >> shift);
+        while (slots[h] != kEmpty) {
+            if (slots[h] == id) return false;
+            h = (h + 1) & mask;
+        }
+        if ((count + 1) * 8 > slots.size() * 7) {
+            grow();
+            place(id);
+        } else {
+            slots[h] = id;
+        }
+        ++count;
+        return true;
+    }
+};
+
+// pooled per-thread search scratch (graph/search/scratch.rs)
+struct SearchScratch {
+    VisitedSet visited;
+    std::vector<uint32_t> beam, list;
+    std::vector<Visit> neighbors;
+};
+
+inline void prefetch_bytes(const void* p, size_t bytes) {
+#if defined(__x86_64__)
+    for (size_t off = 0; off < bytes; off += 64) _mm_prefetch((const char*)p + off, _MM_HINT_T0);
+#else
+    (void)p;
+    (void)bytes;
+#endif
+}
+
 // diskann/src/graph/index.rs:1933-2000.  `record` (optional) receives the nodes picked for
 // expansion in order (VisitedSearchRecord, used by insert).
 void search_internal(const orc_index* idx, const QueryDist& qd, uint32_t l_search,
                      uint32_t beam_width, Queue& best, uint32_t* cmps_out, uint32_t* hops_out,
                      std::vector<Visit>* record) {
-    std::unordered_set<uint32_t> visited;
+    static thread_local SearchScratch scratch;
+    VisitedSet& visited = scratch.visited;
+    // estimate_node_visited_set_size (scratch.rs:186-192): 1.1 * max_degree * 1.3 * L
+    visited.reset((size_t)(1.1 * (double)(idx->adj_stride ? idx->adj_stride - 1 : 64) * 1.3 * (double)l_search) + 1);
     uint32_t cmps = 0, hops = 0;
-    (void)l_search;
     const uint64_t total = idx->n_points + idx->n_start;
     // start_point_distances (diskann-inmem/src/provider.rs:406-433)
     for (uint32_t s = 0; s < idx->n_start; ++s) {
@@ -145,8 +228,17 @@ void search_internal(const orc_index* idx, const QueryDist& qd, uint32_t l_searc
         best.insert(id, qd(id));
         ++cmps;
     }
-    std::vector<uint32_t> beam;
-    std::vector<Visit> neighbors;
+    std::vector<uint32_t>& beam = scratch.beam;
+    std::vector<uint32_t>& list = scratch.list;
+    std::vector<Visit>& neighbors = scratch.neighbors;
+    // what one distance evaluation reads (the row, or the PQ code of the point)
+    const char* fetch_base = idx->pq_codes ? (const char*)idx->pq_codes : (const char*)idx->vectors;
+    const size_t fetch_stride = idx->pq_codes ? (size_t)idx->pq_chunks : (size_t)idx->row_stride;
+    size_t fetch_bytes = fetch_stride;
+    if (!idx->pq_codes) {
+        const size_t es = idx->dtype == ORC_F32 ? 4 : idx->dtype == ORC_F16 ? 2 : 1;
+        fetch_bytes = (size_t)idx->dim * es;
+    }
     if (beam_width == 0) beam_width = 1;
     while (best.has_notvisited()) {
         beam.clear();
@@ -157,14 +249,29 @@ void search_internal(const orc_index* idx, const QueryDist& qd, uint32_t l_searc
             beam.push_back(id);
         }
         neighbors.clear();
-        // expand_beam (diskann-inmem/src/provider.rs:436-479, 620-690)
+        // expand_beam (diskann-inmem/src/provider.rs:436-479): filter the adjacency lists ...
+        list.clear();
         for (uint32_t node : beam) {
             const uint32_t* row = idx->adj + (size_t)node * idx->adj_stride;
             uint32_t deg = row[0];
             for (uint32_t j = 0; j < deg; ++j) {
                 uint32_t n = row[1 + j];
-                if (!visited.insert(n).second) continue;  // pred.eval_mut
-                if (n >= total) continue;                 // is_in_bounds
+                if (!visited.insert(n)) continue;  // pred.eval_mut
+                if (n >= total) continue;          // is_in_bounds
+                list.push_back(n);
+            }
+        }
+        // ... then expand_beam_inner (provider.rs:620-690): distances in list order with the
+        // rows prefetched `lookahead` = 8 entries ahead (Config::DEFAULT_PREFETCH_LOOKAHEAD, :169)
+        {
+            const size_t len = list.size(), lookahead = std::min<size_t>(8, len);
+            for (size_t j = 0; j < lookahead; ++j) prefetch_bytes(fetch_base + (size_t)list[j] * fetch_stride, fetch_bytes);
+            size_t j = lookahead == 0 ? len : lookahead;
+            for (uint32_t n : list) {
+                if (j != len) {
+                    prefetch_bytes(fetch_base + (size_t)list[j] * fetch_stride, fetch_bytes);
+                    ++j;
+                }
                 neighbors.push_back(Visit{n, qd(n)});
             }
         }
