@@ -37,6 +37,9 @@ constexpr int kGroup = 8;  // rows reduced together
 #ifndef DAB_V2_ADJ_SMEM
 #define DAB_V2_ADJ_SMEM 1  // speculative adjacency row into shared memory (0: L2 prefetch)
 #endif
+#ifndef DAB_V2_SPLIT_WAIT
+#define DAB_V2_SPLIT_WAIT 0  // experiment for the next round: compute the first 8 rows while the rest land
+#endif
 #ifndef DAB_V2_F32X2
 #define DAB_V2_F32X2 1     // packed FADD2 / FFMA2 distance arithmetic
 #endif
@@ -211,8 +214,8 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
         uint32_t pred = kEmptyV2;  // node whose adjacency row sits in adjbuf
         bool overflow = false;
 
-        // stage `n` candidate rows (ids cid[c0..)) with per-lane 16 B async copies (one warp
-        // instruction moves 512 B of a row) and compute their distances into cd[]
+        // stage `n` candidate rows (ids cid[c0..)) with per-lane 16 B async copies and compute
+        // their distances into cd[]
         auto distances = [&](uint32_t c0, uint32_t n) {
             // eight lanes per row, 16 B each: one warp instruction moves 128 B of four different
             // rows, and every lane forms its own source address (no cross-lane traffic)
@@ -228,30 +231,54 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 #endif
             };
-            if (p.row_bytes == 4 * offs) {  // 128-d f32 / 256-d f16 rows: fixed trip count, immediate offsets
-                for (uint32_t j = sub; j < n; j += nsub) {
-                    const uint8_t* src = p.vectors + (size_t)cid[c0 + j] * p.row_stride + off0;
-                    const uint32_t dst = rows_a + j * p.row_slot + off0;
+            // copies of rows [lo, hi) as one cp.async group
+            auto issue = [&](uint32_t lo, uint32_t hi) {
+                if (p.row_bytes == 4 * offs) {  // 128-d f32 / 256-d f16 rows: fixed trip count, immediate offsets
+                    for (uint32_t j = lo + sub; j < hi; j += nsub) {
+                        const uint8_t* src = p.vectors + (size_t)cid[c0 + j] * p.row_stride + off0;
+                        const uint32_t dst = rows_a + j * p.row_slot + off0;
 #pragma unroll
-                    for (uint32_t k = 0; k < 4; ++k) copy16(dst + k * offs, src + k * offs);
+                        for (uint32_t k = 0; k < 4; ++k) copy16(dst + k * offs, src + k * offs);
+                    }
+                } else {
+                    for (uint32_t j = lo + sub; j < hi; j += nsub) {
+                        const uint8_t* src = p.vectors + (size_t)cid[c0 + j] * p.row_stride;
+                        const uint32_t dst = rows_a + j * p.row_slot;
+                        for (uint32_t off = off0; off < p.row_bytes; off += offs) copy16(dst + off, src + off);
+                    }
                 }
-            } else {
-                for (uint32_t j = sub; j < n; j += nsub) {
-                    const uint8_t* src = p.vectors + (size_t)cid[c0 + j] * p.row_stride;
-                    const uint32_t dst = rows_a + j * p.row_slot;
-                    for (uint32_t off = off0; off < p.row_bytes; off += offs) copy16(dst + off, src + off);
-                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            auto compute = [&](uint32_t g0) {
+                const float r = group_distance<TD, KIND>(qf, rows + (size_t)g0 * p.row_slot, p.row_slot, dim, lane);
+                const uint32_t u = (((lane >> 3) & 1) << 2) | (((lane >> 4) & 1) << 1) | ((lane >> 2) & 1);
+                if ((lane & 3) == 0 && g0 + u < n) cd[c0 + g0 + u] = post_op<POST>(r);
+            };
+#if DAB_V2_SPLIT_WAIT
+            // the first reduce group is copied as its own cp.async group: its arithmetic runs
+            // while the remaining rows of the stage are still in flight
+            const bool split = n > kGroup;
+            issue(0, split ? kGroup : n);
+            if (split) issue(kGroup, n);
+            DAB_PHASE(3);  // issue of the row copies
+            if (split) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            DAB_PHASE(4);  // waiting for the rows
+            compute(0);
+            if (split) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                for (uint32_t g0 = kGroup; g0 < n; g0 += kGroup) compute(g0);
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+            issue(0, n);
             DAB_PHASE(3);  // issue of the row copies
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
             DAB_PHASE(4);  // waiting for the rows
-            for (uint32_t g0 = 0; g0 < n; g0 += kGroup) {
-                const float r = group_distance<TD, KIND>(qf, rows + (size_t)g0 * p.row_slot, p.row_slot, dim, lane);
-                const uint32_t u = (((lane >> 3) & 1) << 2) | (((lane >> 4) & 1) << 1) | ((lane >> 2) & 1);
-                if ((lane & 3) == 0 && g0 + u < n) cd[c0 + g0 + u] = post_op<POST>(r);
-            }
+            for (uint32_t g0 = 0; g0 < n; g0 += kGroup) compute(g0);
+#endif
             __syncwarp();
         };
 
