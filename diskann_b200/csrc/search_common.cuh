@@ -152,4 +152,62 @@ __device__ __forceinline__ bool bucket_insert(uint32_t* table, uint32_t n_bucket
     }
 }
 
+// ---- experiment (DAB_V2_TAG16_BUILD, off by default): 16-bit quotient tags ---------------------
+// Halves the table footprint (the measured problem: 62 MB of tables do not stay in L2, 30 MB do,
+// profiles/r01_table_footprint.md) without giving up exactness.  Ids < 2^K are hashed with an odd
+// multiplier modulo 2^K (a bijection), h = tag * n_buckets + bucket, so (bucket, tag) identifies
+// the id and only the tag (< 2^K / n_buckets + 1 <= 2^14) is stored: 16 entries per 32-byte
+// bucket.  An entry displaced to the d-th following bucket (d <= 2) carries d in its top two
+// bits, which keeps it distinct from the entries at home there; 0xFFFF is the empty marker.
+struct Tag16Map {
+    uint32_t kmask;   // 2^K - 1, K = bits of the largest id
+    uint32_t nbk;     // buckets per table
+    uint32_t magic;   // ceil(2^(K+s) / nbk), s = ceil(log2 nbk): exact h / nbk for h < 2^K
+    uint32_t shift;   // K + s
+};
+
+__device__ __forceinline__ void tag16_of(uint32_t id, const Tag16Map& m, uint32_t& bucket, uint32_t& tag) {
+    const uint32_t h = (id * 0x9E3779B1u) & m.kmask;
+    tag = (uint32_t)(((uint64_t)h * m.magic) >> m.shift);  // h / nbk
+    bucket = h - tag * m.nbk;                              // h % nbk
+}
+
+// true when the tag was newly inserted; `ovf` is raised when three buckets in a row are full
+__device__ __forceinline__ bool bucket16_insert(uint32_t* table, uint32_t n_buckets, uint32_t b, uint32_t (&s)[8], uint32_t tag, bool& ovf) {
+    uint32_t d = 0;
+    for (;;) {
+        const uint32_t want = (d << 14) | tag, want2 = want * 0x10001u;
+        bool found = false;
+        int ew = -1;
+        uint32_t ehalf = 0;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            const uint32_t x = s[k] ^ want2;
+            found |= (x & 0xFFFFu) == 0 || (x >> 16) == 0;
+            const bool lo_empty = (s[k] & 0xFFFFu) == 0xFFFFu, hi_empty = (s[k] >> 16) == 0xFFFFu;
+            if (lo_empty || hi_empty) {
+                ew = k;
+                ehalf = lo_empty ? 0u : 1u;
+            }
+        }
+        if (found) return false;
+        uint32_t* bp = table + (size_t)b * 8;
+        if (ew >= 0) {
+            unsigned short* slot = reinterpret_cast<unsigned short*>(bp + ew) + ehalf;
+            const unsigned short old = atomicCAS(slot, (unsigned short)0xFFFFu, (unsigned short)want);
+            if (old == 0xFFFFu) return true;
+            if (old == want) return false;
+            // another lane of this warp took the slot: re-read the bucket
+        } else {
+            if (++d > 2) {
+                ovf = true;
+                return false;
+            }
+            b = b + 1 == n_buckets ? 0 : b + 1;
+            bp = table + (size_t)b * 8;
+        }
+        load_bucket(bp, s);
+    }
+}
+
 }  // namespace dab

@@ -168,7 +168,12 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
     const uint32_t warp_slot = blockIdx.x * kV2Warps + wib;
     const uint32_t nbk = p.n_buckets;
     uint32_t* table = p.tables + (size_t)warp_slot * nbk * 8;
+#if DAB_V2_TAG16_BUILD
+    const Tag16Map tmap{p.tag_kmask, nbk, p.tag_magic, p.tag_shift};
+    const uint32_t hlimit = nbk * 14;  // 87.5 % of 16 tags per bucket
+#else
     const uint32_t hlimit = nbk * 7;  // 87.5 % load: 8-way buckets stay short
+#endif
     const uint64_t n_total = p.n_points + p.n_start;
     const int dim = (int)p.dim;
 #if DAB_L2_HINTS
@@ -288,10 +293,18 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
             if ((uint32_t)lane < n) {
                 const uint32_t id = (uint32_t)p.n_points + s0 + lane;
                 cid[lane] = id;
-                const uint32_t b = bucket_of(id, nbk);
                 uint32_t bs[8];
+#if DAB_V2_TAG16_BUILD
+                uint32_t b, tg;
+                bool ovf = false;  // start points cannot fill three buckets in a row
+                tag16_of(id, tmap, b, tg);
+                load_bucket(table + (size_t)b * 8, bs);
+                bucket16_insert(table, nbk, b, bs, tg, ovf);
+#else
+                const uint32_t b = bucket_of(id, nbk);
                 load_bucket(table + (size_t)b * 8, bs);
                 bucket_insert(table, nbk, b, bs, id);
+#endif
             }
             __syncwarp();
             for (uint32_t c0 = 0; c0 < n; c0 += p.stage_rows) distances(c0, min(p.stage_rows, n - c0));
@@ -371,17 +384,31 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                 bool valid[3];
                 uint32_t bk[3];
                 uint32_t bs[3][8];
+#if DAB_V2_TAG16_BUILD
+                uint32_t tg[3];
+                bool ovf = false;
+#endif
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const uint32_t j = c * 32 + lane;
+#if DAB_V2_TAG16_BUILD
+                    // ids beyond 2^K cannot be in bounds and never reach the outputs: not tracked
+                    valid[c] = j >= 1 && j <= deg && wd[c] <= tmap.kmask;
+                    tag16_of(wd[c], tmap, bk[c], tg[c]);
+#else
                     valid[c] = j >= 1 && j <= deg;
                     bk[c] = bucket_of(wd[c], nbk);
+#endif
                     if (valid[c]) load_bucket(table + (size_t)bk[c] * 8, bs[c]);
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     bool inserted = false;
+#if DAB_V2_TAG16_BUILD
+                    if (valid[c]) inserted = bucket16_insert(table, nbk, bk[c], bs[c], tg[c], ovf);
+#else
                     if (valid[c]) inserted = bucket_insert(table, nbk, bk[c], bs[c], wd[c]);
+#endif
                     const bool isnew = inserted && wd[c] < n_total;  // is_in_bounds
                     const unsigned mi = __ballot_sync(kFull, inserted);
                     const unsigned mn = __ballot_sync(kFull, isnew);
@@ -394,12 +421,21 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                     const uint32_t j = c0 + lane;
                     const uint32_t word = j < p.adj_stride ? __ldg(row + j) : kEmptyV2;
                     bool inserted = false;
+#if DAB_V2_TAG16_BUILD
+                    if (j <= deg && word <= tmap.kmask) {
+                        uint32_t b2, t2, bs2[8];
+                        tag16_of(word, tmap, b2, t2);
+                        load_bucket(table + (size_t)b2 * 8, bs2);
+                        inserted = bucket16_insert(table, nbk, b2, bs2, t2, ovf);
+                    }
+#else
                     if (j <= deg) {
                         const uint32_t b2 = bucket_of(word, nbk);
                         uint32_t bs2[8];
                         load_bucket(table + (size_t)b2 * 8, bs2);
                         inserted = bucket_insert(table, nbk, b2, bs2, word);
                     }
+#endif
                     const bool isnew = inserted && word < n_total;
                     const unsigned mi = __ballot_sync(kFull, inserted);
                     const unsigned mn = __ballot_sync(kFull, isnew);
@@ -408,6 +444,9 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                     nvisited += __popc(mi);
                 }
                 if (nvisited + p.max_degree > hlimit) overflow = true;
+#if DAB_V2_TAG16_BUILD
+                if (__any_sync(kFull, ovf)) overflow = true;  // three full buckets in a row: re-run with the 32-bit table
+#endif
             }
             if (overflow) break;
             __syncwarp();
