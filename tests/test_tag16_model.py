@@ -16,7 +16,7 @@ def tag_map(K, nbk):
     return (1 << K) - 1, magic, K + s
 
 
-@pytest.mark.parametrize("K,nbk", [(20, 283), (20, 64), (20, 577), (17, 16), (22, 300), (24, 1024), (12, 16)])
+@pytest.mark.parametrize("K,nbk", [(20, 283), (20, 64), (20, 577), (17, 16), (22, 300), (22, 1024), (12, 16)])
 def test_bucket_tag_is_a_bijection_with_14_bit_tags(K, nbk):
     assert (1 << K) <= nbk << 14, "host picks n_buckets >= 2^K / 2^14"
     kmask, magic, shift = tag_map(K, nbk)
