@@ -177,17 +177,25 @@ __device__ __forceinline__ bool bucket16_insert(uint32_t* table, uint32_t n_buck
     uint32_t d = 0;
     for (;;) {
         const uint32_t want = (d << 14) | tag, want2 = want * 0x10001u;
-        bool found = false;
+        // "some 16-bit half of v is zero" <=> ((v - 0x00010001) & ~v & 0x80008000) != 0 (exact as
+        // a boolean; a borrow can only mis-flag the high half when the low half is itself zero)
+        uint32_t hit = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t x = s[k] ^ want2;
+            hit |= (x - 0x00010001u) & ~x & 0x80008000u;
+        }
+        const bool found = hit != 0;
         int ew = -1;
         uint32_t ehalf = 0;
+        if (!found) {
 #pragma unroll
-        for (int k = 7; k >= 0; --k) {
-            const uint32_t x = s[k] ^ want2;
-            found |= (x & 0xFFFFu) == 0 || (x >> 16) == 0;
-            const bool lo_empty = (s[k] & 0xFFFFu) == 0xFFFFu, hi_empty = (s[k] >> 16) == 0xFFFFu;
-            if (lo_empty || hi_empty) {
-                ew = k;
-                ehalf = lo_empty ? 0u : 1u;
+            for (int k = 7; k >= 0; --k) {
+                const uint32_t y = ~s[k];  // an empty entry (0xFFFF) is a zero half of ~s
+                if ((y - 0x00010001u) & s[k] & 0x80008000u) {
+                    ew = k;
+                    ehalf = (s[k] & 0xFFFFu) == 0xFFFFu ? 0u : 1u;
+                }
             }
         }
         if (found) return false;

@@ -31,3 +31,26 @@ def test_bucket_tag_is_a_bijection_with_14_bit_tags(K, nbk):
     assert len(np.unique(key)) == 1 << K, "(bucket, tag) must identify the id"
     # displaced copies carry d = 1, 2 in the top two bits and never look empty
     assert ((2 << 14) | int(tag.max())) < 0xFFFF
+
+
+def test_halfword_zero_trick_is_exact():
+    """bucket16_insert scans a bucket with (v - 0x00010001) & ~v & 0x80008000: non-zero exactly
+    when one of the two 16-bit halves of v is zero; with the low half checked first the position of
+    an empty (0xFFFF) entry is exact too."""
+    rng = np.random.default_rng(0)
+    special = np.array([0, 1, 0xFFFF, 0x8000, 0x7FFF, 0xBFFF, 0x0100, 0x00FF], np.uint64)
+    lo = np.concatenate([special.repeat(len(special)), rng.integers(0, 1 << 16, 200000).astype(np.uint64)])
+    hi = np.concatenate([np.tile(special, len(special)), rng.integers(0, 1 << 16, 200000).astype(np.uint64)])
+    # force plenty of zero halves
+    lo[::7] = 0
+    hi[::11] = 0
+    v = (hi << np.uint64(16)) | lo
+    m32 = np.uint64(0xFFFFFFFF)
+    flag = ((v - np.uint64(0x00010001)) & m32) & (~v & m32) & np.uint64(0x80008000)
+    assert np.array_equal(flag != 0, (lo == 0) | (hi == 0))
+    # empty-slot position: s = ~v has 0xFFFF where v has a zero half
+    s = ~v & m32
+    has_empty = flag != 0
+    half = np.where((s & np.uint64(0xFFFF)) == np.uint64(0xFFFF), 0, 1)
+    truth = np.where(lo == 0, 0, 1)
+    assert np.array_equal(half[has_empty], truth[has_empty])
