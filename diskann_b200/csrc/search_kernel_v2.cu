@@ -27,6 +27,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace dab {
 
@@ -39,6 +40,9 @@ constexpr int kGroup = 8;  // rows reduced together
 #endif
 #ifndef DAB_V2_SPLIT_WAIT
 #define DAB_V2_SPLIT_WAIT 0  // experiment for the next round: compute the first 8 rows while the rest land
+#endif
+#ifndef DAB_V2_DEFER_CAS
+#define DAB_V2_DEFER_CAS 0  // experiment: visited-set CAS after the row copies are issued (its outcome is known)
 #endif
 #ifndef DAB_V2_F32X2
 #define DAB_V2_F32X2 1     // packed FADD2 / FFMA2 distance arithmetic
@@ -219,9 +223,33 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
         uint32_t pred = kEmptyV2;  // node whose adjacency row sits in adjbuf
         bool overflow = false;
 
+#if DAB_V2_DEFER_CAS && !DAB_V2_TAG16_BUILD
+        // visited-set inserts of the current hop whose outcome is already known (see the probe code)
+        // (the bucket images are re-read — an L2 hit by now — rather than kept in registers)
+        uint32_t d_bk[3], d_id[3];
+        bool d_need[3] = {false, false, false};
+        bool d_pending = false;
+        auto run_deferred = [&]() {
+            if (!d_pending) return;
+            d_pending = false;
+            uint32_t im[3][8];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (d_need[c]) load_bucket(table + (size_t)d_bk[c] * 8, im[c]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (d_need[c]) bucket_insert(table, nbk, d_bk[c], im[c], d_id[c]);
+            __syncwarp();
+        };
+#endif
+
         // stage `n` candidate rows (ids cid[c0..)) with per-lane 16 B async copies and compute
         // their distances into cd[]
+#if DAB_V2_DEFER_CAS && !DAB_V2_TAG16_BUILD
+        auto distances = [&](uint32_t c0, uint32_t n, auto with_deferred) {
+#else
         auto distances = [&](uint32_t c0, uint32_t n) {
+#endif
             // eight lanes per row, 16 B each: one warp instruction moves 128 B of four different
             // rows, and every lane forms its own source address (no cross-lane traffic)
 #if DAB_V2_COPY8
@@ -278,6 +306,9 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
             }
 #else
             issue(0, n);
+#if DAB_V2_DEFER_CAS && !DAB_V2_TAG16_BUILD
+            if constexpr (decltype(with_deferred)::value) run_deferred();  // the postponed CAS round trip runs while the rows are in flight
+#endif
             DAB_PHASE(3);  // issue of the row copies
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
@@ -307,7 +338,11 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
 #endif
             }
             __syncwarp();
+#if DAB_V2_DEFER_CAS && !DAB_V2_TAG16_BUILD
+            for (uint32_t c0 = 0; c0 < n; c0 += p.stage_rows) distances(c0, min(p.stage_rows, n - c0), std::false_type{});
+#else
             for (uint32_t c0 = 0; c0 < n; c0 += p.stage_rows) distances(c0, min(p.stage_rows, n - c0));
+#endif
             merge_round<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, 0, n, lane);
             nvisited += n;
             cmps += n;
@@ -401,11 +436,49 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
 #endif
                     if (valid[c]) load_bucket(table + (size_t)bk[c] * 8, bs[c]);
                 }
+#if DAB_V2_DEFER_CAS && !DAB_V2_TAG16_BUILD
+                // An id that is absent from its home bucket while that bucket still has a free
+                // slot is new for certain (a displaced copy exists only if the home bucket was
+                // full when it was inserted, and buckets never lose entries).  With one node per
+                // hop the candidate list is therefore known before any CAS has run: the inserts
+                // are postponed until the row copies have been issued (run_deferred) and their
+                // round trip overlaps the row fetch.
+                bool need[3], defer = nb == 1 && deg <= 95;
+                {
+                    bool full = false, cand = false;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        bool found = false, has_empty = false;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            found |= bs[c][k] == wd[c];
+                            has_empty |= bs[c][k] == kEmptyV2;
+                        }
+                        need[c] = valid[c] && !found;
+                        full |= need[c] && !has_empty;
+                        cand |= need[c] && wd[c] < n_total;
+                    }
+                    // (a hop without in-bounds candidates stages no rows: nothing to overlap with)
+                    defer = defer && !__any_sync(kFull, full) && __any_sync(kFull, cand);
+                }
+                if (defer) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        d_need[c] = need[c];
+                        d_bk[c] = bk[c];
+                        d_id[c] = wd[c];
+                    }
+                    d_pending = true;
+                }
+#endif
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     bool inserted = false;
 #if DAB_V2_TAG16_BUILD
                     if (valid[c]) inserted = bucket16_insert(table, nbk, bk[c], bs[c], tg[c], ovf);
+#elif DAB_V2_DEFER_CAS
+                    if (defer) inserted = need[c];
+                    else if (valid[c]) inserted = bucket_insert(table, nbk, bk[c], bs[c], wd[c]);
 #else
                     if (valid[c]) inserted = bucket_insert(table, nbk, bk[c], bs[c], wd[c]);
 #endif
@@ -452,7 +525,11 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
             __syncwarp();
             DAB_PHASE(2);  // adjacency fetch + visited filter
 
+#if DAB_V2_DEFER_CAS && !DAB_V2_TAG16_BUILD
+            for (uint32_t c0 = 0; c0 < ncand; c0 += p.stage_rows) distances(c0, min(p.stage_rows, ncand - c0), std::true_type{});
+#else
             for (uint32_t c0 = 0; c0 < ncand; c0 += p.stage_rows) distances(c0, min(p.stage_rows, ncand - c0));
+#endif
             DAB_PHASE(5);  // distance arithmetic
 
             // best.insert for every neighbour in adjacency order (index.rs:1986-1988)
