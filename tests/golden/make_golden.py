@@ -10,6 +10,8 @@ Sources (paths relative to the reference checkout):
   * diskann/test/generated/graph/test/cases/grid_search/search_{1_100,3_5,4_4}.json — checked-in
     greedy-search baselines (query, top-10 (id, distance), hops, comparisons, beam width).
   * diskann-wide/test_data/float16_conversion.txt — f16 <-> f32 conversion table (a sample).
+  * diskann/test/generated/graph/test/cases/grid_insert/insert_{1_100,3_5,4_4}_single/ibc_none.json —
+    searches after inserting the lattice points one by one (driver grid_insert.rs:46-250).
 Only data (numeric literals / JSON payloads) is extracted; no reference source is copied.
 """
 import json
@@ -65,6 +67,24 @@ def grid_search():
     print("grid_search.json", len(out))
 
 
+def grid_insert():
+    out = []
+    for name in ("insert_1_100_single", "insert_3_5_single", "insert_4_4_single"):
+        path = f"{REF}/diskann/test/generated/graph/test/cases/grid_insert/{name}/ibc_none.json"
+        p = json.load(open(path))["payload"]
+        out.append({
+            "case": name, "grid_dims": p["grid_dims"], "grid_size": p["grid_size"], "num_inserted": p["num_inserted"],
+            "searches": [{"beam_width": q["beam_width"], "query": q["query"], "num_results": q["num_results"],
+                          "results": q["results"], "comparisons": q["comparisons"], "hops": q["hops"]} for q in p["searches"]],
+        })
+    json.dump({"source": "diskann/test/generated/graph/test/cases/grid_insert/insert_*_single/ibc_none.json (driver "
+                         "diskann/src/graph/test/cases/grid_insert.rs:46-250: empty provider with the start point at "
+                         "(size,..,size), max_degree = 2*dims, pruned degree = max(max_degree - 2, 2), L_build = 100, L2, "
+                         "points inserted one by one in lattice order; then k = 10, L = 10 searches)",
+               "cases": out}, open(f"{OUT}/grid_insert.json", "w"), indent=0)
+    print("grid_insert.json", len(out))
+
+
 def f16_table():
     path = f"{REF}/diskann-wide/test_data/float16_conversion.txt"
     lines = open(path).read().splitlines()
@@ -83,4 +103,5 @@ if __name__ == "__main__":
         sys.exit("reference checkout not present; fixtures are already committed")
     kat_l2()
     grid_search()
+    grid_insert()
     f16_table()

@@ -482,3 +482,33 @@ def test_oracle_build_and_search_reach_high_recall():
     # single-thread == multi-thread, SIMD emulation == AVX2
     ids2, dists2, *_ = idx.search_batch(queries, 10, 40, flavour=O.SIMD, threads=1)
     assert (ids == ids2).all() and (dists.view(np.uint32) == dists2.view(np.uint32)).all()
+
+
+def test_grid_insert_baselines():
+    """The reference's single-insert baselines (grid_insert.rs:46-250): every lattice point is
+    inserted one by one into an index that starts with the start point only, then two searches.
+    The 1-D baseline is reproduced exactly.  The 3-D / 4-D lattices are full of exactly tied
+    distances and the reference orders a prune pool with `select_nth_unstable_by` +
+    `sort_unstable_by` (graph/internal/sorted_neighbors.rs:26-44), whose tie order is an
+    implementation detail of the Rust standard library and is not restated; there the oracle
+    (stable order) must still return the same distance profile and take the same number of hops."""
+    g = json.load(open(os.path.join(GOLDEN, "grid_insert.json")))
+    assert len(g["cases"]) == 3
+    for case in g["cases"]:
+        dims, size = case["grid_dims"], case["grid_size"]
+        data, _, n = grid(dims, size)
+        assert n == case["num_inserted"]
+        max_degree = 2 * dims
+        pruned = min(max(max_degree - 2, 2), max_degree)     # grid_insert.rs:83-86
+        adj = O.build_graph(data, n, 1, O.L2, pruned, max_degree, 100, 1.2)
+        assert adj[:, 0].max() <= max_degree
+        idx = O.Index(data, adj, n, 1, O.L2)
+        for s in case["searches"]:
+            q = np.array([s["query"]], np.float32)
+            ids, dists, counts, cmps, hops = idx.search_batch(q, 10, 10, beam=s["beam_width"], flavour=O.SIMD)
+            assert int(counts[0]) == s["num_results"]
+            assert int(hops[0]) == s["hops"]
+            assert [float(x) for x in dists[0]] == [r[1] for r in s["results"]]
+            if dims == 1:
+                assert [int(i) for i in ids[0]] == [r[0] for r in s["results"]]
+                assert int(cmps[0]) == s["comparisons"]
