@@ -12,6 +12,8 @@ Sources (paths relative to the reference checkout):
   * diskann-wide/test_data/float16_conversion.txt — f16 <-> f32 conversion table (a sample).
   * diskann/test/generated/graph/test/cases/grid_insert/insert_{1_100,3_5,4_4}_single/ibc_none.json —
     searches after inserting the lattice points one by one (driver grid_insert.rs:46-250).
+  * diskann/test/generated/flat/test/cases/flat_knn_search/search_{1_100,2_5,3_4}.json — exhaustive-scan
+    baselines (brute-force ground truth ordered by (distance, id), k in the reference's sweep).
 Only data (numeric literals / JSON payloads) is extracted; no reference source is copied.
 """
 import json
@@ -85,6 +87,21 @@ def grid_insert():
     print("grid_insert.json", len(out))
 
 
+def flat_knn():
+    out = []
+    for name in ("search_1_100", "search_2_5", "search_3_4"):
+        path = f"{REF}/diskann/test/generated/flat/test/cases/flat_knn_search/{name}.json"
+        for p in json.load(open(path))["payload"]:
+            out.append({"case": name, "grid_dims": p["grid_dims"], "grid_size": p["grid_size"], "k": p["k"],
+                        "query": p["query"], "ground_truth": p["ground_truth"], "top_k_distances": p["top_k_distances"],
+                        "comparisons": p["comparisons"], "result_count": p["result_count"]})
+    json.dump({"source": "diskann/test/generated/flat/test/cases/flat_knn_search/*.json (driver "
+                         "diskann/src/flat/test/cases/flat_knn_search.rs:95-196: size^dims lattice rows, L2, "
+                         "ground truth sorted by (distance asc, id asc))",
+               "cases": out}, open(f"{OUT}/flat_knn.json", "w"), indent=0)
+    print("flat_knn.json", len(out))
+
+
 def f16_table():
     path = f"{REF}/diskann-wide/test_data/float16_conversion.txt"
     lines = open(path).read().splitlines()
@@ -104,4 +121,5 @@ if __name__ == "__main__":
     kat_l2()
     grid_search()
     grid_insert()
+    flat_knn()
     f16_table()

@@ -512,3 +512,21 @@ def test_grid_insert_baselines():
             if dims == 1:
                 assert [int(i) for i in ids[0]] == [r[0] for r in s["results"]]
                 assert int(cmps[0]) == s["comparisons"]
+
+
+def test_flat_knn_baselines():
+    """The reference's exhaustive-scan baselines (flat_knn_search.rs:95-196): brute-force top-k
+    ordered by (distance asc, id asc) over the size^dims lattice, result_count = min(k, len)."""
+    g = json.load(open(os.path.join(GOLDEN, "flat_knn.json")))
+    assert len(g["cases"]) >= 12
+    for case in g["cases"]:
+        data, _, n = grid(case["grid_dims"], case["grid_size"])
+        base = np.ascontiguousarray(data[:n])                 # the flat provider has no start point
+        k = case["k"]
+        q = np.array([case["query"]], np.float32)
+        ids, dists = O.bruteforce_knn(base, q, O.L2, min(k, n), threads=1)
+        want = case["ground_truth"]
+        assert case["result_count"] == min(k, n) == len(want)
+        assert case["comparisons"] == n
+        assert [int(i) for i in ids[0][:len(want)]] == [w[0] for w in want], case["case"]
+        assert [float(x) for x in dists[0][:len(want)]] == [w[1] for w in want] == case["top_k_distances"]
