@@ -44,6 +44,9 @@ constexpr int kGroup = 8;  // rows reduced together
 #ifndef DAB_V2_DEFER_CAS
 #define DAB_V2_DEFER_CAS 0  // experiment: visited-set CAS after the row copies are issued (its outcome is known)
 #endif
+#ifndef DAB_V2_WIDE_LDS
+#define DAB_V2_WIDE_LDS 0   // experiment: 16-byte shared-memory reads with per-lane accumulator chains (needs DAB_V2_F32X2)
+#endif
 #ifndef DAB_V2_F32X2
 #define DAB_V2_F32X2 1     // packed FADD2 / FFMA2 distance arithmetic
 #endif
@@ -149,6 +152,81 @@ __device__ __forceinline__ float group_distance(const float* __restrict__ q, con
     a = __fadd_rn(a, __shfl_xor_sync(kFull, a, 1));
     return a;
 }
+
+#if DAB_V2_WIDE_LDS
+// Experiment: the lane mapping of frontier_wide_kernel (distance_kernels.cu) applied to the staged
+// rows — every lane reads 16 bytes of its row and of the query per step and owns the FMA chains of
+// those slots, so 4 (f16) / 8 (f32) lanes cover a row and a pass covers 8 / 4 rows.  Returns the
+// value of row `lane / (32 / EPL)` of the pass on all lanes of that team.  Same association as
+// group_distance: block k of 8 elements -> accumulator k mod 4, (s0+s1)+(s2+s3), zero-filled
+// remainder on the combined vector, sum_tree.
+template <typename TD, int KIND>
+__device__ __forceinline__ float wide_pass(const float* __restrict__ q, const uint8_t* __restrict__ rows, uint32_t row_slot, int dim,
+                                           int lane) {
+    constexpr int EPL = 16 / (int)sizeof(TD), LPR = 32 / EPL, HALVES = 8 / EPL;
+    const int team = lane / LPR, tl = lane % LPR;
+    const int a = tl / HALVES, h = tl % HALVES;
+    const uint8_t* row = rows + (size_t)team * row_slot;
+    const int nb8 = dim >> 3, full8 = dim & ~7, rem = dim & 7;
+    uint64_t acc2[EPL / 2];
+#pragma unroll
+    for (int i = 0; i < EPL / 2; ++i) acc2[i] = 0ull;
+    for (int k = a; k < nb8; k += 4) {
+        const int e0 = 8 * k + EPL * h;
+        const uint4 v = *reinterpret_cast<const uint4*>(row + (size_t)e0 * sizeof(TD));
+        float y[EPL];
+        if constexpr (sizeof(TD) == 2) {
+            const __half2* hp = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(hp[i]);
+                y[2 * i] = f.x;
+                y[2 * i + 1] = f.y;
+            }
+        } else {
+            y[0] = __uint_as_float(v.x), y[1] = __uint_as_float(v.y), y[2] = __uint_as_float(v.z), y[3] = __uint_as_float(v.w);
+        }
+#pragma unroll
+        for (int i = 0; i < EPL; i += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(q + e0 + i);
+            acc2[i / 2] = step2<KIND>(acc2[i / 2], pack2(x.x, x.y), pack2(y[i], y[i + 1]));
+            acc2[i / 2 + 1] = step2<KIND>(acc2[i / 2 + 1], pack2(x.z, x.w), pack2(y[i + 2], y[i + 3]));
+        }
+    }
+    float acc[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL / 2; ++i) unpack2(acc2[i], acc[2 * i], acc[2 * i + 1]);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        acc[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], HALVES));
+        acc[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], 2 * HALVES));
+    }
+    if (rem) {
+        const TD* tail = reinterpret_cast<const TD*>(row) + full8;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            const int l = EPL * h + i;
+            const float x = l < rem ? q[full8 + l] : 0.0f;
+            const float yv = l < rem ? to_f32(tail[l]) : 0.0f;
+            if (KIND == KIND_L2) {
+                const float d = __fsub_rn(x, yv);
+                acc[i] = __fmaf_rn(d, d, acc[i]);
+            } else {
+                acc[i] = __fmaf_rn(x, yv, acc[i]);
+            }
+        }
+    }
+    if constexpr (HALVES == 1) {
+        return __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[4]), __fadd_rn(acc[2], acc[6])),
+                         __fadd_rn(__fadd_rn(acc[1], acc[5]), __fadd_rn(acc[3], acc[7])));
+    } else {
+        float t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], 1));  // x_i + x_{i+4}
+        return __fadd_rn(__fadd_rn(t[0], t[2]), __fadd_rn(t[1], t[3]));
+    }
+}
+#endif
 
 template <typename TD, int KIND, int POST, int QT>
 #ifndef DAB_V2_MIN_CTAS
@@ -283,9 +361,19 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
             auto compute = [&](uint32_t g0) {
+#if DAB_V2_WIDE_LDS
+                constexpr int ROWS = 16 / (int)sizeof(TD), LPR = 32 / ROWS;
+#pragma unroll
+                for (int pass = 0; pass < kGroup / ROWS; ++pass) {
+                    const float r = wide_pass<TD, KIND>(qf, rows + (size_t)(g0 + pass * ROWS) * p.row_slot, p.row_slot, dim, lane);
+                    const uint32_t u = (uint32_t)(pass * ROWS + lane / LPR);
+                    if (lane % LPR == 0 && g0 + u < n) cd[c0 + g0 + u] = post_op<POST>(r);
+                }
+#else
                 const float r = group_distance<TD, KIND>(qf, rows + (size_t)g0 * p.row_slot, p.row_slot, dim, lane);
                 const uint32_t u = (((lane >> 3) & 1) << 2) | (((lane >> 4) & 1) << 1) | ((lane >> 2) & 1);
                 if ((lane & 3) == 0 && g0 + u < n) cd[c0 + g0 + u] = post_op<POST>(r);
+#endif
             };
 #if DAB_V2_SPLIT_WAIT
             // the first reduce group is copied as its own cp.async group: its arithmetic runs
