@@ -469,6 +469,10 @@ void orc_search_batch(const orc_index* idx, const void* queries, uint64_t query_
 // DiskANNIndex::insert for i = 0..n_points (index.rs:226-341), add_edge_and_prune
 // (index.rs:2264-2341), robust_prune_list (index.rs:2397-2454).  max_backedges defaults to
 // pruned_degree (config/mod.rs:292-306).
+// provider-level write counters of the last orc_build (the reference's test provider reports the
+// same two numbers as `set_neighbors` / `append_neighbors`, test/provider.rs Metrics)
+static uint64_t g_build_sets = 0, g_build_appends = 0;
+
 void orc_build(int dtype, int metric, uint32_t dim, uint64_t n_points, uint32_t n_start,
                const void* vectors, uint64_t row_stride, uint32_t pruned_degree,
                uint32_t max_degree, uint32_t l_build, float alpha, uint32_t* adj,
@@ -493,6 +497,7 @@ void orc_build(int dtype, int metric, uint32_t dim, uint64_t n_points, uint32_t 
     };
     std::vector<Visit> record, pool;
     std::vector<uint32_t> new_neighbors, pruned, list;
+    g_build_sets = g_build_appends = 0;
     for (uint64_t p = 0; p < n_points; ++p) {
         uint32_t id = (uint32_t)p;
         const void* vec = (const char*)vectors + (size_t)id * row_stride;
@@ -504,6 +509,7 @@ void orc_build(int dtype, int metric, uint32_t dim, uint64_t n_points, uint32_t 
         sort_pool(record, MAX_OCCLUSION);
         occlude_list(&idx, record, id, pruned_degree, alpha, flavour, new_neighbors);
         set_neighbors(id, new_neighbors);
+        ++g_build_sets;
         size_t nb = std::min<size_t>(new_neighbors.size(), pruned_degree);
         for (size_t s = 0; s < nb; ++s) {
             uint32_t source = new_neighbors[s];
@@ -515,6 +521,7 @@ void orc_build(int dtype, int metric, uint32_t dim, uint64_t n_points, uint32_t 
             if (deg + 1 <= max_degree) {
                 r[1 + deg] = id;
                 r[0] = deg + 1;
+                ++g_build_appends;
                 continue;
             }
             list.assign(r + 1, r + 1 + deg);
@@ -525,8 +532,14 @@ void orc_build(int dtype, int metric, uint32_t dim, uint64_t n_points, uint32_t 
             sort_pool(pool, MAX_OCCLUSION);
             occlude_list(&idx, pool, source, pruned_degree, alpha, flavour, pruned);
             set_neighbors(source, pruned);
+            ++g_build_sets;
         }
     }
+}
+
+void orc_last_build_counts(uint64_t* set_neighbors, uint64_t* append_neighbors) {
+    *set_neighbors = g_build_sets;
+    *append_neighbors = g_build_appends;
 }
 
 // ------------------------------------------------------------------ queue C API

@@ -155,6 +155,9 @@ void orc_build(int dtype, int metric, uint32_t dim, uint64_t n_points, uint32_t 
                const void* vectors, uint64_t row_stride, uint32_t pruned_degree,
                uint32_t max_degree, uint32_t l_build, float alpha, uint32_t* adj,
                uint32_t adj_stride);
+/* adjacency writes of the last orc_build: full-list writes and single-edge appends (what the
+ * reference's test provider counts as set_neighbors / append_neighbors in the grid_insert baselines) */
+void orc_last_build_counts(uint64_t* set_neighbors, uint64_t* append_neighbors);
 
 /* NeighborPriorityQueue exposed for the reference's queue unit tests (queue.rs:607-...) */
 typedef struct orc_queue orc_queue;

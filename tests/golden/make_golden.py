@@ -76,6 +76,7 @@ def grid_insert():
         p = json.load(open(path))["payload"]
         out.append({
             "case": name, "grid_dims": p["grid_dims"], "grid_size": p["grid_size"], "num_inserted": p["num_inserted"],
+            "set_neighbors": p["insert_metrics"]["set_neighbors"], "append_neighbors": p["insert_metrics"]["append_neighbors"],
             "searches": [{"beam_width": q["beam_width"], "query": q["query"], "num_results": q["num_results"],
                           "results": q["results"], "comparisons": q["comparisons"], "hops": q["hops"]} for q in p["searches"]],
         })

@@ -88,6 +88,8 @@ def lib():
     L.orc_robust_prune.argtypes = [C.POINTER(OrcIndex), vp, vp, vp, u32, u32, f, i, vp, vp]
     L.orc_build.restype = None
     L.orc_build.argtypes = [i, i, u32, u64, u32, vp, u64, u32, u32, u32, f, vp, u32]
+    L.orc_last_build_counts.restype = None
+    L.orc_last_build_counts.argtypes = [C.POINTER(u64), C.POINTER(u64)]
     L.orc_queue_new.restype = vp
     L.orc_queue_new.argtypes = [u32]
     L.orc_queue_free.restype = None
@@ -192,6 +194,13 @@ def build_graph(vectors, n_points, n_start, metric, pruned_degree, max_degree, l
     lib().orc_build(dtype_code(vectors), metric, vectors.shape[1], n_points, n_start, ptr(vectors),
                     vectors.strides[0], pruned_degree, max_degree, l_build, alpha, ptr(adj), stride)
     return adj
+
+
+def last_build_counts():
+    """(set_neighbors, append_neighbors) of the last build_graph call."""
+    a, b = C.c_uint64(), C.c_uint64()
+    lib().orc_last_build_counts(C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 def bruteforce_knn(base, queries, metric, k, threads=None):

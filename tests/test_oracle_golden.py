@@ -502,6 +502,12 @@ def test_grid_insert_baselines():
         pruned = min(max(max_degree - 2, 2), max_degree)     # grid_insert.rs:83-86
         adj = O.build_graph(data, n, 1, O.L2, pruned, max_degree, 100, 1.2)
         assert adj[:, 0].max() <= max_degree
+        sets, appends = O.last_build_counts()
+        if dims == 1:   # provider write counters of the insert phase (test/provider.rs Metrics)
+            assert (sets, appends) == (case["set_neighbors"], case["append_neighbors"])
+        else:           # tie order moves a handful of prune decisions, not the structure
+            assert abs(sets - case["set_neighbors"]) <= 0.02 * case["set_neighbors"]
+            assert abs(appends - case["append_neighbors"]) <= 0.02 * case["append_neighbors"]
         idx = O.Index(data, adj, n, 1, O.L2)
         for s in case["searches"]:
             q = np.array([s["query"]], np.float32)
