@@ -375,13 +375,63 @@ uint32_t robust_prune(const orc_index* idx, const uint32_t* pool_ids, const floa
     return found;
 }
 
-// SortedNeighbors::new (graph/internal/sorted_neighbors.rs:26-44): sort by distance and
-// truncate.  The reference uses an unstable sort, so the order of exactly-tied candidates is
-// unspecified there; the oracle breaks ties by original position (stable).
+// SortedNeighbors::new (graph/internal/sorted_neighbors.rs:26-44): `select_nth_unstable_by` at
+// the last position, then `sort_unstable_by` of the prefix, by distance only.  The order of
+// exactly tied candidates is whatever the Rust standard library's algorithms leave; the parts of
+// them that are simple are followed here, because the lattice baselines are full of ties:
+//   * selecting the last position swaps the FIRST maximum to the end (core::slice::select,
+//     `index == len - 1`);
+//   * a prefix of at most 20 elements is insertion-sorted, which is stable;
+//   * a longer prefix that is already non-descending is left alone, a strictly descending one is
+//     reversed (ipnsort's run detection);
+//   * anything else goes through ipnsort's quicksort, whose tie order is NOT restated: a stable
+//     sort stands in for it.
+
+//
+// The emulation is opt-in (orc_set_pool_tie_mode(1), used by the grid_insert golden test): the
+// default stays the plain stable sort, so that the graphs the GPU parity tests are built on are
+// the ones the kernels were validated with.
+static int g_pool_tie_mode = 0;
+
 void sort_pool(std::vector<Visit>& pool, size_t max) {
-    std::stable_sort(pool.begin(), pool.end(),
-                     [](const Visit& a, const Visit& b) { return a.dist < b.dist; });
-    if (pool.size() > max) pool.resize(max);
+    auto less = [](const Visit& a, const Visit& b) { return a.dist < b.dist; };
+    const size_t len = pool.size();
+    if (len > max || g_pool_tie_mode == 0) {  // (never the case below MAX_OCCLUSION; kept for completeness)
+        std::stable_sort(pool.begin(), pool.end(), less);
+        if (len > max) pool.resize(max);
+        return;
+    }
+    if (len < 2) return;
+    size_t mx = 0;
+    for (size_t i = 1; i < len; ++i)
+        if (less(pool[mx], pool[i])) mx = i;
+    std::swap(pool[mx], pool[len - 1]);
+    const size_t n = len - 1;  // the prefix
+    if (n < 2) return;
+    if (n <= 20) {
+        for (size_t i = 1; i < n; ++i) {
+            Visit v = pool[i];
+            size_t j = i;
+            while (j > 0 && less(v, pool[j - 1])) {
+                pool[j] = pool[j - 1];
+                --j;
+            }
+            pool[j] = v;
+        }
+        return;
+    }
+    size_t run = 2;
+    const bool descending = less(pool[1], pool[0]);
+    if (descending) {
+        while (run < n && less(pool[run], pool[run - 1])) ++run;
+    } else {
+        while (run < n && !less(pool[run], pool[run - 1])) ++run;
+    }
+    if (run == n) {
+        if (descending) std::reverse(pool.begin(), pool.begin() + n);
+        return;
+    }
+    std::stable_sort(pool.begin(), pool.begin() + n, less);
 }
 
 constexpr size_t MAX_OCCLUSION = 750;  // graph/config/defaults.rs:13
@@ -536,6 +586,8 @@ void orc_build(int dtype, int metric, uint32_t dim, uint64_t n_points, uint32_t 
         }
     }
 }
+
+void orc_set_pool_tie_mode(int mode) { g_pool_tie_mode = mode; }
 
 void orc_last_build_counts(uint64_t* set_neighbors, uint64_t* append_neighbors) {
     *set_neighbors = g_build_sets;

@@ -158,6 +158,9 @@ void orc_build(int dtype, int metric, uint32_t dim, uint64_t n_points, uint32_t 
 /* adjacency writes of the last orc_build: full-list writes and single-edge appends (what the
  * reference's test provider counts as set_neighbors / append_neighbors in the grid_insert baselines) */
 void orc_last_build_counts(uint64_t* set_neighbors, uint64_t* append_neighbors);
+/* order of exactly tied candidates in a prune pool: 0 (default) = stable sort by distance,
+ * 1 = follow the simple parts of Rust's select_nth_unstable_by + sort_unstable_by (graph.cpp) */
+void orc_set_pool_tie_mode(int mode);
 
 /* NeighborPriorityQueue exposed for the reference's queue unit tests (queue.rs:607-...) */
 typedef struct orc_queue orc_queue;

@@ -88,6 +88,8 @@ def lib():
     L.orc_robust_prune.argtypes = [C.POINTER(OrcIndex), vp, vp, vp, u32, u32, f, i, vp, vp]
     L.orc_build.restype = None
     L.orc_build.argtypes = [i, i, u32, u64, u32, vp, u64, u32, u32, u32, f, vp, u32]
+    L.orc_set_pool_tie_mode.restype = None
+    L.orc_set_pool_tie_mode.argtypes = [i]
     L.orc_last_build_counts.restype = None
     L.orc_last_build_counts.argtypes = [C.POINTER(u64), C.POINTER(u64)]
     L.orc_queue_new.restype = vp
@@ -187,12 +189,16 @@ class Index:
         return ids, dists, counts, cmps, hops
 
 
-def build_graph(vectors, n_points, n_start, metric, pruned_degree, max_degree, l_build, alpha=1.2):
+def build_graph(vectors, n_points, n_start, metric, pruned_degree, max_degree, l_build, alpha=1.2, tie_mode=0):
+    """tie_mode 1: order exactly tied prune candidates the way the Rust standard library would
+    (as far as oracle/graph.cpp restates it); 0: stable."""
     vectors = np.ascontiguousarray(vectors)
+    lib().orc_set_pool_tie_mode(tie_mode)
     stride = max_degree + 1
     adj = np.zeros((n_points + n_start, stride), np.uint32)
     lib().orc_build(dtype_code(vectors), metric, vectors.shape[1], n_points, n_start, ptr(vectors),
                     vectors.strides[0], pruned_degree, max_degree, l_build, alpha, ptr(adj), stride)
+    lib().orc_set_pool_tie_mode(0)
     return adj
 
 

@@ -487,11 +487,15 @@ def test_oracle_build_and_search_reach_high_recall():
 def test_grid_insert_baselines():
     """The reference's single-insert baselines (grid_insert.rs:46-250): every lattice point is
     inserted one by one into an index that starts with the start point only, then two searches.
-    The 1-D baseline is reproduced exactly.  The 3-D / 4-D lattices are full of exactly tied
-    distances and the reference orders a prune pool with `select_nth_unstable_by` +
-    `sort_unstable_by` (graph/internal/sorted_neighbors.rs:26-44), whose tie order is an
-    implementation detail of the Rust standard library and is not restated; there the oracle
-    (stable order) must still return the same distance profile and take the same number of hops."""
+    The lattices are full of exactly tied distances and the reference orders a prune pool with
+    `select_nth_unstable_by` + `sort_unstable_by` (graph/internal/sorted_neighbors.rs:26-44); the
+    oracle follows the simple parts of those standard-library algorithms (first maximum swapped
+    to the end, insertion sort up to 20 elements, run detection) but not ipnsort's quicksort:
+      * 1-D, 100 points: everything is reproduced (ids, distances, hops, comparisons, and the
+        provider's set_neighbors / append_neighbors write counts of the insert phase);
+      * 3-D, 5^3 points: write counts, hops, comparisons and the distance profile are reproduced,
+        the order among tied result ids is not;
+      * 4-D, 4^4 points: hops and the distance profile; the write counts agree within 2 %."""
     g = json.load(open(os.path.join(GOLDEN, "grid_insert.json")))
     assert len(g["cases"]) == 3
     for case in g["cases"]:
@@ -500,12 +504,12 @@ def test_grid_insert_baselines():
         assert n == case["num_inserted"]
         max_degree = 2 * dims
         pruned = min(max(max_degree - 2, 2), max_degree)     # grid_insert.rs:83-86
-        adj = O.build_graph(data, n, 1, O.L2, pruned, max_degree, 100, 1.2)
+        adj = O.build_graph(data, n, 1, O.L2, pruned, max_degree, 100, 1.2, tie_mode=1)
         assert adj[:, 0].max() <= max_degree
         sets, appends = O.last_build_counts()
-        if dims == 1:   # provider write counters of the insert phase (test/provider.rs Metrics)
+        if dims <= 3:   # provider write counters of the insert phase (test/provider.rs Metrics)
             assert (sets, appends) == (case["set_neighbors"], case["append_neighbors"])
-        else:           # tie order moves a handful of prune decisions, not the structure
+        else:
             assert abs(sets - case["set_neighbors"]) <= 0.02 * case["set_neighbors"]
             assert abs(appends - case["append_neighbors"]) <= 0.02 * case["append_neighbors"]
         idx = O.Index(data, adj, n, 1, O.L2)
@@ -515,9 +519,10 @@ def test_grid_insert_baselines():
             assert int(counts[0]) == s["num_results"]
             assert int(hops[0]) == s["hops"]
             assert [float(x) for x in dists[0]] == [r[1] for r in s["results"]]
+            if dims <= 3:
+                assert int(cmps[0]) == s["comparisons"]
             if dims == 1:
                 assert [int(i) for i in ids[0]] == [r[0] for r in s["results"]]
-                assert int(cmps[0]) == s["comparisons"]
 
 
 def test_flat_knn_baselines():
