@@ -47,6 +47,9 @@ constexpr int kGroup = 8;  // rows reduced together
 #ifndef DAB_V2_WIDE_LDS
 #define DAB_V2_WIDE_LDS 0   // experiment: 16-byte shared-memory reads with per-lane accumulator chains (needs DAB_V2_F32X2)
 #endif
+#ifndef DAB_V2_INT_BUILD
+#define DAB_V2_INT_BUILD 0  // experiment: i8 / u8 rows in search_kernel_v2 (exact integer distances)
+#endif
 #ifndef DAB_V2_F32X2
 #define DAB_V2_F32X2 1     // packed FADD2 / FFMA2 distance arithmetic
 #endif
@@ -228,6 +231,65 @@ __device__ __forceinline__ float wide_pass(const float* __restrict__ q, const ui
 }
 #endif
 
+#if DAB_V2_INT_BUILD
+// Experiment: i8 / u8 rows through the same hop structure.  Integer distances are exact in i32
+// (Sum(x-y)^2 = Sum x^2 + Sum y^2 - 2 Sum xy in wrapping arithmetic, as warp_int_multi), so any
+// summation order gives the reference's value: lane w owns 4-byte word w of all 8 staged rows.
+template <typename T>
+struct V2Int {
+    static constexpr bool value = false, is_signed = false;
+};
+template <>
+struct V2Int<int8_t> {
+    static constexpr bool value = true, is_signed = true;
+};
+template <>
+struct V2Int<uint8_t> {
+    static constexpr bool value = true, is_signed = false;
+};
+
+// value (before the post-op) of staged row u on every lane, for u = 0..7
+template <bool SIGNED, int KIND>
+__device__ __forceinline__ void group_distance_int(const uint8_t* __restrict__ q, const uint8_t* __restrict__ rows, uint32_t row_slot, int dim,
+                                                   int lane, int qq, float (&out)[kGroup]) {
+    int xy[kGroup], yy[kGroup];
+#pragma unroll
+    for (int g = 0; g < kGroup; ++g) xy[g] = yy[g] = 0;
+    const int nwords = dim >> 2;
+    for (int w = lane; w < nwords; w += 32) {
+        const int x = reinterpret_cast<const int*>(q)[w];
+#pragma unroll
+        for (int g = 0; g < kGroup; ++g) {
+            const int y = reinterpret_cast<const int*>(rows + (size_t)g * row_slot)[w];
+            xy[g] = dp4<SIGNED>(x, y, xy[g]);
+            if (KIND != KIND_IP) yy[g] = dp4<SIGNED>(y, y, yy[g]);
+        }
+    }
+    const int tail = dim & 3;
+    if (lane < tail) {
+        const int i = (nwords << 2) + lane;
+        const int x = byte_at<SIGNED>(q, i);
+#pragma unroll
+        for (int g = 0; g < kGroup; ++g) {
+            const int y = byte_at<SIGNED>(rows + (size_t)g * row_slot, i);
+            xy[g] += x * y;
+            if (KIND != KIND_IP) yy[g] += y * y;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < kGroup; ++g) {
+        const int sxy = __reduce_add_sync(kFull, xy[g]);
+        if (KIND == KIND_IP) {
+            out[g] = (float)sxy;
+        } else {
+            const int syy = __reduce_add_sync(kFull, yy[g]);
+            if (KIND == KIND_L2) out[g] = (float)(int)((unsigned)qq + (unsigned)syy - 2u * (unsigned)sxy);
+            else out[g] = cosine_finish((float)qq, (float)syy, (float)sxy);
+        }
+    }
+}
+#endif
+
 template <typename TD, int KIND, int POST, int QT>
 #ifndef DAB_V2_MIN_CTAS
 #define DAB_V2_MIN_CTAS 21
@@ -291,10 +353,25 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
         {
             const TD* s = p.query_rows ? reinterpret_cast<const TD*>(p.vectors + (size_t)p.query_rows[qidx] * p.row_stride)
                                        : reinterpret_cast<const TD*>(p.queries) + (size_t)qidx * dim;
-            for (int e = lane; e < dim; e += 32) qf[e] = to_f32(s[e]);
+#if DAB_V2_INT_BUILD
+            if constexpr (V2Int<TD>::value) {
+                uint8_t* qb = reinterpret_cast<uint8_t*>(qf);
+                const int qbytes = (dim + 3) & ~3;
+                for (int e = lane; e < qbytes; e += 32) qb[e] = e < dim ? reinterpret_cast<const uint8_t*>(s)[e] : 0;
+            } else
+#endif
+            {
+                for (int e = lane; e < dim; e += 32) qf[e] = to_f32(s[e]);
+            }
             for (uint32_t i = lane; i < nbk; i += 32) store_empty_bucket(table + (size_t)i * 8);
         }
         __syncwarp();
+#if DAB_V2_INT_BUILD
+        int qq = 0;  // Sum x^2 of the query (unused by inner product)
+        if constexpr (V2Int<TD>::value) {
+            if (KIND != KIND_IP) qq = warp_int_self<V2Int<TD>::is_signed>(reinterpret_cast<const uint8_t*>(qf), dim, lane);
+        }
+#endif
         DAB_PHASE(0);  // query staging + table clear
 
         uint32_t size = 0, cursor_lo = 0, cmps = 0, hops = 0, nvisited = 0, nrec = 0;
@@ -361,19 +438,31 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
             auto compute = [&](uint32_t g0) {
-#if DAB_V2_WIDE_LDS
-                constexpr int ROWS = 16 / (int)sizeof(TD), LPR = 32 / ROWS;
+#if DAB_V2_INT_BUILD
+                if constexpr (V2Int<TD>::value) {
+                    float vals[kGroup];
+                    group_distance_int<V2Int<TD>::is_signed, KIND>(reinterpret_cast<const uint8_t*>(qf), rows + (size_t)g0 * p.row_slot,
+                                                                  p.row_slot, dim, lane, qq, vals);
 #pragma unroll
-                for (int pass = 0; pass < kGroup / ROWS; ++pass) {
-                    const float r = wide_pass<TD, KIND>(qf, rows + (size_t)(g0 + pass * ROWS) * p.row_slot, p.row_slot, dim, lane);
-                    const uint32_t u = (uint32_t)(pass * ROWS + lane / LPR);
-                    if (lane % LPR == 0 && g0 + u < n) cd[c0 + g0 + u] = post_op<POST>(r);
-                }
-#else
-                const float r = group_distance<TD, KIND>(qf, rows + (size_t)g0 * p.row_slot, p.row_slot, dim, lane);
-                const uint32_t u = (((lane >> 3) & 1) << 2) | (((lane >> 4) & 1) << 1) | ((lane >> 2) & 1);
-                if ((lane & 3) == 0 && g0 + u < n) cd[c0 + g0 + u] = post_op<POST>(r);
+                    for (int u = 0; u < kGroup; ++u)
+                        if (lane == u && g0 + u < n) cd[c0 + g0 + u] = post_op<POST>(vals[u]);
+                } else
 #endif
+                {
+#if DAB_V2_WIDE_LDS
+                    constexpr int ROWS = 16 / (int)sizeof(TD), LPR = 32 / ROWS;
+#pragma unroll
+                    for (int pass = 0; pass < kGroup / ROWS; ++pass) {
+                        const float r = wide_pass<TD, KIND>(qf, rows + (size_t)(g0 + pass * ROWS) * p.row_slot, p.row_slot, dim, lane);
+                        const uint32_t u = (uint32_t)(pass * ROWS + lane / LPR);
+                        if (lane % LPR == 0 && g0 + u < n) cd[c0 + g0 + u] = post_op<POST>(r);
+                    }
+#else
+                    const float r = group_distance<TD, KIND>(qf, rows + (size_t)g0 * p.row_slot, p.row_slot, dim, lane);
+                    const uint32_t u = (((lane >> 3) & 1) << 2) | (((lane >> 4) & 1) << 1) | ((lane >> 2) & 1);
+                    if ((lane & 3) == 0 && g0 + u < n) cd[c0 + g0 + u] = post_op<POST>(r);
+#endif
+                }
             };
 #if DAB_V2_SPLIT_WAIT
             // the first reduce group is copied as its own cp.async group: its arithmetic runs
@@ -679,9 +768,15 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
 // success with `out` filled, or a negative DAB error code.
 int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchParamsV2& p, V2Launch& out) {
     if (getenv("DAB_DISABLE_V2")) return 1;
+#if DAB_V2_INT_BUILD
+    const bool v2_int = idx->dtype == DAB_I8 || idx->dtype == DAB_U8;
+    const MetricPlan plan = plan_for(idx->metric, v2_int);
+    if (plan.kind == KIND_COS && !v2_int) return 1;
+#else
     if (idx->dtype != DAB_F32 && idx->dtype != DAB_F16) return 1;
     const MetricPlan plan = plan_for(idx->metric, false);
     if (plan.kind == KIND_COS) return 1;
+#endif
     const uint32_t cap = l_search + idx->n_start;
     if (cap > 256 || idx->max_degree > 1000) return 1;
     const uint32_t row_bytes = (uint32_t)round_up((size_t)idx->dim * elem_size(idx->dtype), 16);
@@ -689,7 +784,11 @@ int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchPar
     const uint32_t row_slot = row_bytes;
     size_t off = 0;
     p.off_q = (uint32_t)off;
+#if DAB_V2_INT_BUILD
+    off += v2_int ? round_up(round_up((size_t)idx->dim, 4), 16) : round_up((size_t)idx->dim * 4, 16);
+#else
     off += round_up((size_t)idx->dim * 4, 16);
+#endif
     const size_t ncand_max = (size_t)beam * idx->max_degree;
     p.off_cid = (uint32_t)off;
     off += round_up(std::max<size_t>(ncand_max, idx->n_start) * 4, 16);
@@ -736,8 +835,22 @@ int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchPar
         else if (plan.post == POST_NEG) PICK_Q(TD, KIND_IP, POST_NEG);    \
         else PICK_Q(TD, KIND_IP, POST_ONE_MINUS);                         \
     } while (0)
+#if DAB_V2_INT_BUILD
+#define PICK_I(TD)                                                       \
+    do {                                                                 \
+        if (plan.kind == KIND_L2) PICK_Q(TD, KIND_L2, POST_ID);           \
+        else if (plan.kind == KIND_IP) PICK_Q(TD, KIND_IP, POST_NEG);     \
+        else PICK_Q(TD, KIND_COS, POST_ONE_MINUS);                        \
+    } while (0)
+    if (idx->dtype == DAB_F32) PICK_T(float);
+    else if (idx->dtype == DAB_F16) PICK_T(__half);
+    else if (idx->dtype == DAB_I8) PICK_I(int8_t);
+    else PICK_I(uint8_t);
+#undef PICK_I
+#else
     if (idx->dtype == DAB_F32) PICK_T(float);
     else PICK_T(__half);
+#endif
 #undef PICK_T
 #undef PICK_Q
 #undef PICK2
