@@ -53,6 +53,9 @@ constexpr int kGroup = 8;  // rows reduced together
 #ifndef DAB_V2_F32X2
 #define DAB_V2_F32X2 1     // packed FADD2 / FFMA2 distance arithmetic
 #endif
+#if DAB_V2_DEFER_CAS && DAB_V2_SPLIT_WAIT
+#error "DAB_V2_DEFER_CAS runs its postponed inserts in the single-group wait path only: do not combine it with DAB_V2_SPLIT_WAIT"
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
