@@ -54,3 +54,50 @@ def test_halfword_zero_trick_is_exact():
     half = np.where((s & np.uint64(0xFFFF)) == np.uint64(0xFFFF), 0, 1)
     truth = np.where(lo == 0, 0, 1)
     assert np.array_equal(half[has_empty], truth[has_empty])
+
+
+class Tag16Table:
+    """Sequential model of bucket16_insert (search_common.cuh): 16 entries of 16 bits per bucket,
+    entry = (displacement << 14) | tag, 0xFFFF empty, at most two buckets of displacement."""
+
+    def __init__(self, K, nbk):
+        self.kmask, self.magic, self.shift = tag_map(K, nbk)
+        self.nbk = nbk
+        self.t = np.full((nbk, 16), 0xFFFF, np.uint16)
+
+    def insert(self, id_):
+        """-> (newly_inserted, overflow)"""
+        h = (id_ * 0x9E3779B1) & 0xFFFFFFFF & self.kmask
+        tag = (h * self.magic) >> self.shift
+        b = h - tag * self.nbk
+        for d in range(3):
+            want = (d << 14) | tag
+            row = self.t[b]
+            if (row == want).any():
+                return False, False
+            empty = np.flatnonzero(row == 0xFFFF)
+            if len(empty):
+                row[empty[0]] = want
+                return True, False
+            b = 0 if b + 1 == self.nbk else b + 1
+        return False, True
+
+
+@pytest.mark.parametrize("K,nbk,n_ids,seed", [(20, 283, 3400, 0), (20, 283, 3900, 1), (17, 64, 800, 2), (12, 16, 200, 3), (20, 64, 880, 4)])
+def test_tag16_table_is_an_exact_set(K, nbk, n_ids, seed):
+    """Up to the 87.5 % load limit the kernel enforces (14 of 16 entries per bucket on average) the
+    table behaves exactly like a set; an overflow may only be reported, never a wrong answer."""
+    rng = np.random.default_rng(seed)
+    assert n_ids <= nbk * 14
+    universe = rng.choice(1 << K, n_ids, replace=False)
+    stream = np.concatenate([universe, rng.choice(universe, 3 * n_ids)])   # every id again, several times
+    rng.shuffle(stream)
+    table, seen, overflows = Tag16Table(K, nbk), set(), 0
+    for id_ in stream.tolist():
+        fresh, ovf = table.insert(id_)
+        if ovf:
+            overflows += 1          # the kernel re-runs the query with the 32-bit table
+            continue
+        assert fresh == (id_ not in seen), id_
+        seen.add(id_)
+    assert overflows <= 0.02 * len(stream)
