@@ -1,6 +1,8 @@
 // dab_api.cu — handle lifecycle, uploads, error reporting for libdiskann_b200.so.
 #include "dab_common.cuh"
 
+#include <cstdlib>
+
 #include <vector>
 
 namespace dab {
@@ -59,6 +61,24 @@ __global__ void repack_rows_kernel(const uint8_t* __restrict__ src, size_t src_s
     }
 }
 
+void Tuning::load() {
+    auto flag = [](const char* name) { return getenv(name) != nullptr; };
+    auto num = [](const char* name, long lo, long hi) -> int {
+        const char* t = getenv(name);
+        if (!t) return 0;
+        const long v = atol(t);
+        return v >= lo && v <= hi ? (int)v : 0;
+    };
+    disable_v2 = flag("DAB_DISABLE_V2");
+    disable_v3 = flag("DAB_DISABLE_V3");
+    frontier_narrow = flag("DAB_FRONTIER_NARROW");
+    v2_stage_bytes = num("DAB_V2_STAGE_BYTES", 1024, 65536);
+    v2_ctas_per_sm = num("DAB_V2_CTAS_PER_SM", 1, 64);
+    v3_table_bytes = num("DAB_V3_TABLE_BYTES", 512, 200 * 1024);
+    v3_ctas_per_sm = num("DAB_V3_CTAS_PER_SM", 1, 32);
+    test_visited_log2 = num("DAB_TEST_VISITED_LOG2", 8, 30);
+}
+
 }  // namespace dab
 
 using namespace dab;
@@ -97,6 +117,7 @@ int dab_create(dab_index** out, int dtype, int metric, uint32_t dim, uint64_t n_
     idx->row_stride = round_up((size_t)dim * elem_size(dtype), 32);
     idx->adj_stride = (uint32_t)round_up((size_t)max_degree + 1, 8);
     idx->h_stage.pinned_host = true;
+    idx->tune.load();
     cudaError_t e = cudaStreamCreateWithFlags(&idx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete idx;

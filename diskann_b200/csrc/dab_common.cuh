@@ -52,6 +52,19 @@ struct Scratch {
     void release();
 };
 
+// Tuning / test knobs, read from the environment ONCE at dab_create (none changes results).
+struct Tuning {
+    bool disable_v2 = false;       // DAB_DISABLE_V2: skip search_kernel_v2
+    bool disable_v3 = false;       // DAB_DISABLE_V3: skip search_kernel_v3 (shared-memory visited sets)
+    bool frontier_narrow = false;  // DAB_FRONTIER_NARROW: 4-byte-load frontier kernel
+    int v2_stage_bytes = 0;        // DAB_V2_STAGE_BYTES
+    int v2_ctas_per_sm = 0;        // DAB_V2_CTAS_PER_SM
+    int v3_table_bytes = 0;        // DAB_V3_TABLE_BYTES: visited-table bytes per warp
+    int v3_ctas_per_sm = 0;        // DAB_V3_CTAS_PER_SM: cap on resident CTAs
+    int test_visited_log2 = 0;     // DAB_TEST_VISITED_LOG2: tests force the overflow / retry path
+    void load();
+};
+
 }  // namespace dab
 
 struct dab_index {
@@ -85,9 +98,13 @@ struct dab_index {
 
     // search-side state learned across calls
     uint32_t hint_l = 0, hint_beam = 0, hint_visited = 0;  // largest visited set seen at (L, beam)
+    uint32_t v3_overflow_l = 0, v3_overflow_beam = 0;      // share of queries that outgrew the shared-memory
+    float v3_overflow_frac = 0.0f;                         // tables at (L, beam): search_kernel_v3 is skipped when large
     void* l2_window_ptr = nullptr;       // current persisting-L2 window (visited tables)
     size_t l2_window_bytes = 0;
     cudaStream_t l2_window_stream = nullptr;
+
+    dab::Tuning tune;
 
     uint64_t n_total() const { return n_points + n_start; }
 };

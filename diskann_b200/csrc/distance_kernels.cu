@@ -388,7 +388,7 @@ int launch_frontier(const dab_index* idx, const void* d_queries, uint32_t nq, co
     constexpr int U = 4;
     // NA = 4 schemas over f32 / f16 rows: the wide-load kernel (16 B per lane)
     const bool wide = plan.kind != KIND_COS && (idx->dtype == DAB_F32 || idx->dtype == DAB_F16) && idx->row_stride % 16 == 0 &&
-                      !getenv("DAB_FRONTIER_NARROW");  // env: tuning aid, forces the 4-byte-load kernel
+                      !idx->tune.frontier_narrow;  // DAB_FRONTIER_NARROW: tuning aid, forces the 4-byte-load kernel
     if (wide) {
         const int qstride = (dim + 3) & ~3;
         const size_t wsmem = (size_t)kWarpsPerBlock * qstride * 4;

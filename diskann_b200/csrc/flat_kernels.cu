@@ -218,6 +218,7 @@ flat_topk_kernel(const float* __restrict__ dist, size_t ld, uint32_t nq, uint32_
                     __syncwarp();
                 }
             }
+            __syncwarp();  // orders the reads above against the write below when nothing was moved (racecheck)
             if (lane == 0) {
                 td[pos] = dv;
                 ti[pos] = id;

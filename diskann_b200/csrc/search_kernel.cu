@@ -23,6 +23,7 @@
 #include "dab_common.cuh"
 #include "distance_device.cuh"
 #include "search_v2.cuh"
+#include "search_v3.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -117,6 +118,7 @@ __device__ __forceinline__ void queue_insert(float* qd, uint32_t* qi, uint32_t c
             __syncwarp();
         }
     }
+    __syncwarp();  // orders the reads above against the write below when nothing was moved (racecheck)
     if (lane == 0) {
         qd[pos] = d;
         qi[pos] = id;
@@ -534,10 +536,7 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
     // slots per warp: a power of two for the generic kernel, any multiple of 8 (32-byte buckets)
     // for v2 so that the tables of all resident warps stay inside the L2
     uint64_t slots = std::max<uint64_t>(256, (uint64_t)est + 1);
-    if (const char* t = getenv("DAB_TEST_VISITED_LOG2")) {  // tests force the overflow/retry path
-        int v = atoi(t);
-        if (v >= 8 && v <= 30) slots = 1ull << v;
-    }
+    if (idx->tune.test_visited_log2) slots = 1ull << idx->tune.test_visited_log2;  // tests force the overflow/retry path
 
     if ((rc = idx->s_counters.reserve(16 + (size_t)nq * 4))) return rc;
     uint32_t* d_counters = (uint32_t*)idx->s_counters.p;
@@ -570,6 +569,81 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
         }
     }
 #endif
+
+    // ---- first pass with the visited sets in shared memory (search_kernel_v3); queries that
+    // outgrow their table are collected in the overflow list and re-run below on global tables
+    {
+        SearchParamsV3 p3;
+        memset(&p3, 0, sizeof(p3));
+        V3Launch v3;
+        uint32_t need = 0;
+        if (idx->hint_visited > 0 && l_search <= idx->hint_l && beam <= idx->hint_beam)
+            need = (uint32_t)std::min<double>((double)idx->hint_visited * 1.15, 4.0e9);
+        if (idx->tune.test_visited_log2) need = (1u << idx->tune.test_visited_log2) / 2;
+        const bool skip = idx->v3_overflow_l == l_search && idx->v3_overflow_beam == beam && idx->v3_overflow_frac > 0.25f;
+        if (!skip && v3_prepare(idx, l_search, beam, need, p3, v3) == 0) {
+            p3.vectors = p.vectors;
+            p3.row_stride = p.row_stride;
+            p3.adj = p.adj;
+            p3.adj_stride = p.adj_stride;
+            p3.n_points = p.n_points;
+            p3.n_start = p.n_start;
+            p3.dim = p.dim;
+            p3.max_degree = p.max_degree;
+            p3.queries = p.queries;
+            p3.query_rows = p.query_rows;
+            p3.query_list = nullptr;
+            p3.n_work = nq;
+            p3.k = p.k;
+            p3.cap = p.cap;
+            p3.beam = p.beam;
+            p3.out_ids = p.out_ids;
+            p3.out_dists = p.out_dists;
+            p3.out_counts = p.out_counts;
+            p3.out_cmps = p.out_cmps;
+            p3.out_hops = p.out_hops;
+            p3.rec_ids = p.rec_ids;
+            p3.rec_dists = p.rec_dists;
+            p3.rec_counts = p.rec_counts;
+            p3.rec_cap = p.rec_cap;
+            p3.counters = d_counters;
+            p3.overflow_list = d_overflow;
+            DAB_CUDA(cudaMemsetAsync(d_counters, 0, 16, idx->stream));
+            // persistent warps: size the grid so every resident warp runs the same number of queries
+            const uint64_t max_warps = (uint64_t)v3.grid * kV3Warps;
+            const uint64_t rounds = (nq + max_warps - 1) / max_warps;
+            const uint64_t need_warps = (nq + rounds - 1) / rounds;
+            const int launch_grid = (int)((need_warps + kV3Warps - 1) / kV3Warps);
+            v3.kern<<<launch_grid, kV3Warps * 32, v3.smem_block, idx->stream>>>(p3);
+            DAB_LAUNCHED();
+            DAB_CUDA(cudaGetLastError());
+            uint32_t h_counters[3] = {0, 0, 0};
+            DAB_CUDA(cudaMemcpyAsync(h_counters, d_counters, 12, cudaMemcpyDeviceToHost, idx->stream));
+            DAB_CUDA(cudaStreamSynchronize(idx->stream));
+            const uint32_t n_over = h_counters[1];
+            if (!rec_ids) {
+                if (l_search != idx->hint_l || beam != idx->hint_beam) {
+                    idx->hint_l = l_search;
+                    idx->hint_beam = beam;
+                    idx->hint_visited = 0;
+                }
+                idx->hint_visited = std::max(idx->hint_visited, h_counters[2]);
+                idx->v3_overflow_l = l_search;
+                idx->v3_overflow_beam = beam;
+                idx->v3_overflow_frac = (float)n_over / (float)nq;
+            }
+            if (n_over == 0) return DAB_OK;
+            if ((rc = retry_list.reserve((size_t)n_over * 4))) return rc;
+            DAB_CUDA(cudaMemcpyAsync(retry_list.p, d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToDevice, idx->stream));
+            DAB_CUDA(cudaStreamSynchronize(idx->stream));
+            p.query_list = (const uint32_t*)retry_list.p;
+            p.n_work = n_over;
+            // the overflowed queries are the largest: size the global tables from the estimate again
+            if (!idx->tune.test_visited_log2)
+                slots = std::max<uint64_t>(slots, std::min<uint64_t>((uint64_t)(1.1 * idx->max_degree * 1.3 * (double)l_search) + 1,
+                                                                        (uint64_t)((double)idx->n_total() * 1.34) + 1));
+        }
+    }
 
     for (int pass = 0; pass < 6; ++pass) {
         const uint32_t warps = (uint32_t)grid * (use_v2 ? kV2WarpsHost : kSearchWarps);

@@ -48,7 +48,7 @@ constexpr int kGroup = 8;  // rows reduced together
 #define DAB_V2_WIDE_LDS 0   // experiment: 16-byte shared-memory reads with per-lane accumulator chains (needs DAB_V2_F32X2)
 #endif
 #ifndef DAB_V2_INT_BUILD
-#define DAB_V2_INT_BUILD 0  // experiment: i8 / u8 rows in search_kernel_v2 (exact integer distances)
+#define DAB_V2_INT_BUILD 1  // i8 / u8 rows in search_kernel_v2 (exact integer distances); GPU-validated in round 2
 #endif
 #ifndef DAB_V2_F32X2
 #define DAB_V2_F32X2 1     // packed FADD2 / FFMA2 distance arithmetic
@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
 // Returns 1 when this configuration is not covered by v2 (caller falls back to v1), 0 on
 // success with `out` filled, or a negative DAB error code.
 int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchParamsV2& p, V2Launch& out) {
-    if (getenv("DAB_DISABLE_V2")) return 1;
+    if (idx->tune.disable_v2) return 1;
 #if DAB_V2_INT_BUILD
     const bool v2_int = idx->dtype == DAB_I8 || idx->dtype == DAB_U8;
     const MetricPlan plan = plan_for(idx->metric, v2_int);
@@ -813,10 +813,7 @@ int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchPar
     const size_t fixed = off;
     // rows staged per round: as many as fit ~6 KB per warp, a multiple of the reduce group
     size_t stage_bytes = 6144;
-    if (const char* t = getenv("DAB_V2_STAGE_BYTES")) {  // tuning aid
-        const long v = atol(t);
-        if (v >= 1024 && v <= 65536) stage_bytes = (size_t)v;
-    }
+    if (idx->tune.v2_stage_bytes) stage_bytes = (size_t)idx->tune.v2_stage_bytes;  // tuning aid
     uint32_t stage = (uint32_t)std::max<size_t>(kGroup, (stage_bytes / row_slot) / kGroup * kGroup);
     stage = std::min<uint32_t>(stage, 32);
     p.stage_rows = stage;
@@ -866,10 +863,7 @@ int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchPar
         cudaGetLastError();
         return 1;
     }
-    if (const char* t = getenv("DAB_V2_CTAS_PER_SM")) {  // tuning aid
-        const int v = atoi(t);
-        if (v >= 1 && v < per_sm) per_sm = v;
-    }
+    if (idx->tune.v2_ctas_per_sm && idx->tune.v2_ctas_per_sm < per_sm) per_sm = idx->tune.v2_ctas_per_sm;  // tuning aid
     out.grid = per_sm * idx->sm_count;
     return 0;
 }

@@ -1,0 +1,681 @@
+// search_kernel_v3.cu — batched greedy search with the visited set in SHARED memory.
+//
+// Same semantics and bit-identical results as search_kernel.cu / search_kernel_v2.cu
+// (DiskANNIndex::search_internal, index.rs:1933-2000; NeighborPriorityQueue, queue.rs:130-318;
+// expand_beam, provider.rs:436-479, 620-690).  What changes against v2 is the number of
+// dependent GLOBAL-memory round trips a hop costs — v2 has three (bucket probe, CAS, row
+// copy), and its per-warp tables (62 MB for 3334 resident warps) do not stay in L2, so ≈3 GB of
+// the 8.8 GB a launch moves is random 32-byte table sectors (profiles/r01_table_footprint.md):
+//
+//   * the visited set of a query is an exact open-addressed table of 16-bit quotient tags in
+//     the warp's own shared memory (id -> (bucket, tag) is a bijection for ids < 2^K, so only
+//     the tag is stored: 16 entries per 32-byte bucket, displacement <= 2 buckets recorded in
+//     the tag's top two bits).  A probe is two LDS.128, an insert one 32-bit shared-memory CAS;
+//     a query that outgrows its table is handed to the global-table kernel (exactness is kept,
+//     only speed is lost);
+//   * the only HBM round trip left on a hop's critical path is the row gather itself: rows are
+//     read straight into registers with 16-byte loads, 8 (f32) / 4 (f16) lanes per row and up
+//     to 16 rows in flight per warp, each lane running the FMA chains of the SIMD slots it
+//     loaded (the lane mapping of frontier_wide_kernel, which reaches 0.84-0.96 of the measured
+//     HBM peak) — no staging buffer, which is what makes room for the table;
+//   * i8 / u8 rows use the same structure with exact i32 dot products (dp4a);
+//   * the adjacency row of the predicted next node is copied into shared memory while the
+//     current hop runs (as in v2), so a hop normally starts without a global round trip.
+#include "dab_common.cuh"
+#include "distance_device.cuh"
+#include "search_common.cuh"
+#include "search_v3.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+
+namespace dab {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- shared-memory visited set: 16 tags of 16 bits per 32-byte bucket -----------------------
+// Entries fill a bucket from slot 0 upwards and are never removed, so an id that is absent
+// from its home bucket while that bucket has a free slot is new; an id displaced to the d-th
+// following bucket (d <= 2) carries d in its top two bits.  0xFFFF marks an empty slot.
+__device__ __forceinline__ void load_bucket_smem(const uint32_t* bp, uint32_t (&s)[8]) {
+    const uint4 lo = reinterpret_cast<const uint4*>(bp)[0];
+    const uint4 hi = reinterpret_cast<const uint4*>(bp)[1];
+    s[0] = lo.x, s[1] = lo.y, s[2] = lo.z, s[3] = lo.w, s[4] = hi.x, s[5] = hi.y, s[6] = hi.z, s[7] = hi.w;
+}
+
+// true when the id was newly inserted (HashSet::insert); `ovf` is raised when the home bucket
+// and the two after it are full
+__device__ __forceinline__ bool smem16_insert(uint32_t* table, uint32_t n_buckets, uint32_t b, uint32_t tag, bool& ovf) {
+    uint32_t d = 0;
+    for (;;) {
+        uint32_t* bp = table + (size_t)b * 8;
+        uint32_t s[8];
+        load_bucket_smem(bp, s);
+        const uint32_t want = (d << 14) | tag, want2 = want * 0x10001u;
+        // "some 16-bit half of x is zero" <=> ((x - 0x00010001) & ~x & 0x80008000) != 0
+        uint32_t hit = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t x = s[k] ^ want2;
+            hit |= (x - 0x00010001u) & ~x & 0x80008000u;
+        }
+        if (hit) return false;
+        // first free slot: slots fill in order, so it is the number of occupied halves
+        int ew = -1;
+        uint32_t old = 0;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            if ((s[k] >> 16) == 0xFFFFu) {
+                ew = k;
+                old = s[k];
+            }
+        }
+        if (ew >= 0) {
+            const uint32_t neu = (old & 0xFFFFu) == 0xFFFFu ? (0xFFFF0000u | want) : ((old & 0xFFFFu) | (want << 16));
+            if (atomicCAS(bp + ew, old, neu) == old) return true;
+            continue;  // another lane of this warp changed the word: look at the bucket again
+        }
+        if (++d > 2) {
+            ovf = true;
+            return false;
+        }
+        b = b + 1 == n_buckets ? 0 : b + 1;
+    }
+}
+
+// Packed f32x2 arithmetic (FADD2 / FFMA2): each half is an IEEE round-to-nearest operation.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+template <int KIND>
+__device__ __forceinline__ uint64_t step2(uint64_t acc, uint64_t x2, uint64_t y2) {
+    if (KIND == KIND_L2) {
+        uint64_t c2;
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c2) : "l"(x2), "l"(y2));
+        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(acc) : "l"(c2), "l"(acc));
+    } else {
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(acc) : "l"(x2), "l"(y2), "l"(acc));
+    }
+    return acc;
+}
+
+__device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// All candidate rows of a hop are requested from HBM at once with one bulk L2 prefetch per row
+// (no registers, no shared memory); the register passes below then overlap with the fills and
+// find all but the first rows in L2.
+__device__ __forceinline__ void prefetch_rows(const uint8_t* __restrict__ vectors, size_t row_stride, const uint32_t* __restrict__ cid,
+                                              uint32_t n, uint32_t row_bytes16, int lane) {
+    for (uint32_t j = lane; j < n; j += 32) {
+        const uint8_t* src = vectors + (size_t)cid[j] * row_stride;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(row_bytes16) : "memory");
+    }
+}
+
+// ---- float rows: distances of candidates cid[0..n) into cd[0..n) ----------------------------
+// Lane mapping of frontier_wide_kernel (distance_kernels.cu): a 16-byte load carries EPL
+// elements of one 8-element SIMD block; block k belongs to accumulator k mod 4, so the lane
+// with (a, h) = (accumulator, half of the block) loads blocks a, a+4, a+8, ... and runs the FMA
+// chains of its EPL slots itself.  LPR lanes cover a row, a pass covers ROWS rows, P passes of U
+// loads each are in flight together.  Association as distance_device.cuh: (s0+s1)+(s2+s3),
+// zero-filled remainder on the combined vector, sum_tree.
+template <typename TD, int KIND, int POST, int P, int U>
+__device__ __forceinline__ void wide_distances(const float* __restrict__ q, const uint8_t* __restrict__ vectors, size_t row_stride,
+                                               const uint32_t* __restrict__ cid, uint32_t n, float* __restrict__ cd, int dim, int lane) {
+    constexpr int EPL = 16 / (int)sizeof(TD), LPR = 32 / EPL, ROWS = EPL, HALVES = 8 / EPL;
+    const int team = lane / LPR, tl = lane % LPR;
+    const int a = tl / HALVES, h = tl % HALVES;
+    const int nb8 = dim >> 3, full8 = dim & ~7, rem = dim & 7;
+    const int nm = (nb8 + 3) >> 2;  // 16-byte loads per lane per row (the last may be predicated off)
+    if (n > P * ROWS) prefetch_rows(vectors, row_stride, cid, n, (uint32_t)((dim * (int)sizeof(TD) + 15) & ~15), lane);
+    for (uint32_t j0 = 0; j0 < n; j0 += P * ROWS) {
+        const uint8_t* row[P];
+        bool act[P];
+#pragma unroll
+        for (int pp = 0; pp < P; ++pp) {
+            act[pp] = j0 + pp * ROWS < n;  // warp-uniform
+            const uint32_t jj = min(j0 + pp * ROWS + team, n - 1);
+            row[pp] = vectors + (size_t)cid[jj] * row_stride + 16 * tl;
+        }
+        uint64_t acc2[P][EPL / 2];
+#pragma unroll
+        for (int pp = 0; pp < P; ++pp)
+#pragma unroll
+            for (int i = 0; i < EPL / 2; ++i) acc2[pp][i] = 0ull;
+        for (int m0 = 0; m0 < nm; m0 += U) {
+            uint4 v[P][U];
+#pragma unroll
+            for (int pp = 0; pp < P; ++pp) {
+                if (act[pp]) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (a + 4 * (m0 + u) < nb8) v[pp][u] = ldg16(row[pp] + (size_t)(m0 + u) * (LPR * 16));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (a + 4 * (m0 + u) < nb8) {
+                    const float* qx = q + ((m0 + u) * (LPR * 16) + 16 * tl) / (int)sizeof(TD);
+                    float4 x[EPL / 4];
+#pragma unroll
+                    for (int i = 0; i < EPL / 4; ++i) x[i] = reinterpret_cast<const float4*>(qx)[i];
+#pragma unroll
+                    for (int pp = 0; pp < P; ++pp) {
+                        if (act[pp]) {
+                            if constexpr (sizeof(TD) == 2) {
+                                const __half2* hp = reinterpret_cast<const __half2*>(&v[pp][u]);
+                                const float2 f0 = __half22float2(hp[0]), f1 = __half22float2(hp[1]);
+                                const float2 f2 = __half22float2(hp[2]), f3 = __half22float2(hp[3]);
+                                acc2[pp][0] = step2<KIND>(acc2[pp][0], pack2(x[0].x, x[0].y), pack2(f0.x, f0.y));
+                                acc2[pp][1] = step2<KIND>(acc2[pp][1], pack2(x[0].z, x[0].w), pack2(f1.x, f1.y));
+                                acc2[pp][2] = step2<KIND>(acc2[pp][2], pack2(x[1].x, x[1].y), pack2(f2.x, f2.y));
+                                acc2[pp][3] = step2<KIND>(acc2[pp][3], pack2(x[1].z, x[1].w), pack2(f3.x, f3.y));
+                            } else {
+                                const uint4 w = v[pp][u];
+                                acc2[pp][0] = step2<KIND>(acc2[pp][0], pack2(x[0].x, x[0].y),
+                                                          pack2(__uint_as_float(w.x), __uint_as_float(w.y)));
+                                acc2[pp][1] = step2<KIND>(acc2[pp][1], pack2(x[0].z, x[0].w),
+                                                          pack2(__uint_as_float(w.z), __uint_as_float(w.w)));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int pp = 0; pp < P; ++pp) {
+            if (!act[pp]) continue;
+            float acc[EPL];
+#pragma unroll
+            for (int i = 0; i < EPL / 2; ++i) unpack2(acc2[pp][i], acc[2 * i], acc[2 * i + 1]);
+            // (s0 + s1) + (s2 + s3), slot-wise
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                acc[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], HALVES));
+                acc[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], 2 * HALVES));
+            }
+            if (rem) {  // zero-filled tail on the combined vector (simd.rs:733-744)
+                const TD* tail = reinterpret_cast<const TD*>(row[pp] - 16 * tl) + full8;
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) {
+                    const int l = EPL * h + i;
+                    const float x = l < rem ? q[full8 + l] : 0.0f;
+                    const float yv = l < rem ? ldg_elem(tail + l) : 0.0f;
+                    if (KIND == KIND_L2) {
+                        const float dd = __fsub_rn(x, yv);
+                        acc[i] = __fmaf_rn(dd, dd, acc[i]);
+                    } else {
+                        acc[i] = __fmaf_rn(x, yv, acc[i]);
+                    }
+                }
+            }
+            float r;
+            if constexpr (HALVES == 1) {
+                r = __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[4]), __fadd_rn(acc[2], acc[6])),
+                              __fadd_rn(__fadd_rn(acc[1], acc[5]), __fadd_rn(acc[3], acc[7])));
+            } else {
+                float ts[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ts[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], 1));  // x_i + x_{i+4}
+                r = __fadd_rn(__fadd_rn(ts[0], ts[2]), __fadd_rn(ts[1], ts[3]));
+            }
+            const uint32_t jj = j0 + pp * ROWS + team;
+            if (tl == 0 && jj < n) cd[jj] = post_op<POST>(r);
+        }
+    }
+}
+
+// ---- i8 / u8 rows: exact i32 arithmetic, so any summation order gives the reference's value --
+// 8 lanes per row, 16 bytes per lane per load, 4 rows per pass, P passes in flight.
+// q: query bytes in shared memory, zero-padded to a multiple of 16; qq = sum q*q.
+template <bool SIGNED, int KIND, int POST, int P>
+__device__ __forceinline__ void wide_distances_int(const uint8_t* __restrict__ q, int qq, const uint8_t* __restrict__ vectors,
+                                                   size_t row_stride, const uint32_t* __restrict__ cid, uint32_t n,
+                                                   float* __restrict__ cd, int dim, int lane) {
+    constexpr int ROWS = 4;
+    const int team = lane >> 3, tl = lane & 7;
+    const int nfull = dim >> 4, tail = dim & 15;
+    const int nm = (nfull + 7) >> 3;
+    if (n > P * ROWS) prefetch_rows(vectors, row_stride, cid, n, (uint32_t)((dim + 15) & ~15), lane);
+    for (uint32_t j0 = 0; j0 < n; j0 += P * ROWS) {
+        const uint8_t* row[P];
+        bool act[P];
+        int xy[P], yy[P];
+#pragma unroll
+        for (int pp = 0; pp < P; ++pp) {
+            act[pp] = j0 + pp * ROWS < n;
+            const uint32_t jj = min(j0 + pp * ROWS + team, n - 1);
+            row[pp] = vectors + (size_t)cid[jj] * row_stride;
+            xy[pp] = yy[pp] = 0;
+        }
+        for (int m = 0; m < nm; ++m) {
+            const int c = m * 8 + tl;
+            if (c < nfull) {
+                uint4 v[P];
+#pragma unroll
+                for (int pp = 0; pp < P; ++pp)
+                    if (act[pp]) v[pp] = ldg16(row[pp] + (size_t)c * 16);
+                const uint4 x = reinterpret_cast<const uint4*>(q)[c];
+#pragma unroll
+                for (int pp = 0; pp < P; ++pp) {
+                    if (act[pp]) {
+                        xy[pp] = dp4<SIGNED>((int)x.x, (int)v[pp].x, xy[pp]);
+                        xy[pp] = dp4<SIGNED>((int)x.y, (int)v[pp].y, xy[pp]);
+                        xy[pp] = dp4<SIGNED>((int)x.z, (int)v[pp].z, xy[pp]);
+                        xy[pp] = dp4<SIGNED>((int)x.w, (int)v[pp].w, xy[pp]);
+                        if (KIND != KIND_IP) {
+                            yy[pp] = dp4<SIGNED>((int)v[pp].x, (int)v[pp].x, yy[pp]);
+                            yy[pp] = dp4<SIGNED>((int)v[pp].y, (int)v[pp].y, yy[pp]);
+                            yy[pp] = dp4<SIGNED>((int)v[pp].z, (int)v[pp].z, yy[pp]);
+                            yy[pp] = dp4<SIGNED>((int)v[pp].w, (int)v[pp].w, yy[pp]);
+                        }
+                    }
+                }
+            }
+        }
+        if (tail) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int i = (nfull << 4) + tl * 2 + t;
+                if (tl * 2 + t < tail) {
+                    const int x = byte_at<SIGNED>(q, i);
+#pragma unroll
+                    for (int pp = 0; pp < P; ++pp) {
+                        if (act[pp]) {
+                            const int y = SIGNED ? (int)(int8_t)__ldg(row[pp] + i) : (int)__ldg(row[pp] + i);
+                            xy[pp] += x * y;
+                            if (KIND != KIND_IP) yy[pp] += y * y;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int pp = 0; pp < P; ++pp) {
+            if (!act[pp]) continue;
+            int sxy = xy[pp], syy = yy[pp];
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1) {
+                sxy += __shfl_xor_sync(kFull, sxy, o);
+                if (KIND != KIND_IP) syy += __shfl_xor_sync(kFull, syy, o);
+            }
+            float r;
+            if (KIND == KIND_IP) r = (float)sxy;
+            else if (KIND == KIND_L2) r = (float)(int)((unsigned)qq + (unsigned)syy - 2u * (unsigned)sxy);
+            else r = cosine_finish((float)qq, (float)syy, (float)sxy);
+            const uint32_t jj = j0 + pp * ROWS + team;
+            if (tl == 0 && jj < n) cd[jj] = post_op<POST>(r);
+        }
+    }
+}
+
+template <typename T>
+struct IsInt {
+    static constexpr bool value = std::is_same<T, int8_t>::value || std::is_same<T, uint8_t>::value;
+};
+
+#ifndef DAB_V3_MIN_CTAS
+#define DAB_V3_MIN_CTAS 4
+#endif
+#ifndef DAB_V3_P_F32
+#define DAB_V3_P_F32 2  // f32 rows: passes (of 4 rows, 4 x 16-byte loads per lane each) in flight
+#endif
+#ifndef DAB_V3_P_F16
+#define DAB_V3_P_F16 2  // f16 rows: passes (of 8 rows) in flight
+#endif
+#ifndef DAB_V3_U_F16
+#define DAB_V3_U_F16 4  // f16 rows: 16-byte loads per lane per pass in flight
+#endif
+#ifndef DAB_V3_P_INT
+#define DAB_V3_P_INT 4  // i8 / u8 rows: passes (of 4 rows, one 16-byte load per lane each) in flight
+#endif
+
+}  // namespace
+
+template <typename TD, int KIND, int POST, int QT>
+__global__ void __launch_bounds__(kV3Warps * 32, DAB_V3_MIN_CTAS) search_kernel_v3(const SearchParamsV3 p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr bool kInt = IsInt<TD>::value;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint8_t* base = smem + (size_t)wib * p.warp_smem;
+    float* qf = reinterpret_cast<float*>(base + p.off_q);
+    float* qd = reinterpret_cast<float*>(base + p.off_qd);
+    uint32_t* qi = reinterpret_cast<uint32_t*>(base + p.off_qi);
+    uint32_t* cid = reinterpret_cast<uint32_t*>(base + p.off_cid);
+    float* cd = reinterpret_cast<float*>(base + p.off_cd);
+    uint32_t* beam_ids = reinterpret_cast<uint32_t*>(base + p.off_beam);
+    uint32_t* adjbuf = reinterpret_cast<uint32_t*>(base + p.off_adj);
+    const uint32_t adjbuf_a = smem_addr(adjbuf);
+    uint32_t* table = reinterpret_cast<uint32_t*>(base + p.off_table);
+    const uint32_t nbk = p.n_buckets;
+    const Tag16Map tmap{p.tag_kmask, nbk, p.tag_magic, p.tag_shift};
+    const uint64_t n_total = p.n_points + p.n_start;
+    const int dim = (int)p.dim;
+
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(p.counters, 1u);
+        w = __shfl_sync(kFull, w, 0);
+        if (w >= p.n_work) break;
+        const uint32_t qidx = p.query_list ? p.query_list[w] : w;
+
+        __syncwarp();
+        {
+            const TD* s = p.query_rows ? reinterpret_cast<const TD*>(p.vectors + (size_t)p.query_rows[qidx] * p.row_stride)
+                                       : reinterpret_cast<const TD*>(p.queries) + (size_t)qidx * dim;
+            if constexpr (kInt) {
+                uint8_t* qb = reinterpret_cast<uint8_t*>(qf);
+                const int qbytes = (dim + 15) & ~15;
+                for (int e = lane; e < qbytes; e += 32) qb[e] = e < dim ? reinterpret_cast<const uint8_t*>(s)[e] : 0;
+            } else {
+                for (int e = lane; e < dim; e += 32) qf[e] = to_f32(s[e]);
+            }
+            const uint4 e4 = make_uint4(kEmptyV2, kEmptyV2, kEmptyV2, kEmptyV2);
+            for (uint32_t i = lane; i < nbk * 2; i += 32) reinterpret_cast<uint4*>(table)[i] = e4;
+        }
+        __syncwarp();
+        int qq = 0;  // sum x^2 of an integer query (unused by inner product)
+        if constexpr (kInt) {
+            if (KIND != KIND_IP) qq = warp_int_self<std::is_same<TD, int8_t>::value>(reinterpret_cast<const uint8_t*>(qf), dim, lane);
+        }
+        (void)qq;
+
+        uint32_t size = 0, cursor_lo = 0, cmps = 0, hops = 0, nvisited = 0, nrec = 0;
+        uint32_t pred = kEmptyV2;  // node whose adjacency row sits in adjbuf
+        bool overflow = false;
+
+        auto distances = [&](uint32_t c0, uint32_t n) {
+            if constexpr (kInt) {
+                wide_distances_int<std::is_same<TD, int8_t>::value, KIND, POST, DAB_V3_P_INT>(reinterpret_cast<const uint8_t*>(qf), qq, p.vectors,
+                                                                                 p.row_stride, cid + c0, n, cd + c0, dim, lane);
+            } else if constexpr (sizeof(TD) == 2) {
+                wide_distances<TD, KIND, POST, DAB_V3_P_F16, DAB_V3_U_F16>(qf, p.vectors, p.row_stride, cid + c0, n, cd + c0, dim, lane);
+            } else {
+                wide_distances<TD, KIND, POST, DAB_V3_P_F32, 4>(qf, p.vectors, p.row_stride, cid + c0, n, cd + c0, dim, lane);
+            }
+            __syncwarp();
+        };
+
+        // ---- start points (SearchAccessor::start_point_distances, provider.rs:406-433)
+        for (uint32_t s0 = 0; s0 < p.n_start; s0 += 32) {
+            const uint32_t n = min(32u, p.n_start - s0);
+            bool ovf = false;
+            if ((uint32_t)lane < n) {
+                const uint32_t id = (uint32_t)p.n_points + s0 + lane;
+                cid[lane] = id;
+                uint32_t b, tg;
+                tag16_of(id, tmap, b, tg);
+                smem16_insert(table, nbk, b, tg, ovf);
+            }
+            if (__any_sync(kFull, ovf)) overflow = true;
+            __syncwarp();
+            distances(0, n);
+            merge_round<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, 0, n, lane);
+            nvisited += n;
+            cmps += n;
+        }
+        if (nvisited > p.visited_limit) overflow = true;
+
+        // ---- greedy loop (index.rs:1961-1992)
+        while (!overflow) {
+            const uint32_t lim = min(p.cap, size);
+            uint32_t nb = 0;
+            while (nb < p.beam) {  // closest_notvisited x beam_width (queue.rs:297-313)
+                const uint32_t idx = first_unvisited(qi, cursor_lo, lim, lane);
+                if (idx >= lim) break;
+                const uint32_t id = qi[idx];
+                __syncwarp();
+                if (lane == 0) {
+                    qi[idx] = id | kFlagV2;
+                    beam_ids[nb] = id;
+                    if (p.rec_ids && nrec < p.rec_cap) {
+                        p.rec_ids[(size_t)qidx * p.rec_cap + nrec] = id;
+                        p.rec_dists[(size_t)qidx * p.rec_cap + nrec] = qd[idx];
+                    }
+                }
+                cursor_lo = idx + 1;
+                ++nrec;
+                ++nb;
+                __syncwarp();
+            }
+            if (nb == 0) break;
+
+            uint32_t ncand = 0;
+            for (uint32_t b = 0; b < nb; ++b) {
+                const uint32_t node = beam_ids[b];
+                const uint32_t* row = p.adj + (size_t)node * p.adj_stride;
+                uint32_t wd[3];
+                if (b == 0 && p.adj_words) {
+                    // the speculative copy of the previous hop must be drained before the buffer
+                    // is read or re-targeted
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                }
+                if (b == 0 && node == pred) {
+                    wd[0] = adjbuf[lane];
+                    wd[1] = 32 + lane < p.adj_words ? adjbuf[32 + lane] : kEmptyV2;
+                    wd[2] = 64 + lane < p.adj_words ? adjbuf[64 + lane] : kEmptyV2;
+                    __syncwarp();
+                } else {
+                    wd[0] = __ldg(row + lane);
+                    wd[1] = 32 + lane < p.adj_stride ? __ldg(row + 32 + lane) : kEmptyV2;
+                    wd[2] = 64 + lane < p.adj_stride ? __ldg(row + 64 + lane) : kEmptyV2;
+                }
+                if (b == 0) {
+                    // speculative: the next hop most likely expands the now-first unvisited entry
+                    const uint32_t nxt = first_unvisited(qi, cursor_lo, lim, lane);
+                    pred = kEmptyV2;
+                    if (nxt < lim && p.adj_words) {
+                        const uint32_t nid = qi[nxt] & ~kFlagV2;
+                        const uint32_t* nrow = p.adj + (size_t)nid * p.adj_stride;
+                        pred = nid;
+                        if ((uint32_t)lane * 4 < p.adj_words)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(adjbuf_a + lane * 16), "l"(nrow + lane * 4) : "memory");
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    }
+                }
+                const uint32_t deg = min(__shfl_sync(kFull, wd[0], 0), p.max_degree);
+                if (nvisited + deg > p.visited_limit) {  // the table could pass its load limit: global-table kernel
+                    overflow = true;
+                    break;
+                }
+                bool ovf = false;
+                auto filter = [&](uint32_t word, uint32_t j) {
+                    bool inserted = false;
+                    // ids beyond 2^K cannot be in bounds and never reach the outputs: not tracked
+                    if (j >= 1 && j <= deg && word <= tmap.kmask) {
+                        uint32_t bk, tg;
+                        tag16_of(word, tmap, bk, tg);
+                        inserted = smem16_insert(table, nbk, bk, tg, ovf);
+                    }
+                    const bool isnew = inserted && word < n_total;  // is_in_bounds
+                    const unsigned mi = __ballot_sync(kFull, inserted);
+                    const unsigned mn = __ballot_sync(kFull, isnew);
+                    if (isnew) cid[ncand + __popc(mn & ((1u << lane) - 1u))] = word;
+                    ncand += __popc(mn);
+                    nvisited += __popc(mi);
+                };
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    if ((uint32_t)c * 32 <= deg) filter(wd[c], c * 32 + lane);
+                // adjacency rows longer than 95 neighbours: remaining chunks
+                for (uint32_t c0 = 96; c0 < deg + 1; c0 += 32) {
+                    const uint32_t j = c0 + lane;
+                    filter(j < p.adj_stride ? __ldg(row + j) : kEmptyV2, j);
+                }
+                if (__any_sync(kFull, ovf)) {
+                    overflow = true;
+                    break;
+                }
+            }
+            if (overflow) break;
+            __syncwarp();
+
+            distances(0, ncand);
+
+            // best.insert for every neighbour in adjacency order (index.rs:1986-1988)
+            for (uint32_t c0 = 0; c0 < ncand; c0 += 32)
+                merge_round<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, c0, min(32u, ncand - c0), lane);
+            cmps += ncand;
+            hops += nb;
+        }
+
+        if (overflow) {
+            if (p.adj_words) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t o = atomicAdd(p.counters + 1, 1u);
+                p.overflow_list[o] = qidx;
+            }
+            continue;
+        }
+
+        // ---- post-process: drop start points, first k (provider.rs:907-950)
+        {
+            const uint32_t n = min(p.cap, size);
+            uint32_t count = 0;
+            for (uint32_t b = 0; b < n && count < p.k; b += 32) {
+                const uint32_t i = b + lane;
+                const uint32_t id = i < n ? (qi[i] & ~kFlagV2) : kEmptyV2;
+                const bool keep = i < n && id < p.n_points;
+                const unsigned m = __ballot_sync(kFull, keep);
+                const uint32_t pos = count + __popc(m & ((1u << lane) - 1u));
+                if (keep && pos < p.k) {
+                    p.out_ids[(size_t)qidx * p.k + pos] = id;
+                    p.out_dists[(size_t)qidx * p.k + pos] = qd[i];
+                }
+                count += __popc(m);
+            }
+            count = min(count, p.k);
+            for (uint32_t i = count + lane; i < p.k; i += 32) {
+                p.out_ids[(size_t)qidx * p.k + i] = kEmptyV2;
+                p.out_dists[(size_t)qidx * p.k + i] = __int_as_float(0x7F800000);
+            }
+            if (lane == 0) {
+                atomicMax(p.counters + 2, nvisited);
+                if (p.out_counts) p.out_counts[qidx] = count;
+                if (p.out_cmps) p.out_cmps[qidx] = cmps;
+                if (p.out_hops) p.out_hops[qidx] = hops;
+                if (p.rec_counts) p.rec_counts[qidx] = min(nrec, p.rec_cap);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host side
+int v3_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, uint32_t visited_need, SearchParamsV3& p, V3Launch& out) {
+    if (idx->tune.disable_v3) return 1;
+    const bool is_int = idx->dtype == DAB_I8 || idx->dtype == DAB_U8;
+    const MetricPlan plan = plan_for(idx->metric, is_int);
+    if (plan.kind == KIND_COS && !is_int) return 1;  // float cosine: NA = 2 schema, generic kernel
+    const uint32_t cap = l_search + idx->n_start;
+    if (cap > 256 || idx->max_degree > 1000) return 1;
+    if ((idx->row_stride & 15) != 0) return 1;
+    // quotient tags: ids < 2^K, tag = h / n_buckets must fit 14 bits
+    uint32_t K = 8;
+    while (((uint64_t)1 << K) < idx->n_total()) ++K;
+    if (K > 30) return 1;
+    const uint64_t min_buckets = std::max<uint64_t>(16, (((uint64_t)1 << K) + 16383) >> 14);
+
+    size_t off = 0;
+    p.off_q = (uint32_t)off;
+    off += is_int ? round_up((size_t)idx->dim, 16) : round_up((size_t)idx->dim * 4, 16);
+    const size_t ncand_max = std::max<size_t>((size_t)beam * idx->max_degree, std::min<uint32_t>(32, idx->n_start));
+    p.off_cid = (uint32_t)off;
+    off += round_up(ncand_max * 4, 16);
+    p.off_cd = (uint32_t)off;
+    off += round_up(ncand_max * 4, 16);
+    p.off_beam = (uint32_t)off;
+    off += round_up((size_t)beam * 4, 16);
+    p.adj_words = idx->adj_stride % 4 == 0 ? (uint32_t)std::min<size_t>(idx->adj_stride, 96) : 0;
+    p.off_adj = (uint32_t)off;
+    off += (size_t)p.adj_words * 4;
+    const size_t cap_pad = round_up(cap, 4);
+    p.off_qd = (uint32_t)off;
+    off += cap_pad * 4;
+    p.off_qi = (uint32_t)off;
+    off += cap_pad * 4;
+    off = round_up(off, 32);
+    p.off_table = (uint32_t)off;
+    const size_t fixed = off;
+
+    // table size: what the visited sets seen so far need at 87.5 % load (+ one adjacency row of
+    // slack), bounded so that at least kMinWarps warps stay resident per SM; without a hint, the
+    // size that keeps kTargetWarps resident.  Queries that outgrow it re-run on the global tables.
+    const size_t smem_sm = 227 * 1024;  // per SM, 1 KB per CTA is reserved by the system
+    auto table_bytes_at = [&](int ctas) -> long long {
+        const long long per_cta = (long long)(smem_sm / ctas) - 1024;
+        return (per_cta / kV3Warps - (long long)fixed) / 32 * 32;
+    };
+    const int ctas_min = 2, ctas_target = 4;
+    long long tbytes;
+    if (visited_need) {
+        const uint64_t slots = (uint64_t)((visited_need + idx->max_degree) / 0.875) + 16;
+        tbytes = (long long)round_up(slots * 2, 32);
+        if (tbytes > table_bytes_at(ctas_min)) tbytes = table_bytes_at(ctas_min);
+    } else {
+        tbytes = table_bytes_at(ctas_target);
+    }
+    if (idx->tune.v3_table_bytes > 0) tbytes = (long long)round_up((size_t)idx->tune.v3_table_bytes, 32);
+    if (tbytes < (long long)min_buckets * 32) tbytes = (long long)min_buckets * 32;
+    if (tbytes > table_bytes_at(1)) return 1;
+    uint64_t nbk = (uint64_t)tbytes / 32;
+    uint32_t sbits = 0;
+    while (((uint64_t)1 << sbits) < nbk) ++sbits;
+    if (K + sbits > 32) return 1;
+    p.n_buckets = (uint32_t)nbk;
+    p.tag_kmask = (uint32_t)(((uint64_t)1 << K) - 1);
+    p.tag_shift = K + sbits;
+    p.tag_magic = (uint32_t)((((uint64_t)1 << (K + sbits)) + nbk - 1) / nbk);
+    p.visited_limit = (uint32_t)(nbk * 14);  // 87.5 % of 16 tags per bucket
+    out.capacity = p.visited_limit > idx->max_degree ? p.visited_limit - idx->max_degree : 0;
+    if (out.capacity < 4 * idx->max_degree) return 1;
+    p.warp_smem = (uint32_t)round_up(fixed + (size_t)tbytes, 128);
+    out.smem_block = (size_t)p.warp_smem * kV3Warps;
+
+#define PICK2(TD, K_, P_, Q_) out.kern = search_kernel_v3<TD, K_, P_, Q_>
+#define PICK_Q(TD, K_, P_)                 \
+    do {                                   \
+        if (cap <= 128) PICK2(TD, K_, P_, 4); \
+        else PICK2(TD, K_, P_, 8);         \
+    } while (0)
+#define PICK_T(TD)                                                       \
+    do {                                                                 \
+        if (plan.kind == KIND_L2) PICK_Q(TD, KIND_L2, POST_ID);           \
+        else if (plan.post == POST_NEG) PICK_Q(TD, KIND_IP, POST_NEG);    \
+        else PICK_Q(TD, KIND_IP, POST_ONE_MINUS);                         \
+    } while (0)
+#define PICK_I(TD)                                                       \
+    do {                                                                 \
+        if (plan.kind == KIND_L2) PICK_Q(TD, KIND_L2, POST_ID);           \
+        else if (plan.kind == KIND_IP) PICK_Q(TD, KIND_IP, POST_NEG);     \
+        else PICK_Q(TD, KIND_COS, POST_ONE_MINUS);                        \
+    } while (0)
+    if (idx->dtype == DAB_F32) PICK_T(float);
+    else if (idx->dtype == DAB_F16) PICK_T(__half);
+    else if (idx->dtype == DAB_I8) PICK_I(int8_t);
+    else PICK_I(uint8_t);
+#undef PICK_I
+#undef PICK_T
+#undef PICK_Q
+#undef PICK2
+    if (cudaFuncSetAttribute(out.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out.smem_block) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, out.kern, kV3Warps * 32, out.smem_block) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return 1;
+    }
+    if (idx->tune.v3_ctas_per_sm && idx->tune.v3_ctas_per_sm < per_sm) per_sm = idx->tune.v3_ctas_per_sm;  // tuning aid
+    out.grid = per_sm * idx->sm_count;
+    return 0;
+}
+
+}  // namespace dab
