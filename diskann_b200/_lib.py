@@ -24,6 +24,9 @@ SYMBOLS = {
     "dab_upload_graph_device": (_i, [_vp, _vp, _u32, _u64, _u64]),
     "dab_download_graph": (_i, [_vp, _vp, _u32, _u64, _u64]),
     "dab_upload_pq": (_i, [_vp, _vp, _u32, _vp, _u32, _vp]),
+    "dab_pq_train": (_i, [_vp, _vp, _u64, _u32, _u32, _u32, _u64]),
+    "dab_pq_encode_all": (_i, [_vp]),
+    "dab_pq_download": (_i, [_vp, _vp, _vp, _vp]),
     "dab_pair_distances": (_i, [_i, _i, _i, _u32, _vp, _vp, _u64, _vp, _i]),
     "dab_distances": (_i, [_vp, _vp, _u32, _vp, _u32, _vp]),
     "dab_distances_device": (_i, [_vp, _vp, _u32, _vp, _u32, _vp]),

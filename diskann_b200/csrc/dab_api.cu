@@ -71,6 +71,7 @@ void Tuning::load() {
     };
     disable_v2 = flag("DAB_DISABLE_V2");
     disable_v3 = flag("DAB_DISABLE_V3");
+    v3_generic = flag("DAB_V3_GENERIC");
     frontier_narrow = flag("DAB_FRONTIER_NARROW");
     v2_stage_bytes = num("DAB_V2_STAGE_BYTES", 1024, 65536);
     v2_ctas_per_sm = num("DAB_V2_CTAS_PER_SM", 1, 64);
@@ -274,6 +275,7 @@ int dab_upload_pq(dab_index* idx, const float* pivots, uint32_t n_centers, const
         DAB_CUDA(cudaMemset(idx->d_codes, 0, idx->n_total() * (size_t)n_chunks));
     idx->pq_chunks = n_chunks;
     idx->pq_centers = n_centers;
+    idx->pq_codes_ready = codes != nullptr;
     return DAB_OK;
 }
 

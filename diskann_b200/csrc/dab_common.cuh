@@ -60,6 +60,7 @@ struct Tuning {
     int v2_stage_bytes = 0;        // DAB_V2_STAGE_BYTES
     int v2_ctas_per_sm = 0;        // DAB_V2_CTAS_PER_SM
     int v3_table_bytes = 0;        // DAB_V3_TABLE_BYTES: visited-table bytes per warp
+    bool v3_generic = false;       // DAB_V3_GENERIC: generic distance loop also for 32 / 64 / 96 / 128-d f32 rows
     int v3_ctas_per_sm = 0;        // DAB_V3_CTAS_PER_SM: cap on resident CTAs
     int test_visited_log2 = 0;     // DAB_TEST_VISITED_LOG2: tests force the overflow / retry path
     void load();
@@ -91,6 +92,7 @@ struct dab_index {
     uint32_t* d_offsets = nullptr; // [n_chunks + 1]
     uint8_t* d_codes = nullptr;    // [n_total][n_chunks]
     uint32_t pq_chunks = 0, pq_centers = 0;
+    bool pq_codes_ready = false;   // codes uploaded (dab_upload_pq) or produced (dab_pq_encode_all)
 
     // scratch (grow-only)
     dab::Scratch s_queries, s_ids, s_out, s_out2, s_tables, s_counters, s_stats;

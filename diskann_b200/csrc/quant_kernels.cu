@@ -247,6 +247,31 @@ static int launch_lut(const dab_index* idx, const float* d_queries, uint32_t nq,
 
 using namespace dab;
 
+namespace dab {
+// pq_encode_kernel over n f32 vectors already on the device; codes written to d_codes_out (device).
+// Used by dab_pq_encode_all (pq_train.cu).  Rows that are infinitely far from every centre
+// (inf / NaN input) are reported like BasicTable::compress_into does.
+int pq_encode_device(dab_index* idx, const float* d_vectors, uint64_t n, uint8_t* d_codes_out) {
+    int rc;
+    if ((rc = idx->s_counters.reserve(16))) return rc;
+    unsigned long long* d_bad = (unsigned long long*)idx->s_counters.p;
+    DAB_CUDA(cudaMemsetAsync(d_bad, 0xFF, 8, idx->stream));
+    const uint64_t warps = n * idx->pq_chunks;
+    const int grid = (int)std::min<uint64_t>((warps + 7) / 8, (uint64_t)idx->sm_count * 8);
+    pq_encode_kernel<<<grid, 256, 0, idx->stream>>>(d_vectors, n, idx->d_pivots, idx->pq_centers, idx->d_offsets, idx->pq_chunks, idx->dim,
+                                                    d_codes_out, d_bad);
+    DAB_LAUNCHED();
+    DAB_CUDA(cudaGetLastError());
+    unsigned long long bad = 0;
+    DAB_CUDA(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, idx->stream));
+    DAB_CUDA(cudaStreamSynchronize(idx->stream));
+    if (bad != ~0ull)
+        return fail(DAB_ERR_INVALID_ARGUMENT, "pq encode: vector %llu chunk %llu is infinitely far from every center (inf/NaN input)",
+                    bad / idx->pq_chunks, bad % idx->pq_chunks);
+    return DAB_OK;
+}
+}  // namespace dab
+
 extern "C" {
 
 int dab_pq_populate_lut(dab_index* idx, const float* queries, uint32_t nq, int metric, float* out_lut) {

@@ -573,48 +573,39 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
     // ---- first pass with the visited sets in shared memory (search_kernel_v3); queries that
     // outgrow their table are collected in the overflow list and re-run below on global tables
     {
-        SearchParamsV3 p3;
-        memset(&p3, 0, sizeof(p3));
-        V3Launch v3;
         uint32_t need = 0;
         if (idx->hint_visited > 0 && l_search <= idx->hint_l && beam <= idx->hint_beam)
             need = (uint32_t)std::min<double>((double)idx->hint_visited * 1.15, 4.0e9);
         if (idx->tune.test_visited_log2) need = (1u << idx->tune.test_visited_log2) / 2;
         const bool skip = idx->v3_overflow_l == l_search && idx->v3_overflow_beam == beam && idx->v3_overflow_frac > 0.25f;
-        if (!skip && v3_prepare(idx, l_search, beam, need, p3, v3) == 0) {
-            p3.vectors = p.vectors;
-            p3.row_stride = p.row_stride;
-            p3.adj = p.adj;
-            p3.adj_stride = p.adj_stride;
-            p3.n_points = p.n_points;
-            p3.n_start = p.n_start;
-            p3.dim = p.dim;
-            p3.max_degree = p.max_degree;
-            p3.queries = p.queries;
-            p3.query_rows = p.query_rows;
-            p3.query_list = nullptr;
-            p3.n_work = nq;
-            p3.k = p.k;
-            p3.cap = p.cap;
-            p3.beam = p.beam;
-            p3.out_ids = p.out_ids;
-            p3.out_dists = p.out_dists;
-            p3.out_counts = p.out_counts;
-            p3.out_cmps = p.out_cmps;
-            p3.out_hops = p.out_hops;
-            p3.rec_ids = p.rec_ids;
-            p3.rec_dists = p.rec_dists;
-            p3.rec_counts = p.rec_counts;
-            p3.rec_cap = p.rec_cap;
-            p3.counters = d_counters;
-            p3.overflow_list = d_overflow;
+        SearchParamsV3 p3;
+        memset(&p3, 0, sizeof(p3));
+        V3Launch v3;
+        int which = 0;
+        if (!skip && v3_prepare(idx, l_search, beam, need, p3, v3) == 0) which = 3;
+        if (which) {
+#define DAB_FILL_FIRST(q)                                                                            \
+    do {                                                                                             \
+        q.vectors = p.vectors, q.row_stride = p.row_stride, q.adj = p.adj, q.adj_stride = p.adj_stride; \
+        q.n_points = p.n_points, q.n_start = p.n_start, q.dim = p.dim, q.max_degree = p.max_degree;  \
+        q.queries = p.queries, q.query_rows = p.query_rows, q.query_list = nullptr, q.n_work = nq;   \
+        q.k = p.k, q.cap = p.cap, q.beam = p.beam;                                                   \
+        q.out_ids = p.out_ids, q.out_dists = p.out_dists, q.out_counts = p.out_counts;               \
+        q.out_cmps = p.out_cmps, q.out_hops = p.out_hops;                                            \
+        q.rec_ids = p.rec_ids, q.rec_dists = p.rec_dists, q.rec_counts = p.rec_counts, q.rec_cap = p.rec_cap; \
+        q.counters = d_counters, q.overflow_list = d_overflow;                                       \
+    } while (0)
             DAB_CUDA(cudaMemsetAsync(d_counters, 0, 16, idx->stream));
-            // persistent warps: size the grid so every resident warp runs the same number of queries
-            const uint64_t max_warps = (uint64_t)v3.grid * kV3Warps;
-            const uint64_t rounds = (nq + max_warps - 1) / max_warps;
-            const uint64_t need_warps = (nq + rounds - 1) / rounds;
-            const int launch_grid = (int)((need_warps + kV3Warps - 1) / kV3Warps);
-            v3.kern<<<launch_grid, kV3Warps * 32, v3.smem_block, idx->stream>>>(p3);
+            // persistent workers: size the grid so every resident worker runs the same number of queries
+            {
+                DAB_FILL_FIRST(p3);
+                const uint64_t max_workers = (uint64_t)v3.grid * kV3Warps;
+                const uint64_t rounds = (nq + max_workers - 1) / max_workers;
+                const uint64_t need_warps = (nq + rounds - 1) / rounds;
+                const int launch_grid = (int)((need_warps + kV3Warps - 1) / kV3Warps);
+                v3.kern<<<launch_grid, kV3Warps * 32, v3.smem_block, idx->stream>>>(p3);
+            }
+#undef DAB_FILL_FIRST
             DAB_LAUNCHED();
             DAB_CUDA(cudaGetLastError());
             uint32_t h_counters[3] = {0, 0, 0};

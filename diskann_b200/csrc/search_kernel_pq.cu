@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchPa
 static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam,
                          uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cmps, uint32_t* d_hops) {
     if (!idx->graph_ready) return fail(DAB_ERR_NOT_READY, "dab_search_batch_pq: graph must be uploaded first");
-    if (!idx->d_pivots || !idx->d_codes) return fail(DAB_ERR_NOT_READY, "dab_search_batch_pq: dab_upload_pq (with codes) has not been called");
+    if (!idx->d_pivots || !idx->d_codes || !idx->pq_codes_ready)
+        return fail(DAB_ERR_NOT_READY, "dab_search_batch_pq: no PQ codes (dab_upload_pq with codes, or dab_pq_encode_all)");
     if (k == 0 || l_search == 0 || beam == 0 || beam > 64) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: bad k / l_search / beam_width");
     if (idx->metric == DAB_COSINE)
         return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: Metric::Cosine traverses with DirectCosine (no table); use dab_pq_distances");

@@ -24,6 +24,7 @@
 #include "dab_common.cuh"
 #include "distance_device.cuh"
 #include "search_common.cuh"
+#include "search_smem.cuh"
 #include "search_v3.cuh"
 
 #include <algorithm>
@@ -33,90 +34,6 @@
 namespace dab {
 
 namespace {
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// ---- shared-memory visited set: 16 tags of 16 bits per 32-byte bucket -----------------------
-// Entries fill a bucket from slot 0 upwards and are never removed, so an id that is absent
-// from its home bucket while that bucket has a free slot is new; an id displaced to the d-th
-// following bucket (d <= 2) carries d in its top two bits.  0xFFFF marks an empty slot.
-__device__ __forceinline__ void load_bucket_smem(const uint32_t* bp, uint32_t (&s)[8]) {
-    const uint4 lo = reinterpret_cast<const uint4*>(bp)[0];
-    const uint4 hi = reinterpret_cast<const uint4*>(bp)[1];
-    s[0] = lo.x, s[1] = lo.y, s[2] = lo.z, s[3] = lo.w, s[4] = hi.x, s[5] = hi.y, s[6] = hi.z, s[7] = hi.w;
-}
-
-// true when the id was newly inserted (HashSet::insert); `ovf` is raised when the home bucket
-// and the two after it are full
-__device__ __forceinline__ bool smem16_insert(uint32_t* table, uint32_t n_buckets, uint32_t b, uint32_t tag, bool& ovf) {
-    uint32_t d = 0;
-    for (;;) {
-        uint32_t* bp = table + (size_t)b * 8;
-        uint32_t s[8];
-        load_bucket_smem(bp, s);
-        const uint32_t want = (d << 14) | tag, want2 = want * 0x10001u;
-        // "some 16-bit half of x is zero" <=> ((x - 0x00010001) & ~x & 0x80008000) != 0
-        uint32_t hit = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t x = s[k] ^ want2;
-            hit |= (x - 0x00010001u) & ~x & 0x80008000u;
-        }
-        if (hit) return false;
-        // first free slot: slots fill in order, so it is the number of occupied halves
-        int ew = -1;
-        uint32_t old = 0;
-#pragma unroll
-        for (int k = 7; k >= 0; --k) {
-            if ((s[k] >> 16) == 0xFFFFu) {
-                ew = k;
-                old = s[k];
-            }
-        }
-        if (ew >= 0) {
-            const uint32_t neu = (old & 0xFFFFu) == 0xFFFFu ? (0xFFFF0000u | want) : ((old & 0xFFFFu) | (want << 16));
-            if (atomicCAS(bp + ew, old, neu) == old) return true;
-            continue;  // another lane of this warp changed the word: look at the bucket again
-        }
-        if (++d > 2) {
-            ovf = true;
-            return false;
-        }
-        b = b + 1 == n_buckets ? 0 : b + 1;
-    }
-}
-
-// Packed f32x2 arithmetic (FADD2 / FFMA2): each half is an IEEE round-to-nearest operation.
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-template <int KIND>
-__device__ __forceinline__ uint64_t step2(uint64_t acc, uint64_t x2, uint64_t y2) {
-    if (KIND == KIND_L2) {
-        uint64_t c2;
-        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c2) : "l"(x2), "l"(y2));
-        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(acc) : "l"(c2), "l"(acc));
-    } else {
-        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(acc) : "l"(x2), "l"(y2), "l"(acc));
-    }
-    return acc;
-}
-
-__device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-
-// All candidate rows of a hop are requested from HBM at once with one bulk L2 prefetch per row
-// (no registers, no shared memory); the register passes below then overlap with the fills and
-// find all but the first rows in L2.
-__device__ __forceinline__ void prefetch_rows(const uint8_t* __restrict__ vectors, size_t row_stride, const uint32_t* __restrict__ cid,
-                                              uint32_t n, uint32_t row_bytes16, int lane) {
-    for (uint32_t j = lane; j < n; j += 32) {
-        const uint8_t* src = vectors + (size_t)cid[j] * row_stride;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(row_bytes16) : "memory");
-    }
-}
 
 // ---- float rows: distances of candidates cid[0..n) into cd[0..n) ----------------------------
 // Lane mapping of frontier_wide_kernel (distance_kernels.cu): a 16-byte load carries EPL
@@ -231,6 +148,63 @@ __device__ __forceinline__ void wide_distances(const float* __restrict__ q, cons
     }
 }
 
+// ---- f32 rows of 32 * nm <= 128 elements (the headline shapes: 128-d, 96-d) ------------------
+// Same lane mapping and association as wide_distances, with the per-hop overheads removed: the
+// 16 query elements a lane ever multiplies live in registers (packed pairs), a step covers 8
+// rows (two passes) whose 8 x nm 16-byte loads are issued back to back, and the two passes are
+// reduced together with a transpose-butterfly — 9 shuffles + 9 adds for 8 rows instead of 24 +
+// 30: stage A (xor 2) adds accumulator pairs while splitting the passes between the lanes,
+// stage B (xor 4) finishes (s0+s1)+(s2+s3) while splitting the slots, stage C (xor 1) is
+// x_i + x_{i+4}, then (t0+t2) and (t1+t3) (xor 4) and their sum (xor 1).
+template <int KIND, int POST>
+__device__ __forceinline__ void wide_distances_f32_fast(const uint64_t (&q2)[8], int nm, const uint8_t* __restrict__ vectors,
+                                                        size_t row_stride, const uint32_t* __restrict__ cid, uint32_t n,
+                                                        float* __restrict__ cd, int lane) {
+    const int team = lane >> 3, tl = lane & 7;
+    const bool pA = (tl & 2) != 0, pB = (tl & 4) != 0, hh = (tl & 1) != 0;
+    if (n > 8) prefetch_rows(vectors, row_stride, cid, n, (uint32_t)nm * 128u, lane);
+    for (uint32_t j0 = 0; j0 < n; j0 += 8) {
+        const bool two = j0 + 4 < n;  // warp-uniform: the second pass has rows
+        const uint8_t* row0 = vectors + (size_t)cid[min(j0 + team, n - 1)] * row_stride + 16 * tl;
+        const uint8_t* row1 = vectors + (size_t)cid[min(j0 + 4 + team, n - 1)] * row_stride + 16 * tl;
+        uint4 v0[4], v1[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            if (m < nm) {
+                v0[m] = ldg16(row0 + m * 128);
+                if (two) v1[m] = ldg16(row1 + m * 128);
+            }
+        }
+        uint64_t a0[2] = {0ull, 0ull}, a1[2] = {0ull, 0ull};
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            if (m < nm) {
+                a0[0] = step2<KIND>(a0[0], q2[2 * m], pack2(__uint_as_float(v0[m].x), __uint_as_float(v0[m].y)));
+                a0[1] = step2<KIND>(a0[1], q2[2 * m + 1], pack2(__uint_as_float(v0[m].z), __uint_as_float(v0[m].w)));
+                if (two) {
+                    a1[0] = step2<KIND>(a1[0], q2[2 * m], pack2(__uint_as_float(v1[m].x), __uint_as_float(v1[m].y)));
+                    a1[1] = step2<KIND>(a1[1], q2[2 * m + 1], pack2(__uint_as_float(v1[m].z), __uint_as_float(v1[m].w)));
+                }
+            }
+        }
+        float x0[4], x1[4];
+        unpack2(a0[0], x0[0], x0[1]);
+        unpack2(a0[1], x0[2], x0[3]);
+        unpack2(a1[0], x1[0], x1[1]);
+        unpack2(a1[1], x1[2], x1[3]);
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __fadd_rn(pA ? x1[i] : x0[i], __shfl_xor_sync(kFull, pA ? x0[i] : x1[i], 2));
+        const float w0 = __fadd_rn(pB ? v[2] : v[0], __shfl_xor_sync(kFull, pB ? v[0] : v[2], 4));
+        const float w1 = __fadd_rn(pB ? v[3] : v[1], __shfl_xor_sync(kFull, pB ? v[1] : v[3], 4));
+        const float u = __fadd_rn(hh ? w1 : w0, __shfl_xor_sync(kFull, hh ? w0 : w1, 1));  // x_i + x_{i+4}, i = 2 pB + h
+        const float z = __fadd_rn(u, __shfl_xor_sync(kFull, u, 4));                        // t0 + t2 | t1 + t3
+        const float r = __fadd_rn(z, __shfl_xor_sync(kFull, z, 1));
+        const uint32_t jj = j0 + (pA ? 4 : 0) + team;  // lanes with pA hold the second pass
+        if ((tl == 0 || tl == 2) && jj < n) cd[jj] = post_op<POST>(r);
+    }
+}
+
 // ---- i8 / u8 rows: exact i32 arithmetic, so any summation order gives the reference's value --
 // 8 lanes per row, 16 bytes per lane per load, 4 rows per pass, P passes in flight.
 // q: query bytes in shared memory, zero-padded to a multiple of 16; qq = sum q*q.
@@ -323,6 +297,9 @@ struct IsInt {
 #ifndef DAB_V3_MIN_CTAS
 #define DAB_V3_MIN_CTAS 4
 #endif
+#ifndef DAB_V3_LP16
+#define DAB_V3_LP16 1  // visited set: linear-probing 16-bit slots (0: buckets of 16 tags)
+#endif
 #ifndef DAB_V3_P_F32
 #define DAB_V3_P_F32 2  // f32 rows: passes (of 4 rows, 4 x 16-byte loads per lane each) in flight
 #endif
@@ -338,7 +315,7 @@ struct IsInt {
 
 }  // namespace
 
-template <typename TD, int KIND, int POST, int QT>
+template <typename TD, int KIND, int POST, int QT, bool FAST>
 __global__ void __launch_bounds__(kV3Warps * 32, DAB_V3_MIN_CTAS) search_kernel_v3(const SearchParamsV3 p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr bool kInt = IsInt<TD>::value;
@@ -354,7 +331,20 @@ __global__ void __launch_bounds__(kV3Warps * 32, DAB_V3_MIN_CTAS) search_kernel_
     const uint32_t adjbuf_a = smem_addr(adjbuf);
     uint32_t* table = reinterpret_cast<uint32_t*>(base + p.off_table);
     const uint32_t nbk = p.n_buckets;
+#if DAB_V3_LP16
+    const Lp16Map tmap{p.tag_kmask, nbk * 16, p.tag_magic, p.tag_shift, p.tag_bits, p.tag_dmax};
+#else
     const Tag16Map tmap{p.tag_kmask, nbk, p.tag_magic, p.tag_shift};
+#endif
+    auto visit = [&](uint32_t id, bool& ovf) -> bool {
+#if DAB_V3_LP16
+        return lp16_insert(table, tmap, id, ovf);
+#else
+        uint32_t bk, tg;
+        tag16_of(id, tmap, bk, tg);
+        return smem16_insert(table, nbk, bk, tg, ovf);
+#endif
+    };
     const uint64_t n_total = p.n_points + p.n_start;
     const int dim = (int)p.dim;
 
@@ -385,6 +375,20 @@ __global__ void __launch_bounds__(kV3Warps * 32, DAB_V3_MIN_CTAS) search_kernel_
             if (KIND != KIND_IP) qq = warp_int_self<std::is_same<TD, int8_t>::value>(reinterpret_cast<const uint8_t*>(qf), dim, lane);
         }
         (void)qq;
+        // fast f32 path: the 16 query elements this lane multiplies, as packed pairs
+        uint64_t q2[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+        if constexpr (FAST) {
+            {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    if (m < (int)p.fast_nm) {
+                        const float4 x = *reinterpret_cast<const float4*>(qf + 32 * m + 4 * (lane & 7));
+                        q2[2 * m] = pack2(x.x, x.y);
+                        q2[2 * m + 1] = pack2(x.z, x.w);
+                    }
+                }
+            }
+        }
 
         uint32_t size = 0, cursor_lo = 0, cmps = 0, hops = 0, nvisited = 0, nrec = 0;
         uint32_t pred = kEmptyV2;  // node whose adjacency row sits in adjbuf
@@ -396,6 +400,8 @@ __global__ void __launch_bounds__(kV3Warps * 32, DAB_V3_MIN_CTAS) search_kernel_
                                                                                  p.row_stride, cid + c0, n, cd + c0, dim, lane);
             } else if constexpr (sizeof(TD) == 2) {
                 wide_distances<TD, KIND, POST, DAB_V3_P_F16, DAB_V3_U_F16>(qf, p.vectors, p.row_stride, cid + c0, n, cd + c0, dim, lane);
+            } else if constexpr (FAST) {
+                wide_distances_f32_fast<KIND, POST>(q2, (int)p.fast_nm, p.vectors, p.row_stride, cid + c0, n, cd + c0, lane);
             } else {
                 wide_distances<TD, KIND, POST, DAB_V3_P_F32, 4>(qf, p.vectors, p.row_stride, cid + c0, n, cd + c0, dim, lane);
             }
@@ -409,9 +415,7 @@ __global__ void __launch_bounds__(kV3Warps * 32, DAB_V3_MIN_CTAS) search_kernel_
             if ((uint32_t)lane < n) {
                 const uint32_t id = (uint32_t)p.n_points + s0 + lane;
                 cid[lane] = id;
-                uint32_t b, tg;
-                tag16_of(id, tmap, b, tg);
-                smem16_insert(table, nbk, b, tg, ovf);
+                visit(id, ovf);
             }
             if (__any_sync(kFull, ovf)) overflow = true;
             __syncwarp();
@@ -489,11 +493,7 @@ __global__ void __launch_bounds__(kV3Warps * 32, DAB_V3_MIN_CTAS) search_kernel_
                 auto filter = [&](uint32_t word, uint32_t j) {
                     bool inserted = false;
                     // ids beyond 2^K cannot be in bounds and never reach the outputs: not tracked
-                    if (j >= 1 && j <= deg && word <= tmap.kmask) {
-                        uint32_t bk, tg;
-                        tag16_of(word, tmap, bk, tg);
-                        inserted = smem16_insert(table, nbk, bk, tg, ovf);
-                    }
+                    if (j >= 1 && j <= deg && word <= tmap.kmask) inserted = visit(word, ovf);
                     const bool isnew = inserted && word < n_total;  // is_in_bounds
                     const unsigned mi = __ballot_sync(kFull, inserted);
                     const unsigned mn = __ballot_sync(kFull, isnew);
@@ -604,24 +604,38 @@ int v3_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, uint32_t 
     p.off_table = (uint32_t)off;
     const size_t fixed = off;
 
-    // table size: what the visited sets seen so far need at 87.5 % load (+ one adjacency row of
-    // slack), bounded so that at least kMinWarps warps stay resident per SM; without a hint, the
-    // size that keeps kTargetWarps resident.  Queries that outgrow it re-run on the global tables.
     const size_t smem_sm = 227 * 1024;  // per SM, 1 KB per CTA is reserved by the system
     auto table_bytes_at = [&](int ctas) -> long long {
         const long long per_cta = (long long)(smem_sm / ctas) - 1024;
         return (per_cta / kV3Warps - (long long)fixed) / 32 * 32;
     };
-    const int ctas_min = 2, ctas_target = 4;
-    long long tbytes;
-    if (visited_need) {
-        const uint64_t slots = (uint64_t)((visited_need + idx->max_degree) / 0.875) + 16;
-        tbytes = (long long)round_up(slots * 2, 32);
-        if (tbytes > table_bytes_at(ctas_min)) tbytes = table_bytes_at(ctas_min);
-    } else {
-        tbytes = table_bytes_at(ctas_target);
-    }
+    // registers bound the residency (DAB_V3_MIN_CTAS CTAs per SM), so the table takes all the shared
+    // memory that residency leaves: a smaller table would only overflow more often
+    long long tbytes = table_bytes_at(DAB_V3_MIN_CTAS);
+    if (idx->tune.test_visited_log2 && visited_need)  // tests: a table small enough to overflow
+        tbytes = (long long)round_up((size_t)((visited_need + idx->max_degree) / 0.875) * 2 + 32, 32);
     if (idx->tune.v3_table_bytes > 0) tbytes = (long long)round_up((size_t)idx->tune.v3_table_bytes, 32);
+#if DAB_V3_LP16
+    if (tbytes < 1024) tbytes = 1024;
+    if (tbytes > table_bytes_at(1)) return 1;
+    const uint64_t nbk = (uint64_t)tbytes / 32;
+    const uint64_t n_slots = nbk * 16;
+    uint32_t sbits = 0;
+    while (((uint64_t)1 << sbits) < n_slots) ++sbits;
+    if (K + sbits > 32) return 1;
+    const uint64_t tag_max = ((((uint64_t)1 << K) - 1)) / n_slots;
+    uint32_t tag_bits = 0;
+    while (((uint64_t)1 << tag_bits) <= tag_max) ++tag_bits;
+    if (tag_bits > 10) return 1;  // fewer than 6 displacement bits: index too large for this table size
+    p.n_buckets = (uint32_t)nbk;
+    p.tag_kmask = (uint32_t)(((uint64_t)1 << K) - 1);
+    p.tag_shift = K + sbits;
+    p.tag_magic = (uint32_t)((((uint64_t)1 << (K + sbits)) + n_slots - 1) / n_slots);
+    p.tag_bits = tag_bits;
+    p.tag_dmax = (1u << (16 - tag_bits)) - 2;
+    p.visited_limit = (uint32_t)(n_slots * 7 / 8);
+    (void)min_buckets;
+#else
     if (tbytes < (long long)min_buckets * 32) tbytes = (long long)min_buckets * 32;
     if (tbytes > table_bytes_at(1)) return 1;
     uint64_t nbk = (uint64_t)tbytes / 32;
@@ -633,12 +647,18 @@ int v3_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, uint32_t 
     p.tag_shift = K + sbits;
     p.tag_magic = (uint32_t)((((uint64_t)1 << (K + sbits)) + nbk - 1) / nbk);
     p.visited_limit = (uint32_t)(nbk * 14);  // 87.5 % of 16 tags per bucket
+#endif
+    p.fast_nm = (idx->dtype == DAB_F32 && idx->dim % 32 == 0 && idx->dim <= 128 && !idx->tune.v3_generic) ? idx->dim / 32 : 0;
     out.capacity = p.visited_limit > idx->max_degree ? p.visited_limit - idx->max_degree : 0;
     if (out.capacity < 4 * idx->max_degree) return 1;
     p.warp_smem = (uint32_t)round_up(fixed + (size_t)tbytes, 128);
     out.smem_block = (size_t)p.warp_smem * kV3Warps;
 
-#define PICK2(TD, K_, P_, Q_) out.kern = search_kernel_v3<TD, K_, P_, Q_>
+#define PICK2(TD, K_, P_, Q_)                                                              \
+    do {                                                                                   \
+        if (std::is_same<TD, float>::value && p.fast_nm) out.kern = search_kernel_v3<float, K_, P_, Q_, true>; \
+        else out.kern = search_kernel_v3<TD, K_, P_, Q_, false>;                            \
+    } while (0)
 #define PICK_Q(TD, K_, P_)                 \
     do {                                   \
         if (cap <= 128) PICK2(TD, K_, P_, 4); \

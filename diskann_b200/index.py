@@ -154,6 +154,25 @@ class GpuIndex:
         self.pq_chunks, self.pq_centers = len(offsets) - 1, pivots.shape[0]
         check(_lib.lib().dab_upload_pq(self._h, _ptr(pivots), pivots.shape[0], _ptr(offsets), len(offsets) - 1, _ptr(codes)))
 
+    def pq_train(self, train, n_chunks, n_centers=256, lloyds_reps=5, seed=0):
+        """train_pq on the device: k-means++ + Lloyd per chunk over host training rows [n, dim] f32."""
+        train = np.ascontiguousarray(train, np.float32)
+        if train.ndim != 2 or train.shape[1] != self.dim:
+            raise DabError(1, f"training rows must be [n, {self.dim}] f32")
+        check(_lib.lib().dab_pq_train(self._h, _ptr(train), train.shape[0], n_chunks, n_centers, lloyds_reps, seed))
+        self.pq_chunks, self.pq_centers = n_chunks, n_centers
+
+    def pq_encode_all(self):
+        check(_lib.lib().dab_pq_encode_all(self._h))
+
+    def download_pq(self, codes=True):
+        """(pivots [n_centers, dim] f32, offsets u64 [n_chunks + 1], codes u8 [n_total, n_chunks] or None)."""
+        pivots = np.empty((self.pq_centers, self.dim), np.float32)
+        offsets = np.empty(self.pq_chunks + 1, np.uint64)
+        c = np.empty((self.n_total, self.pq_chunks), np.uint8) if codes else None
+        check(_lib.lib().dab_pq_download(self._h, _ptr(pivots), _ptr(offsets), _ptr(c)))
+        return pivots, offsets, c
+
     # -- distances
     def _queries(self, queries):
         queries = np.ascontiguousarray(queries)

@@ -87,9 +87,26 @@ int dab_download_graph(dab_index* idx, uint32_t* adj, uint32_t dst_stride, uint6
 /* FixedChunkPQTable::new(dim, pq_table, chunk_offsets)
  * (diskann-providers/src/model/pq/fixed_chunk_pq_table.rs:104-135) + the compressed
  * vectors of the quant store: pivots [n_centers][dim] f32, offsets [n_chunks + 1],
- * codes [(n_points + n_start)][n_chunks] (may be NULL, then call dab_pq_encode_all). */
+ * codes [(n_points + n_start)][n_chunks] (may be NULL, then call dab_pq_encode_all; a PQ
+ * traversal before that returns DAB_ERR_NOT_READY). */
 int dab_upload_pq(dab_index* idx, const float* pivots, uint32_t n_centers,
                   const uint64_t* offsets, uint32_t n_chunks, const uint8_t* codes);
+
+/* train_pq (diskann-providers/src/index/diskann_async.rs:61-89 -> model/pq/pq_construction.rs:163-243
+ * -> diskann-quantization/src/product/train.rs): per chunk k-means++ seeding
+ * (algorithms/kmeans/plusplus.rs:381-498) and `lloyds_reps` Lloyd iterations (lloyds.rs:372-426; the
+ * benchmark uses 5) over n host training rows [n][dim] f32, entirely on the device, arithmetic in the
+ * reference's order.  Chunk offsets are ChunkOffsets::partition (quantization/src/views.rs:226-243).
+ * The random draws come from SplitMix64(seed + chunk) (the reference's StdRng is not reproduced).
+ * Replaces the resident table; codes are cleared until dab_pq_encode_all. */
+int dab_pq_train(dab_index* idx, const float* train, uint64_t n, uint32_t n_chunks, uint32_t n_centers,
+                 uint32_t lloyds_reps, uint64_t seed);
+/* BasicTable::compress_into (product/tables/basic.rs:161-194) for every uploaded row (converted to
+ * f32, T: Into<f32>) into the resident codes — the quant store of a quantized build. */
+int dab_pq_encode_all(dab_index* idx);
+/* copies the resident table back: pivots [n_centers][dim], offsets [n_chunks + 1], codes
+ * [(n_points + n_start)][n_chunks]; any pointer may be NULL. */
+int dab_pq_download(dab_index* idx, float* pivots, uint64_t* offsets, uint8_t* codes);
 
 /* ------------------------------------------------------------------ (1) per-pair / per-query distances */
 

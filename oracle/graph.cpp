@@ -285,12 +285,39 @@ void search_internal(const orc_index* idx, const QueryDist& qd, uint32_t l_searc
 
 uint32_t search_one(const orc_index* idx, const void* query, uint32_t k, uint32_t l_search,
                     uint32_t beam_width, int flavour, uint32_t* out_ids, float* out_dists,
-                    uint32_t* out_cmps, uint32_t* out_hops) {
+                    uint32_t* out_cmps, uint32_t* out_hops, bool rerank = false) {
     QueryDist qd(idx, query, flavour);
     // scratch.rs:195-208: queue capacity = L + number of start points
     Queue best((size_t)l_search + idx->n_start);
     uint32_t cmps = 0, hops = 0;
     search_internal(idx, qd, l_search, beam_width, best, &cmps, &hops, nullptr);
+    if (rerank) {
+        // Pipeline<FilterStartPoints, Rerank> (providers .../inmem/product.rs:391-400,
+        // full_precision.rs:356-399): every entry of best.iter() that is not a start point gets its
+        // full-precision Distance<T, T> to the query, the list is sorted by that distance
+        // (`sort_unstable_by`: the order of exactly tied entries is unspecified in the reference;
+        // here ties keep their traversal order) and the output buffer takes the first k.
+        std::vector<Visit> cand;
+        size_t n = std::min(best.capacity, best.size);
+        for (size_t i = 0; i < n; ++i) {
+            if (best.ids[i] >= idx->n_points) continue;
+            const char* row = (const char*)idx->vectors + (size_t)best.ids[i] * idx->row_stride;
+            cand.push_back(Visit{best.ids[i], orc_distance(flavour, idx->dtype, idx->dtype, idx->metric, query, row, idx->dim, nullptr)});
+        }
+        std::stable_sort(cand.begin(), cand.end(), [](const Visit& a, const Visit& b) { return a.dist < b.dist; });
+        uint32_t count = (uint32_t)std::min<size_t>(k, cand.size());
+        for (uint32_t i = 0; i < count; ++i) {
+            out_ids[i] = cand[i].id;
+            out_dists[i] = cand[i].dist;
+        }
+        for (uint32_t i = count; i < k; ++i) {
+            out_ids[i] = 0xFFFFFFFFu;
+            out_dists[i] = std::numeric_limits<float>::infinity();
+        }
+        if (out_cmps) *out_cmps = cmps;
+        if (out_hops) *out_hops = hops;
+        return count;
+    }
     // post-process (diskann-inmem/src/provider.rs:907-950): skip ids with no external
     // mapping (start points), stop when the output buffer is full.
     uint32_t count = 0;
@@ -485,10 +512,31 @@ uint32_t orc_search(const orc_index* idx, const void* query, uint32_t k, uint32_
 
 // benchmark-core/src/search/api.rs:400-434 (PartitionIter: contiguous ranges, the first
 // nq % T ranges one longer).
+static void search_batch_impl(const orc_index* idx, const void* queries, uint64_t query_stride,
+                              uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam_width,
+                              int flavour, int n_threads, uint32_t* out_ids, float* out_dists,
+                              uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops, bool rerank);
+
 void orc_search_batch(const orc_index* idx, const void* queries, uint64_t query_stride,
                       uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam_width,
                       int flavour, int n_threads, uint32_t* out_ids, float* out_dists,
                       uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops) {
+    search_batch_impl(idx, queries, query_stride, nq, k, l_search, beam_width, flavour, n_threads, out_ids, out_dists,
+                      out_counts, out_cmps, out_hops, false);
+}
+
+void orc_search_batch_rerank(const orc_index* idx, const void* queries, uint64_t query_stride,
+                             uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam_width,
+                             int flavour, int n_threads, uint32_t* out_ids, float* out_dists,
+                             uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops) {
+    search_batch_impl(idx, queries, query_stride, nq, k, l_search, beam_width, flavour, n_threads, out_ids, out_dists,
+                      out_counts, out_cmps, out_hops, true);
+}
+
+static void search_batch_impl(const orc_index* idx, const void* queries, uint64_t query_stride,
+                              uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam_width,
+                              int flavour, int n_threads, uint32_t* out_ids, float* out_dists,
+                              uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops, bool rerank) {
     if (n_threads < 1) n_threads = 1;
     if ((uint32_t)n_threads > nq) n_threads = nq ? (int)nq : 1;
     auto work = [&](uint32_t lo, uint32_t hi) {
@@ -496,7 +544,7 @@ void orc_search_batch(const orc_index* idx, const void* queries, uint64_t query_
             uint32_t c = 0, h = 0;
             uint32_t cnt = search_one(idx, (const char*)queries + (size_t)i * query_stride, k,
                                       l_search, beam_width, flavour, out_ids + (size_t)i * k,
-                                      out_dists + (size_t)i * k, &c, &h);
+                                      out_dists + (size_t)i * k, &c, &h, rerank);
             if (out_counts) out_counts[i] = cnt;
             if (out_cmps) out_cmps[i] = c;
             if (out_hops) out_hops[i] = h;

@@ -102,6 +102,13 @@ float orc_sq_compress(const float* shift, float scale, size_t dim, int nbits, co
 float orc_sq_distance(int metric, int nbits, float scale_squared, float shift_square_norm,
                       const uint8_t* x, float comp_x, const uint8_t* y, float comp_y, size_t dim);
 
+/* PQ codebook training (diskann-providers/src/index/diskann_async.rs:61-89 -> pq_construction.rs:163-243
+ * -> diskann-quantization/src/product/train.rs): per chunk k-means++ (algorithms/kmeans/plusplus.rs)
+ * and `lloyds_reps` Lloyd iterations (lloyds.rs), arithmetic in the reference's order; the random draws
+ * come from SplitMix64(seed + chunk) instead of Rust's StdRng.  pivots: [n_centers][dim], offsets: [n_chunks+1]. */
+int orc_pq_train(const float* data, uint64_t n, uint32_t dim, uint32_t n_chunks, uint32_t n_centers,
+                 uint32_t lloyds_reps, uint64_t seed, float* pivots, uint64_t* offsets);
+
 /* ---------------------------------------------------------------- graph search / prune */
 
 typedef struct orc_index {
@@ -135,6 +142,14 @@ void orc_search_batch(const orc_index* idx, const void* queries, uint64_t query_
                       uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam_width,
                       int flavour, int n_threads, uint32_t* out_ids, float* out_dists,
                       uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops);
+
+/* The same followed by the quantized providers' post-processing Pipeline<FilterStartPoints, Rerank>
+ * (diskann-providers/.../inmem/product.rs:391-400, full_precision.rs:356-399): the whole candidate
+ * list is re-scored with the full-precision Distance<T, T> and sorted before the first k are taken. */
+void orc_search_batch_rerank(const orc_index* idx, const void* queries, uint64_t query_stride,
+                             uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam_width,
+                             int flavour, int n_threads, uint32_t* out_ids, float* out_dists,
+                             uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops);
 
 /* graph/config/mod.rs:80-103.  kind: 0 TriangleInequality, 1 Occluding */
 float orc_update_occlude_factor(int kind, float d_ik, float d_jk, float cur, float alpha);

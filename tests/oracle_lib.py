@@ -74,6 +74,8 @@ def lib():
     L.orc_pq_self_distance.argtypes = [vp, sz, vp, sz, i, vp, vp]
     L.orc_pq_encode.restype = i
     L.orc_pq_encode.argtypes = [vp, sz, sz, vp, sz, vp, vp]
+    L.orc_pq_train.restype = i
+    L.orc_pq_train.argtypes = [vp, u64, u32, u32, u32, u32, u64, vp, vp]
     L.orc_sq_compress.restype = f
     L.orc_sq_compress.argtypes = [vp, f, sz, i, vp, vp, C.POINTER(C.c_int)]
     L.orc_sq_distance.restype = f
@@ -82,6 +84,8 @@ def lib():
     L.orc_search.argtypes = [C.POINTER(OrcIndex), vp, u32, u32, u32, i, vp, vp, vp, vp]
     L.orc_search_batch.restype = None
     L.orc_search_batch.argtypes = [C.POINTER(OrcIndex), vp, u64, u32, u32, u32, u32, i, i, vp, vp, vp, vp, vp]
+    L.orc_search_batch_rerank.restype = None
+    L.orc_search_batch_rerank.argtypes = [C.POINTER(OrcIndex), vp, u64, u32, u32, u32, u32, i, i, vp, vp, vp, vp, vp]
     L.orc_update_occlude_factor.restype = f
     L.orc_update_occlude_factor.argtypes = [i, f, f, f, f]
     L.orc_robust_prune.restype = u32
@@ -145,6 +149,15 @@ def pq_offsets(dim, n_chunks):
     return out
 
 
+def pq_train(data, n_chunks, n_centers=256, lloyds_reps=5, seed=0):
+    """(pivots [n_centers, dim] f32, offsets u64, status) — train_pq's per-chunk k-means++ + Lloyd."""
+    data = np.ascontiguousarray(data, np.float32)
+    pivots = np.zeros((n_centers, data.shape[1]), np.float32)
+    offsets = np.zeros(n_chunks + 1, np.uint64)
+    st = lib().orc_pq_train(ptr(data), data.shape[0], data.shape[1], n_chunks, n_centers, lloyds_reps, seed, ptr(pivots), ptr(offsets))
+    return pivots, offsets, st
+
+
 class Index:
     """Host-side view of an index for the oracle (keeps the numpy arrays alive)."""
 
@@ -186,6 +199,20 @@ class Index:
         hops = np.empty(nq, np.uint32)
         lib().orc_search_batch(C.byref(self.c), ptr(queries), queries.strides[0], nq, k, l_search, beam,
                                flavour, threads, ptr(ids), ptr(dists), ptr(counts), ptr(cmps), ptr(hops))
+        return ids, dists, counts, cmps, hops
+
+
+    def search_batch_rerank(self, queries, k, l_search, beam=1, flavour=AVX2, threads=1):
+        """PQ (or full-precision) traversal followed by the providers' full-precision Rerank."""
+        queries = np.ascontiguousarray(queries)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), np.uint32)
+        dists = np.empty((nq, k), np.float32)
+        counts = np.empty(nq, np.uint32)
+        cmps = np.empty(nq, np.uint32)
+        hops = np.empty(nq, np.uint32)
+        lib().orc_search_batch_rerank(C.byref(self.c), ptr(queries), queries.strides[0], nq, k, l_search, beam,
+                                      flavour, threads, ptr(ids), ptr(dists), ptr(counts), ptr(cmps), ptr(hops))
         return ids, dists, counts, cmps, hops
 
 

@@ -13,11 +13,30 @@ import bench  # noqa: E402
 
 def test_algorithmic_bytes_follows_the_survey_formula():
     # cmps*(d*sizeof(T)+8) + hops*(max_degree+1)*4 + d*sizeof(T) + k*8 per query
-    cmps = np.array([1000, 2000], np.uint32)
-    hops = np.array([100, 110], np.uint32)
-    got = bench.algorithmic_bytes(cmps, hops, 128, 4, 10, 83)
-    want = 3000 * 520 + 210 * 336 + 2 * (512 + 80)
-    assert got == want
+    c2 = bench.WORKLOADS["c2_1Mx128_f32_l2"]
+    assert bench.unit_bytes(c2) == 520
+    assert bench.algorithmic_bytes(c2, 3000, 210, 2, 83) == 3000 * 520 + 210 * 336 + 2 * (512 + 80)
+    assert bench.unit_bytes(bench.WORKLOADS["c3_1Mx768_f16_ip"]) == 1544
+    c4 = bench.WORKLOADS["c4_10Mx128_i8_pq32"]
+    assert bench.unit_bytes(c4) == 40  # 32 code bytes + id + output
+    # PQ traversal + rerank: L full-precision rows (136 B each) per query on top
+    assert bench.algorithmic_bytes(c4, 1000, 100, 1, 83, rerank_rows=100) == 1000 * 40 + 100 * 336 + (128 + 80) + 100 * 136
+    assert bench.unit_bytes(bench.WORKLOADS["c5_100Mx96_f32_l2"]) == 392
+
+
+def test_host_cores_respects_affinity():
+    hc = bench.host_cores()
+    assert 1 <= hc["threads"] <= hc["cores_affinity"] <= hc["cores_hw"]
+
+
+def test_data_generators():
+    cfg = dict(bench.WORKLOADS["c3_1Mx768_f16_ip"], centers=8)
+    x = bench.make_data(cfg, 1, 100, bench.make_centers(cfg))
+    assert x.dtype == np.float16 and abs(float((x.astype(np.float32) ** 2).sum(1).mean()) - 1.0) < 1e-2
+    cfg = dict(bench.WORKLOADS["c4_10Mx128_i8_pq32"], centers=8)
+    y = bench.make_data(cfg, 1, 100, bench.make_centers(cfg))
+    assert y.dtype == np.int8 and y.min() >= -127 and np.abs(y).max() > 40
+    assert np.array_equal(bench.find_medoid(y), y[np.argmin(((y.astype(np.float32) - y.astype(np.float32).mean(0)) ** 2).sum(1))])
 
 
 def test_max_degree_is_the_reference_slack():

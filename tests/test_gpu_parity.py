@@ -510,6 +510,31 @@ def test_pq_traversal_search_identical_to_oracle(dab, dt, metric, d, chunks):
             g.search_batch_pq(f32[:2], 5, 10)  # DirectCosine has no table: rejected loudly
 
 
+@pytest.mark.parametrize("dim,chunks,centers,n", [(24, 5, 32, 3000), (128, 32, 256, 6000), (40, 1, 16, 1500)])
+def test_pq_training_on_the_device_is_bit_identical_to_the_cpu_restatement(dab, dim, chunks, centers, n):
+    """train_pq (k-means++ + 5 Lloyd iterations per chunk) and the encoding of every stored row:
+    same pivots (bits), offsets and codes as oracle/kmeans.cpp + BasicTable::compress_into."""
+    rng = np.random.default_rng(dim * 1000 + chunks)
+    base = clustered(rng, n + 1, dim, n_centers=64)
+    train = base[rng.choice(n, n // 2, replace=False)]
+    want_piv, want_off, st = O.pq_train(train, chunks, centers, 5, 12345)
+    assert st == 0
+    with dab.GpuIndex(dab.DType.f32, dab.Metric.L2, dim, n, 1, 8) as g:
+        g.upload_vectors(base)
+        g.pq_train(train, chunks, centers, 5, 12345)
+        with pytest.raises(dab.DabError):
+            g.search_batch_pq(base[:2], 5, 10)  # no codes yet: NOT_READY, never distances to centre 0
+        g.pq_encode_all()
+        piv, off, codes = g.download_pq()
+    assert np.array_equal(off, want_off)
+    assert np.array_equal(bits(piv), bits(want_piv))
+    want_codes = np.zeros_like(codes)
+    L = O.lib()
+    for i in range(n + 1):
+        assert L.orc_pq_encode(O.ptr(want_piv), centers, dim, O.ptr(want_off), chunks, O.ptr(base[i]), O.ptr(want_codes[i])) == 0
+    assert np.array_equal(codes, want_codes)
+
+
 def test_search_c3_shape_f16_768_inner_product(dab):
     """BASELINE config C3 shape (768-d f16, inner product) at test size through the v2 kernel."""
     rng = np.random.default_rng(768)

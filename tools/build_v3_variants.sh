@@ -1,6 +1,6 @@
 #!/bin/bash
 # Builds build/lib_v3_<name>.so: search_kernel_v3 (and its dispatcher) recompiled with tuning macros,
-# linked with the default objects.  usage: tools/build_v3_variants.sh   (needs nvcc, no GPU)
+# linked with the default objects.  usage: tools/build_v3_variants.sh name:-DMACRO=1,-DOTHER=2 ...
 set -e
 cd "$(dirname "$0")/.."
 make -C diskann_b200/csrc -j8 > /dev/null
