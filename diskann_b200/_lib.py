@@ -27,6 +27,11 @@ SYMBOLS = {
     "dab_pq_train": (_i, [_vp, _vp, _u64, _u32, _u32, _u32, _u64]),
     "dab_pq_encode_all": (_i, [_vp]),
     "dab_pq_download": (_i, [_vp, _vp, _vp, _vp]),
+    "dab_comm_unique_id": (_i, [_vp]),
+    "dab_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "dab_broadcast_index": (_i, [_vp, _i]),
+    "dab_comm_destroy": (_i, [_vp]),
+    "dab_broadcast": (_i, [_vp, _i]),
     "dab_pair_distances": (_i, [_i, _i, _i, _u32, _vp, _vp, _u64, _vp, _i]),
     "dab_distances": (_i, [_vp, _vp, _u32, _vp, _u32, _vp]),
     "dab_distances_device": (_i, [_vp, _vp, _u32, _vp, _u32, _vp]),
@@ -38,6 +43,8 @@ SYMBOLS = {
     "dab_pq_distances": (_i, [_vp, _vp, _u32, _vp, _u32, _vp]),
     "dab_pq_encode": (_i, [_vp, _vp, _u64, _vp]),
     "dab_search_batch_pq": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "dab_search_batch_pq_rerank": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "dab_search_batch_pq_device": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _i, _vp, _vp, _vp, _vp, _vp]),
     "dab_sq_compress": (_i, [_i, _vp, _f, _u32, _i, _vp, _u64, _vp, _vp]),
     "dab_sq_distances": (_i, [_i, _i, _i, _f, _f, _u32, _vp, _vp, _vp, _vp, _u64, _vp]),
     "dab_robust_prune": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _f, _vp, _vp]),

@@ -143,6 +143,7 @@ void dab_destroy(dab_index* idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
     if (idx->own_stream) cudaStreamSynchronize(idx->own_stream);
+    comm_release(idx);
     cudaFree(idx->d_vectors);
     cudaFree(idx->d_adj);
     cudaFree(idx->d_pivots);

@@ -13,6 +13,8 @@
 
 #include "../../include/diskann_b200.h"
 
+struct dab_index;
+
 namespace dab {
 
 constexpr uint32_t kNoId = 0xFFFFFFFFu;
@@ -21,6 +23,7 @@ constexpr uint32_t kNoId = 0xFFFFFFFFu;
 char* error_buffer();
 int fail(int code, const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
+void comm_release(struct ::dab_index* idx);  // replicate.cu
 
 #define DAB_CUDA(expr)                                                                        \
     do {                                                                                      \
@@ -107,6 +110,10 @@ struct dab_index {
     cudaStream_t l2_window_stream = nullptr;
 
     dab::Tuning tune;
+
+    // replication (replicate.cu): NCCL communicator of a one-process-per-GPU host
+    void* nccl_comm = nullptr;
+    int nccl_rank = 0, nccl_ranks = 0;
 
     uint64_t n_total() const { return n_points + n_start; }
 };

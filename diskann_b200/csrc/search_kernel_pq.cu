@@ -16,8 +16,10 @@
 #include "dab_common.cuh"
 #include "quant_device.cuh"
 #include "search_common.cuh"
+#include "search_smem.cuh"
 
 #include <algorithm>
+#include <type_traits>
 
 namespace dab {
 
@@ -51,6 +53,10 @@ struct SearchParamsPq {
     uint32_t n_buckets;
     uint32_t* counters;
     uint32_t* overflow_list;
+    // optional: the whole candidate list (best.iter()) for the rerank stage
+    uint32_t* list_ids;     // [nq][list_cap]
+    uint32_t* list_counts;  // [nq]
+    uint32_t list_cap;
     uint32_t warp_smem, off_q, off_qd, off_qi, off_cid, off_cd, off_beam;
 };
 
@@ -216,6 +222,10 @@ __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchPa
         }
         {
             const uint32_t n = min(p.cap, size);
+            if (p.list_ids) {
+                for (uint32_t i = lane; i < n; i += 32) p.list_ids[(size_t)qidx * p.list_cap + i] = qi[i] & ~kFlagV2;
+                if (lane == 0) p.list_counts[qidx] = n;
+            }
             uint32_t count = 0;
             for (uint32_t b = 0; b < n && count < p.k; b += 32) {
                 const uint32_t i = b + lane;
@@ -244,8 +254,147 @@ __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchPa
     }
 }
 
+// ---- Rerank (diskann-providers/.../inmem/full_precision.rs:356-399 behind FilterStartPoints,
+// product.rs:391-400): every candidate of best.iter() that is not a start point gets its
+// full-precision Distance<T, T> to the query; the list is ordered by that distance (ties keep
+// their traversal order: the reference's sort_unstable_by leaves them unspecified) and the
+// first k are returned.  One warp per query; rows are gathered with the wide-load loops of
+// search_smem.cuh (f32 x f32 has the query x row association; i8 / u8 are exact).
+constexpr int kRerankWarps = 4;
+struct RerankParams {
+    const uint8_t* vectors;
+    size_t row_stride;
+    uint64_t n_points;
+    uint32_t dim;
+    const void* queries;  // index dtype
+    uint32_t nq, k, list_cap;
+    const uint32_t* list_ids;
+    const uint32_t* list_counts;
+    uint32_t* out_ids;
+    float* out_dists;
+    uint32_t* out_counts;
+    uint32_t warp_smem, off_ids, off_d;
+};
+
+template <typename TD, int KIND, int POST>
+__global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const RerankParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr bool kInt = std::is_same<TD, int8_t>::value || std::is_same<TD, uint8_t>::value;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint8_t* base = smem + (size_t)wib * p.warp_smem;
+    float* qf = reinterpret_cast<float*>(base);
+    uint32_t* cid = reinterpret_cast<uint32_t*>(base + p.off_ids);
+    float* cd = reinterpret_cast<float*>(base + p.off_d);
+    const int dim = (int)p.dim;
+    for (uint32_t q = blockIdx.x * kRerankWarps + wib; q < p.nq; q += gridDim.x * kRerankWarps) {
+        __syncwarp();
+        const TD* s = reinterpret_cast<const TD*>(p.queries) + (size_t)q * dim;
+        if constexpr (kInt) {
+            uint8_t* qb = reinterpret_cast<uint8_t*>(qf);
+            const int qbytes = (dim + 15) & ~15;
+            for (int e = lane; e < qbytes; e += 32) qb[e] = e < dim ? reinterpret_cast<const uint8_t*>(s)[e] : 0;
+        } else {
+            for (int e = lane; e < dim; e += 32) qf[e] = to_f32(s[e]);
+        }
+        const uint32_t n = min(p.list_counts[q], p.list_cap);
+        uint32_t m = 0;  // candidates that are not start points, traversal order kept
+        for (uint32_t b = 0; b < n; b += 32) {
+            const uint32_t i = b + lane;
+            const uint32_t id = i < n ? p.list_ids[(size_t)q * p.list_cap + i] : kEmptyV2;
+            const bool keep = i < n && id < p.n_points;
+            const unsigned mk = __ballot_sync(kFull, keep);
+            if (keep) cid[m + __popc(mk & ((1u << lane) - 1u))] = id;
+            m += __popc(mk);
+        }
+        __syncwarp();
+        if constexpr (kInt) {
+            int qq = 0;
+            if (KIND != KIND_IP) qq = warp_int_self<std::is_same<TD, int8_t>::value>(reinterpret_cast<const uint8_t*>(qf), dim, lane);
+            wide_distances_int<std::is_same<TD, int8_t>::value, KIND, POST, 4>(reinterpret_cast<const uint8_t*>(qf), qq, p.vectors, p.row_stride,
+                                                                             cid, m, cd, dim, lane);
+        } else {
+            wide_distances<TD, KIND, POST, 2, 4>(qf, p.vectors, p.row_stride, cid, m, cd, dim, lane);
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < m; i += 32) {
+            const float di = cd[i];
+            uint32_t r = 0;
+            for (uint32_t j = 0; j < m; ++j) {
+                const float dj = cd[j];
+                r += (dj < di || (dj == di && j < i)) ? 1u : 0u;
+            }
+            if (r < p.k) {
+                p.out_ids[(size_t)q * p.k + r] = cid[i];
+                p.out_dists[(size_t)q * p.k + r] = di;
+            }
+        }
+        const uint32_t count = min(m, p.k);
+        for (uint32_t i = count + lane; i < p.k; i += 32) {
+            p.out_ids[(size_t)q * p.k + i] = kEmptyV2;
+            p.out_dists[(size_t)q * p.k + i] = __int_as_float(0x7F800000);
+        }
+        if (lane == 0 && p.out_counts) p.out_counts[q] = count;
+    }
+}
+
+static int launch_rerank(dab_index* idx, const void* d_queries, uint32_t nq, uint32_t k, uint32_t list_cap, const uint32_t* d_list,
+                         const uint32_t* d_list_n, uint32_t* d_ids, float* d_dists, uint32_t* d_counts) {
+    const bool is_int = idx->dtype == DAB_I8 || idx->dtype == DAB_U8;
+    if (idx->dtype == DAB_F16)
+        return fail(DAB_ERR_INVALID_ARGUMENT, "rerank: f16 x f16 full-precision distances (Strategy2x4) are not built on this path");
+    const MetricPlan plan = plan_for(idx->metric, is_int);
+    if (plan.kind == KIND_COS && !is_int) return fail(DAB_ERR_INVALID_ARGUMENT, "rerank: Metric::Cosine over float rows is not built on this path");
+    RerankParams p;
+    memset(&p, 0, sizeof(p));
+    p.vectors = idx->d_vectors;
+    p.row_stride = idx->row_stride;
+    p.n_points = idx->n_points;
+    p.dim = idx->dim;
+    p.queries = d_queries;
+    p.nq = nq;
+    p.k = k;
+    p.list_cap = list_cap;
+    p.list_ids = d_list;
+    p.list_counts = d_list_n;
+    p.out_ids = d_ids;
+    p.out_dists = d_dists;
+    p.out_counts = d_counts;
+    size_t off = is_int ? round_up((size_t)idx->dim, 16) : round_up((size_t)idx->dim * 4, 16);
+    p.off_ids = (uint32_t)off;
+    off += round_up((size_t)list_cap * 4, 16);
+    p.off_d = (uint32_t)off;
+    off += round_up((size_t)list_cap * 4, 16);
+    p.warp_smem = (uint32_t)off;
+    const size_t smem = off * kRerankWarps;
+    if (smem > 200 * 1024) return fail(DAB_ERR_INVALID_ARGUMENT, "rerank: configuration needs %zu B shared memory per CTA", smem);
+    const int grid = (int)std::min<uint64_t>(((uint64_t)nq + kRerankWarps - 1) / kRerankWarps, (uint64_t)idx->sm_count * 8);
+#define DAB_RERANK(TD, K_, P_)                                                                               \
+    do {                                                                                                     \
+        auto kern = rerank_kernel<TD, K_, P_>;                                                               \
+        DAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        kern<<<grid, kRerankWarps * 32, smem, idx->stream>>>(p);                                             \
+    } while (0)
+    if (idx->dtype == DAB_F32) {
+        if (plan.kind == KIND_L2) DAB_RERANK(float, KIND_L2, POST_ID);
+        else if (plan.post == POST_NEG) DAB_RERANK(float, KIND_IP, POST_NEG);
+        else DAB_RERANK(float, KIND_IP, POST_ONE_MINUS);
+    } else if (idx->dtype == DAB_I8) {
+        if (plan.kind == KIND_L2) DAB_RERANK(int8_t, KIND_L2, POST_ID);
+        else if (plan.kind == KIND_IP) DAB_RERANK(int8_t, KIND_IP, POST_NEG);
+        else DAB_RERANK(int8_t, KIND_COS, POST_ONE_MINUS);
+    } else {
+        if (plan.kind == KIND_L2) DAB_RERANK(uint8_t, KIND_L2, POST_ID);
+        else if (plan.kind == KIND_IP) DAB_RERANK(uint8_t, KIND_IP, POST_NEG);
+        else DAB_RERANK(uint8_t, KIND_COS, POST_ONE_MINUS);
+    }
+#undef DAB_RERANK
+    DAB_LAUNCHED();
+    DAB_CUDA(cudaGetLastError());
+    return DAB_OK;
+}
+
 static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam,
-                         uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cmps, uint32_t* d_hops) {
+                         uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cmps, uint32_t* d_hops, bool rerank) {
     if (!idx->graph_ready) return fail(DAB_ERR_NOT_READY, "dab_search_batch_pq: graph must be uploaded first");
     if (!idx->d_pivots || !idx->d_codes || !idx->pq_codes_ready)
         return fail(DAB_ERR_NOT_READY, "dab_search_batch_pq: no PQ codes (dab_upload_pq with codes, or dab_pq_encode_all)");
@@ -317,6 +466,13 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     if ((rc = idx->s_out2.reserve(lut_bytes))) return rc;
     p.luts = (float*)idx->s_out2.p;
     p.n_work = nq;
+    if (rerank) {
+        if (!idx->vectors_ready) return fail(DAB_ERR_NOT_READY, "dab_search_batch_pq: rerank needs the full-precision vectors");
+        if ((rc = idx->s_ids.reserve(((size_t)nq * cap + nq) * 4))) return rc;
+        p.list_ids = (uint32_t*)idx->s_ids.p;
+        p.list_counts = p.list_ids + (size_t)nq * cap;
+        p.list_cap = cap;
+    }
     Scratch retry;
     for (int pass = 0; pass < 6; ++pass) {
         p.n_buckets = (uint32_t)((slots + 7) / 8);
@@ -334,6 +490,7 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
         DAB_CUDA(cudaStreamSynchronize(idx->stream));
         if (h[1] == 0) {
             retry.release();
+            if (rerank) return launch_rerank(idx, d_queries, nq, k, cap, p.list_ids, p.list_counts, d_ids, d_dists, d_counts);
             return DAB_OK;
         }
         Scratch next;
@@ -356,9 +513,8 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
 
 using namespace dab;
 
-extern "C" int dab_search_batch_pq(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search,
-                                   uint32_t beam_width, uint32_t* out_ids, float* out_dists, uint32_t* out_counts,
-                                   uint32_t* out_cmps, uint32_t* out_hops) {
+static int search_pq_host(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam_width,
+                          uint32_t* out_ids, float* out_dists, uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops, bool rerank) {
     if (!idx) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: idx is NULL");
     if (nq == 0) return DAB_OK;
     if (!queries || !out_ids || !out_dists) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: NULL argument");
@@ -376,7 +532,7 @@ extern "C" int dab_search_batch_pq(dab_index* idx, const void* queries, uint32_t
     uint32_t* d_cmps = d_counts + nq;
     uint32_t* d_hops = d_cmps + nq;
     DAB_CUDA(cudaMemcpyAsync(idx->s_queries.p, queries, qbytes, cudaMemcpyHostToDevice, idx->stream));
-    if ((rc = run_search_pq(idx, idx->s_queries.p, nq, k, l_search, beam_width, d_ids, d_dists, d_counts, d_cmps, d_hops))) return rc;
+    if ((rc = run_search_pq(idx, idx->s_queries.p, nq, k, l_search, beam_width, d_ids, d_dists, d_counts, d_cmps, d_hops, rerank))) return rc;
     DAB_CUDA(cudaMemcpyAsync(out_ids, d_ids, rbytes, cudaMemcpyDeviceToHost, idx->stream));
     DAB_CUDA(cudaMemcpyAsync(out_dists, d_dists, rbytes, cudaMemcpyDeviceToHost, idx->stream));
     if (out_counts) DAB_CUDA(cudaMemcpyAsync(out_counts, d_counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, idx->stream));
@@ -385,3 +541,27 @@ extern "C" int dab_search_batch_pq(dab_index* idx, const void* queries, uint32_t
     DAB_CUDA(cudaStreamSynchronize(idx->stream));
     return DAB_OK;
 }
+
+extern "C" {
+
+int dab_search_batch_pq(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam_width,
+                        uint32_t* out_ids, float* out_dists, uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops) {
+    return search_pq_host(idx, queries, nq, k, l_search, beam_width, out_ids, out_dists, out_counts, out_cmps, out_hops, false);
+}
+
+int dab_search_batch_pq_rerank(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam_width,
+                               uint32_t* out_ids, float* out_dists, uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops) {
+    return search_pq_host(idx, queries, nq, k, l_search, beam_width, out_ids, out_dists, out_counts, out_cmps, out_hops, true);
+}
+
+int dab_search_batch_pq_device(dab_index* idx, const void* d_queries, uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam_width,
+                               int rerank, uint32_t* d_out_ids, float* d_out_dists, uint32_t* d_out_counts, uint32_t* d_out_cmps,
+                               uint32_t* d_out_hops) {
+    if (!idx) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq_device: idx is NULL");
+    if (nq == 0) return DAB_OK;
+    if (!d_queries || !d_out_ids || !d_out_dists) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq_device: NULL argument");
+    DAB_CUDA(cudaSetDevice(idx->device));
+    return run_search_pq(idx, d_queries, nq, k, l_search, beam_width, d_out_ids, d_out_dists, d_out_counts, d_out_cmps, d_out_hops, rerank != 0);
+}
+
+}  // extern "C"

@@ -35,119 +35,6 @@ namespace dab {
 
 namespace {
 
-// ---- float rows: distances of candidates cid[0..n) into cd[0..n) ----------------------------
-// Lane mapping of frontier_wide_kernel (distance_kernels.cu): a 16-byte load carries EPL
-// elements of one 8-element SIMD block; block k belongs to accumulator k mod 4, so the lane
-// with (a, h) = (accumulator, half of the block) loads blocks a, a+4, a+8, ... and runs the FMA
-// chains of its EPL slots itself.  LPR lanes cover a row, a pass covers ROWS rows, P passes of U
-// loads each are in flight together.  Association as distance_device.cuh: (s0+s1)+(s2+s3),
-// zero-filled remainder on the combined vector, sum_tree.
-template <typename TD, int KIND, int POST, int P, int U>
-__device__ __forceinline__ void wide_distances(const float* __restrict__ q, const uint8_t* __restrict__ vectors, size_t row_stride,
-                                               const uint32_t* __restrict__ cid, uint32_t n, float* __restrict__ cd, int dim, int lane) {
-    constexpr int EPL = 16 / (int)sizeof(TD), LPR = 32 / EPL, ROWS = EPL, HALVES = 8 / EPL;
-    const int team = lane / LPR, tl = lane % LPR;
-    const int a = tl / HALVES, h = tl % HALVES;
-    const int nb8 = dim >> 3, full8 = dim & ~7, rem = dim & 7;
-    const int nm = (nb8 + 3) >> 2;  // 16-byte loads per lane per row (the last may be predicated off)
-    if (n > P * ROWS) prefetch_rows(vectors, row_stride, cid, n, (uint32_t)((dim * (int)sizeof(TD) + 15) & ~15), lane);
-    for (uint32_t j0 = 0; j0 < n; j0 += P * ROWS) {
-        const uint8_t* row[P];
-        bool act[P];
-#pragma unroll
-        for (int pp = 0; pp < P; ++pp) {
-            act[pp] = j0 + pp * ROWS < n;  // warp-uniform
-            const uint32_t jj = min(j0 + pp * ROWS + team, n - 1);
-            row[pp] = vectors + (size_t)cid[jj] * row_stride + 16 * tl;
-        }
-        uint64_t acc2[P][EPL / 2];
-#pragma unroll
-        for (int pp = 0; pp < P; ++pp)
-#pragma unroll
-            for (int i = 0; i < EPL / 2; ++i) acc2[pp][i] = 0ull;
-        for (int m0 = 0; m0 < nm; m0 += U) {
-            uint4 v[P][U];
-#pragma unroll
-            for (int pp = 0; pp < P; ++pp) {
-                if (act[pp]) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        if (a + 4 * (m0 + u) < nb8) v[pp][u] = ldg16(row[pp] + (size_t)(m0 + u) * (LPR * 16));
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (a + 4 * (m0 + u) < nb8) {
-                    const float* qx = q + ((m0 + u) * (LPR * 16) + 16 * tl) / (int)sizeof(TD);
-                    float4 x[EPL / 4];
-#pragma unroll
-                    for (int i = 0; i < EPL / 4; ++i) x[i] = reinterpret_cast<const float4*>(qx)[i];
-#pragma unroll
-                    for (int pp = 0; pp < P; ++pp) {
-                        if (act[pp]) {
-                            if constexpr (sizeof(TD) == 2) {
-                                const __half2* hp = reinterpret_cast<const __half2*>(&v[pp][u]);
-                                const float2 f0 = __half22float2(hp[0]), f1 = __half22float2(hp[1]);
-                                const float2 f2 = __half22float2(hp[2]), f3 = __half22float2(hp[3]);
-                                acc2[pp][0] = step2<KIND>(acc2[pp][0], pack2(x[0].x, x[0].y), pack2(f0.x, f0.y));
-                                acc2[pp][1] = step2<KIND>(acc2[pp][1], pack2(x[0].z, x[0].w), pack2(f1.x, f1.y));
-                                acc2[pp][2] = step2<KIND>(acc2[pp][2], pack2(x[1].x, x[1].y), pack2(f2.x, f2.y));
-                                acc2[pp][3] = step2<KIND>(acc2[pp][3], pack2(x[1].z, x[1].w), pack2(f3.x, f3.y));
-                            } else {
-                                const uint4 w = v[pp][u];
-                                acc2[pp][0] = step2<KIND>(acc2[pp][0], pack2(x[0].x, x[0].y),
-                                                          pack2(__uint_as_float(w.x), __uint_as_float(w.y)));
-                                acc2[pp][1] = step2<KIND>(acc2[pp][1], pack2(x[0].z, x[0].w),
-                                                          pack2(__uint_as_float(w.z), __uint_as_float(w.w)));
-                            }
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int pp = 0; pp < P; ++pp) {
-            if (!act[pp]) continue;
-            float acc[EPL];
-#pragma unroll
-            for (int i = 0; i < EPL / 2; ++i) unpack2(acc2[pp][i], acc[2 * i], acc[2 * i + 1]);
-            // (s0 + s1) + (s2 + s3), slot-wise
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) {
-                acc[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], HALVES));
-                acc[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], 2 * HALVES));
-            }
-            if (rem) {  // zero-filled tail on the combined vector (simd.rs:733-744)
-                const TD* tail = reinterpret_cast<const TD*>(row[pp] - 16 * tl) + full8;
-#pragma unroll
-                for (int i = 0; i < EPL; ++i) {
-                    const int l = EPL * h + i;
-                    const float x = l < rem ? q[full8 + l] : 0.0f;
-                    const float yv = l < rem ? ldg_elem(tail + l) : 0.0f;
-                    if (KIND == KIND_L2) {
-                        const float dd = __fsub_rn(x, yv);
-                        acc[i] = __fmaf_rn(dd, dd, acc[i]);
-                    } else {
-                        acc[i] = __fmaf_rn(x, yv, acc[i]);
-                    }
-                }
-            }
-            float r;
-            if constexpr (HALVES == 1) {
-                r = __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[4]), __fadd_rn(acc[2], acc[6])),
-                              __fadd_rn(__fadd_rn(acc[1], acc[5]), __fadd_rn(acc[3], acc[7])));
-            } else {
-                float ts[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) ts[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], 1));  // x_i + x_{i+4}
-                r = __fadd_rn(__fadd_rn(ts[0], ts[2]), __fadd_rn(ts[1], ts[3]));
-            }
-            const uint32_t jj = j0 + pp * ROWS + team;
-            if (tl == 0 && jj < n) cd[jj] = post_op<POST>(r);
-        }
-    }
-}
-
 // ---- f32 rows of 32 * nm <= 128 elements (the headline shapes: 128-d, 96-d) ------------------
 // Same lane mapping and association as wide_distances, with the per-hop overheads removed: the
 // 16 query elements a lane ever multiplies live in registers (packed pairs), a step covers 8
@@ -202,90 +89,6 @@ __device__ __forceinline__ void wide_distances_f32_fast(const uint64_t (&q2)[8],
         const float r = __fadd_rn(z, __shfl_xor_sync(kFull, z, 1));
         const uint32_t jj = j0 + (pA ? 4 : 0) + team;  // lanes with pA hold the second pass
         if ((tl == 0 || tl == 2) && jj < n) cd[jj] = post_op<POST>(r);
-    }
-}
-
-// ---- i8 / u8 rows: exact i32 arithmetic, so any summation order gives the reference's value --
-// 8 lanes per row, 16 bytes per lane per load, 4 rows per pass, P passes in flight.
-// q: query bytes in shared memory, zero-padded to a multiple of 16; qq = sum q*q.
-template <bool SIGNED, int KIND, int POST, int P>
-__device__ __forceinline__ void wide_distances_int(const uint8_t* __restrict__ q, int qq, const uint8_t* __restrict__ vectors,
-                                                   size_t row_stride, const uint32_t* __restrict__ cid, uint32_t n,
-                                                   float* __restrict__ cd, int dim, int lane) {
-    constexpr int ROWS = 4;
-    const int team = lane >> 3, tl = lane & 7;
-    const int nfull = dim >> 4, tail = dim & 15;
-    const int nm = (nfull + 7) >> 3;
-    if (n > P * ROWS) prefetch_rows(vectors, row_stride, cid, n, (uint32_t)((dim + 15) & ~15), lane);
-    for (uint32_t j0 = 0; j0 < n; j0 += P * ROWS) {
-        const uint8_t* row[P];
-        bool act[P];
-        int xy[P], yy[P];
-#pragma unroll
-        for (int pp = 0; pp < P; ++pp) {
-            act[pp] = j0 + pp * ROWS < n;
-            const uint32_t jj = min(j0 + pp * ROWS + team, n - 1);
-            row[pp] = vectors + (size_t)cid[jj] * row_stride;
-            xy[pp] = yy[pp] = 0;
-        }
-        for (int m = 0; m < nm; ++m) {
-            const int c = m * 8 + tl;
-            if (c < nfull) {
-                uint4 v[P];
-#pragma unroll
-                for (int pp = 0; pp < P; ++pp)
-                    if (act[pp]) v[pp] = ldg16(row[pp] + (size_t)c * 16);
-                const uint4 x = reinterpret_cast<const uint4*>(q)[c];
-#pragma unroll
-                for (int pp = 0; pp < P; ++pp) {
-                    if (act[pp]) {
-                        xy[pp] = dp4<SIGNED>((int)x.x, (int)v[pp].x, xy[pp]);
-                        xy[pp] = dp4<SIGNED>((int)x.y, (int)v[pp].y, xy[pp]);
-                        xy[pp] = dp4<SIGNED>((int)x.z, (int)v[pp].z, xy[pp]);
-                        xy[pp] = dp4<SIGNED>((int)x.w, (int)v[pp].w, xy[pp]);
-                        if (KIND != KIND_IP) {
-                            yy[pp] = dp4<SIGNED>((int)v[pp].x, (int)v[pp].x, yy[pp]);
-                            yy[pp] = dp4<SIGNED>((int)v[pp].y, (int)v[pp].y, yy[pp]);
-                            yy[pp] = dp4<SIGNED>((int)v[pp].z, (int)v[pp].z, yy[pp]);
-                            yy[pp] = dp4<SIGNED>((int)v[pp].w, (int)v[pp].w, yy[pp]);
-                        }
-                    }
-                }
-            }
-        }
-        if (tail) {
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int i = (nfull << 4) + tl * 2 + t;
-                if (tl * 2 + t < tail) {
-                    const int x = byte_at<SIGNED>(q, i);
-#pragma unroll
-                    for (int pp = 0; pp < P; ++pp) {
-                        if (act[pp]) {
-                            const int y = SIGNED ? (int)(int8_t)__ldg(row[pp] + i) : (int)__ldg(row[pp] + i);
-                            xy[pp] += x * y;
-                            if (KIND != KIND_IP) yy[pp] += y * y;
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int pp = 0; pp < P; ++pp) {
-            if (!act[pp]) continue;
-            int sxy = xy[pp], syy = yy[pp];
-#pragma unroll
-            for (int o = 4; o >= 1; o >>= 1) {
-                sxy += __shfl_xor_sync(kFull, sxy, o);
-                if (KIND != KIND_IP) syy += __shfl_xor_sync(kFull, syy, o);
-            }
-            float r;
-            if (KIND == KIND_IP) r = (float)sxy;
-            else if (KIND == KIND_L2) r = (float)(int)((unsigned)qq + (unsigned)syy - 2u * (unsigned)sxy);
-            else r = cosine_finish((float)qq, (float)syy, (float)sxy);
-            const uint32_t jj = j0 + pp * ROWS + team;
-            if (tl == 0 && jj < n) cd[jj] = post_op<POST>(r);
-        }
     }
 }
 
@@ -622,7 +425,7 @@ int v3_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, uint32_t 
     const uint64_t n_slots = nbk * 16;
     uint32_t sbits = 0;
     while (((uint64_t)1 << sbits) < n_slots) ++sbits;
-    if (K + sbits > 32) return 1;
+    // magic = ceil(2^(K+s) / n_slots) < 2^(K+1) fits 32 bits and h * magic < 2^(2K+1) fits 64 for K <= 30
     const uint64_t tag_max = ((((uint64_t)1 << K) - 1)) / n_slots;
     uint32_t tag_bits = 0;
     while (((uint64_t)1 << tag_bits) <= tag_max) ++tag_bits;

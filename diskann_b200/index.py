@@ -113,6 +113,20 @@ class GpuIndex:
     def set_stream(self, cuda_stream_ptr):
         check(_lib.lib().dab_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
+    # -- replication (one process per GPU): NCCL inside the library
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(128)
+        check(_lib.lib().dab_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id, n_ranks, rank):
+        check(_lib.lib().dab_comm_init(self._h, C.c_char_p(unique_id), n_ranks, rank))
+
+    def broadcast_index(self, root=0):
+        """One NCCL broadcast per resident buffer (vectors, adjacency, PQ) from `root` to every rank."""
+        check(_lib.lib().dab_broadcast_index(self._h, root))
+
     # -- uploads
     def _rows(self, rows):
         rows = np.ascontiguousarray(rows)
@@ -240,8 +254,9 @@ class GpuIndex:
         check(_lib.lib().dab_pq_distances(self._h, _ptr(queries), queries.shape[0], _ptr(ids), ids.shape[1], _ptr(out)))
         return out
 
-    def search_batch_pq(self, queries, k, l_search, beam_width=1):
-        """KNN::search with PQ ADC traversal distances (providers' QuantAccessor)."""
+    def search_batch_pq(self, queries, k, l_search, beam_width=1, rerank=False):
+        """KNN::search with PQ ADC traversal distances (providers' QuantAccessor); rerank=True adds the
+        providers' full-precision Rerank post-processing."""
         queries = self._queries(queries)
         nq = queries.shape[0]
         ids = np.empty((nq, k), np.uint32)
@@ -249,9 +264,16 @@ class GpuIndex:
         counts = np.empty(nq, np.uint32)
         cmps = np.empty(nq, np.uint32)
         hops = np.empty(nq, np.uint32)
-        check(_lib.lib().dab_search_batch_pq(self._h, _ptr(queries), nq, k, l_search, beam_width, _ptr(ids), _ptr(dists),
-                                             _ptr(counts), _ptr(cmps), _ptr(hops)))
+        fn = _lib.lib().dab_search_batch_pq_rerank if rerank else _lib.lib().dab_search_batch_pq
+        check(fn(self._h, _ptr(queries), nq, k, l_search, beam_width, _ptr(ids), _ptr(dists), _ptr(counts), _ptr(cmps), _ptr(hops)))
         return ids, dists, counts, cmps, hops
+
+    def search_batch_pq_device(self, d_queries, nq, k, l_search, beam_width, d_ids, d_dists, d_counts=0, d_cmps=0, d_hops=0,
+                               rerank=True):
+        """Same with device pointers (integers); results stay in HBM."""
+        check(_lib.lib().dab_search_batch_pq_device(self._h, C.c_void_p(d_queries), nq, k, l_search, beam_width, int(bool(rerank)),
+                                                    C.c_void_p(d_ids), C.c_void_p(d_dists), C.c_void_p(d_counts or None),
+                                                    C.c_void_p(d_cmps or None), C.c_void_p(d_hops or None)))
 
     def pq_encode(self, vectors):
         vectors = np.ascontiguousarray(vectors, np.float32)

@@ -1,0 +1,140 @@
+//! Safe wrapper over `diskann-b200-sys` (see INTEGRATION.md for how it plugs into the reference:
+//! `GpuIndex` is the device snapshot a `layers::GpuFull<T>` mirrors into, `search_batch` is what a
+//! `benchmark_core::search::Search` implementation (`GpuKNN`) calls once per query batch).
+//! This image has no Rust toolchain: the crate is kept in step with the header by tools/gen_ffi.py
+//! (the -sys half) and mirrors diskann_b200/index.py, which the tests drive through the same ABI.
+use diskann_b200_sys as sys;
+use std::os::raw::c_void;
+use std::ptr;
+
+/// `diskann_vector::distance::Metric` values (`#[repr(C)]`, metric.rs:8-20) — pass `metric as i32`.
+#[repr(i32)]
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+pub enum Metric {
+    Cosine = 0,
+    InnerProduct = 1,
+    L2 = 2,
+    CosineNormalized = 3,
+}
+
+/// Element types with a device path (VectorRepr implementors the reference instantiates).
+pub trait Element: Copy {
+    const DTYPE: i32;
+}
+impl Element for f32 {
+    const DTYPE: i32 = 0;
+}
+impl Element for i8 {
+    const DTYPE: i32 = 2;
+}
+impl Element for u8 {
+    const DTYPE: i32 = 3;
+}
+// f16: `half::f16` with DTYPE = 1 (the crate does not depend on `half`; add the impl next to it)
+
+#[derive(Debug)]
+pub struct Error(pub String);
+pub type Result<T> = std::result::Result<T, Error>;
+
+fn check(status: i32) -> Result<()> {
+    sys::check(status).map_err(Error)
+}
+
+/// Results of one batched search: row-major `[nq][k]`, padded with `u32::MAX` / `+inf`;
+/// `cmps` / `hops` follow `SearchStats` (diskann/src/graph/index.rs:1990-1991).
+pub struct Batch {
+    pub k: usize,
+    pub ids: Vec<u32>,
+    pub dists: Vec<f32>,
+    pub counts: Vec<u32>,
+    pub cmps: Vec<u32>,
+    pub hops: Vec<u32>,
+}
+
+pub struct GpuIndex<T: Element> {
+    raw: *mut sys::dab_index,
+    dim: usize,
+    _marker: std::marker::PhantomData<T>,
+}
+
+// one CUDA stream per handle; read-only calls from one thread at a time
+unsafe impl<T: Element> Send for GpuIndex<T> {}
+
+impl<T: Element> GpuIndex<T> {
+    pub fn new(metric: Metric, dim: usize, n_points: u64, n_start: u32, max_degree: u32, device: i32) -> Result<Self> {
+        let mut raw = ptr::null_mut();
+        check(unsafe { sys::dab_create(&mut raw, T::DTYPE, metric as i32, dim as u32, n_points, n_start, max_degree, device) })?;
+        Ok(Self { raw, dim, _marker: std::marker::PhantomData })
+    }
+
+    /// Dense row-major rows `[count][dim]` starting at row `first` (start points follow the data points).
+    pub fn upload_vectors(&mut self, rows: &[T], first: u64) -> Result<()> {
+        assert_eq!(rows.len() % self.dim, 0, "rows must be a whole number of vectors");
+        check(unsafe { sys::dab_upload_vectors(self.raw, rows.as_ptr() as *const c_void, first, (rows.len() / self.dim) as u64) })
+    }
+
+    /// Adjacency rows `[count][stride]` with `row[0] = degree` (diskann-inmem/src/neighbors.rs:69-163).
+    pub fn upload_graph(&mut self, adj: &[u32], stride: u32, first: u64) -> Result<()> {
+        assert_eq!(adj.len() % stride as usize, 0);
+        check(unsafe { sys::dab_upload_graph(self.raw, adj.as_ptr(), stride, first, (adj.len() / stride as usize) as u64) })
+    }
+
+    /// Batched `multi_insert`-style construction on the device over the uploaded vectors.
+    pub fn build(&mut self, pruned_degree: u32, l_build: u32, alpha: f32) -> Result<()> {
+        check(unsafe { sys::dab_build(self.raw, pruned_degree, l_build, alpha, 0) })
+    }
+
+    /// `KNN::search` for every query of the batch at once (search_internal + post-processing).
+    pub fn search_batch(&self, queries: &[T], k: usize, l_search: u32, beam_width: u32) -> Result<Batch> {
+        assert_eq!(queries.len() % self.dim, 0);
+        let nq = queries.len() / self.dim;
+        let mut b = Batch { k, ids: vec![0; nq * k], dists: vec![0.0; nq * k], counts: vec![0; nq], cmps: vec![0; nq], hops: vec![0; nq] };
+        check(unsafe {
+            sys::dab_search_batch(self.raw, queries.as_ptr() as *const c_void, nq as u32, k as u32, l_search, beam_width,
+                                  b.ids.as_mut_ptr(), b.dists.as_mut_ptr(), b.counts.as_mut_ptr(), b.cmps.as_mut_ptr(), b.hops.as_mut_ptr())
+        })?;
+        Ok(b)
+    }
+
+    /// PQ traversal + the providers' full-precision `Rerank` (what `use_fp_for_search: false` runs).
+    pub fn search_batch_pq_rerank(&self, queries: &[T], k: usize, l_search: u32, beam_width: u32) -> Result<Batch> {
+        assert_eq!(queries.len() % self.dim, 0);
+        let nq = queries.len() / self.dim;
+        let mut b = Batch { k, ids: vec![0; nq * k], dists: vec![0.0; nq * k], counts: vec![0; nq], cmps: vec![0; nq], hops: vec![0; nq] };
+        check(unsafe {
+            sys::dab_search_batch_pq_rerank(self.raw, queries.as_ptr() as *const c_void, nq as u32, k as u32, l_search, beam_width,
+                                            b.ids.as_mut_ptr(), b.dists.as_mut_ptr(), b.counts.as_mut_ptr(), b.cmps.as_mut_ptr(),
+                                            b.hops.as_mut_ptr())
+        })?;
+        Ok(b)
+    }
+
+    /// `train_pq` + encoding of every stored row, on the device.
+    pub fn train_pq(&mut self, train: &[f32], n_chunks: u32, seed: u64) -> Result<()> {
+        assert_eq!(train.len() % self.dim, 0);
+        check(unsafe { sys::dab_pq_train(self.raw, train.as_ptr(), (train.len() / self.dim) as u64, n_chunks, 256, 5, seed) })?;
+        check(unsafe { sys::dab_pq_encode_all(self.raw) })
+    }
+
+    /// One process per GPU: join the communicator described by `id` (from `unique_id()` on rank 0) …
+    pub fn comm_init(&mut self, id: &[u8; 128], n_ranks: i32, rank: i32) -> Result<()> {
+        check(unsafe { sys::dab_comm_init(self.raw, id.as_ptr() as *const _, n_ranks, rank) })
+    }
+
+    /// … and replicate the resident snapshot from `root` (one NCCL broadcast per buffer, at load).
+    pub fn broadcast_index(&mut self, root: i32) -> Result<()> {
+        check(unsafe { sys::dab_broadcast_index(self.raw, root) })
+    }
+}
+
+pub fn unique_id() -> Result<[u8; 128]> {
+    let mut id = [0u8; 128];
+    check(unsafe { sys::dab_comm_unique_id(id.as_mut_ptr() as *mut _) })?;
+    Ok(id)
+}
+
+impl<T: Element> Drop for GpuIndex<T> {
+    fn drop(&mut self) {
+        unsafe { sys::dab_destroy(self.raw) }
+    }
+}

@@ -108,6 +108,22 @@ int dab_pq_encode_all(dab_index* idx);
  * [(n_points + n_start)][n_chunks]; any pointer may be NULL. */
 int dab_pq_download(dab_index* idx, float* pivots, uint64_t* offsets, uint8_t* codes);
 
+/* ------------------------------------------------------------------ replication across GPUs */
+
+/* The index is replicated, the query batch is sharded, the search path has no collective
+ * (benchmark-core/src/search/api.rs:410-419 partitions queries over tasks the same way).
+ * One NCCL broadcast per resident buffer (vectors, adjacency, PQ table and codes) at load.  NCCL is
+ * resolved with dlopen("libnccl.so.2") at first use; DAB_ERR_NOT_READY if it cannot be loaded.
+ * One process per GPU: rank 0 calls dab_comm_unique_id and ships the 128 bytes to the other ranks,
+ * every rank calls dab_comm_init on its own handle (created with the same shape), then
+ * dab_broadcast_index(idx, root).  dab_destroy releases the communicator. */
+int dab_comm_unique_id(char* out_id128);
+int dab_comm_init(dab_index* idx, const char* id128, int n_ranks, int rank);
+int dab_broadcast_index(dab_index* idx, int root);
+int dab_comm_destroy(dab_index* idx);
+/* One process driving several GPUs: per_gpu[0] is the root, per_gpu[i] lives on its own device. */
+int dab_broadcast(dab_index* const* per_gpu, int n_gpus);
+
 /* ------------------------------------------------------------------ (1) per-pair / per-query distances */
 
 /* DistanceProvider::distance_comparer(metric, dim) -> Distance<T,U>::call
@@ -176,6 +192,21 @@ int dab_pq_distances(dab_index* idx, const float* queries, uint32_t nq, const ui
 int dab_search_batch_pq(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search,
                         uint32_t beam_width, uint32_t* out_ids, float* out_dists,
                         uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops);
+
+/* The same followed by the quantized providers' default post-processing
+ * Pipeline<FilterStartPoints, Rerank> (inmem/product.rs:391-400; full_precision.rs:356-399): every
+ * entry of the candidate list that is not a start point is re-scored with the full-precision
+ * Distance<T, T> over the uploaded rows, the list is ordered by that distance (ties keep their
+ * traversal order; the reference leaves them unspecified) and the first k are returned — what
+ * `use_fp_for_search: false` runs in diskann-benchmark (src/index/inmem/product.rs:233-239).
+ * f32, i8 and u8 rows. */
+int dab_search_batch_pq_rerank(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search,
+                               uint32_t beam_width, uint32_t* out_ids, float* out_dists,
+                               uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops);
+/* device-pointer variant of both (rerank = 0 / 1); results stay in HBM */
+int dab_search_batch_pq_device(dab_index* idx, const void* d_queries, uint32_t nq, uint32_t k, uint32_t l_search,
+                               uint32_t beam_width, int rerank, uint32_t* d_out_ids, float* d_out_dists,
+                               uint32_t* d_out_counts, uint32_t* d_out_cmps, uint32_t* d_out_hops);
 
 /* BasicTable::compress_into (diskann-quantization/src/product/tables/basic.rs:161-194) for n
  * host vectors (f32): codes [n][n_chunks].  Returns DAB_ERR_INVALID_ARGUMENT if a chunk's

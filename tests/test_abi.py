@@ -72,3 +72,14 @@ def test_argument_validation_happens_before_any_device_work():
     assert L.dab_pair_distances(0, 0, 9, 4, None, None, 0, None, 0) == 1
     L.dab_destroy(None)  # no-op
     assert dab.Metric.Cosine == 0 and dab.Metric.InnerProduct == 1 and dab.Metric.L2 == 2 and dab.Metric.CosineNormalized == 3
+
+
+def test_rust_sys_crate_is_generated_from_the_header():
+    """ffi/diskann-b200-sys/src/lib.rs declares exactly the header's entry points (tools/gen_ffi.py --check)."""
+    import subprocess
+    import sys
+    assert subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_ffi.py"), "--check"]).returncode == 0
+    text = open(os.path.join(ROOT, "ffi", "diskann-b200-sys", "src", "lib.rs")).read()
+    import diskann_b200._lib as L
+    for name in L.SYMBOLS:
+        assert f"pub fn {name}(" in text, name

@@ -502,6 +502,15 @@ def test_pq_traversal_search_identical_to_oracle(dab, dt, metric, d, chunks):
             want = oidx.search_batch(queries, k, Ls, beam=beam, threads=4)
             for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
                 assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, k, Ls, beam)
+            # + Pipeline<FilterStartPoints, Rerank>: the candidate list re-scored with Distance<T, T>
+            if vecs.dtype != np.float16:
+                got = g.search_batch_pq(queries, k, Ls, beam, rerank=True)
+                want = oidx.search_batch_rerank(queries, k, Ls, beam=beam, threads=4)
+                for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
+                    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), ("rerank", name, k, Ls, beam)
+            else:
+                with pytest.raises(dab.DabError):
+                    g.search_batch_pq(queries[:2], k, Ls, beam, rerank=True)
     with dab.GpuIndex(dab.DType.f32, dab.Metric.Cosine, d, n, 1, maxdeg) as g:
         g.upload_vectors(f32)
         g.upload_graph(adj)
