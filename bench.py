@@ -61,6 +61,7 @@ TARGET_RECALL = 0.95
 NB = 4            # distinct query batches rotated through the timed loop
 PARITY_PER_BATCH = 256
 L_SWEEP = [10, 15, 20, 25, 30, 40, 50, 60, 70, 80, 90, 100, 120, 140, 160, 200, 250]
+L_SWEEP_PQ = L_SWEEP + [300, 350, 400, 450, 500]  # the PQ traversal kernel holds lists of up to 512 entries
 SEED_BASE, SEED_QUERY, SEED_PQ = 0xD15C0003, 0xD15C0004, 13076402859301299683  # PQ seed of example/product.json
 NP_DTYPE = {"f32": np.float32, "f16": np.float16, "i8": np.int8}
 ELEM = {"f32": 4, "f16": 2, "i8": 1}
@@ -378,7 +379,7 @@ def run_gpu(args):
     sweep, min_l = [], None
     l_search = args.l_search or cfg["l_search"]
     if rank == 0 and not args.l_search:
-        for L in L_SWEEP:
+        for L in (L_SWEEP_PQ if is_pq else L_SWEEP):
             ids, _, counts, cmps, hops = search_host(batches[0], L)
             r = recall_of(gts[0], ids, counts)
             sweep.append({"l": L, "recall": round(r, 5), "mean_cmps": float(cmps.mean()), "mean_hops": float(hops.mean())})
@@ -386,7 +387,7 @@ def run_gpu(args):
                 min_l = L
                 break
         if min_l is None:
-            min_l = L_SWEEP[-1]
+            min_l = (L_SWEEP_PQ if is_pq else L_SWEEP)[-1]
         if min_l > l_search:
             l_search = min_l
     if world > 1:
@@ -524,7 +525,7 @@ def run_gpu(args):
                          f"{NB} query batches rotate and each step gathers GBs of random rows",
             "setup_s": dict(t_prep, data=round(t_data, 1), ground_truth=round(t_gt, 2)),
             "l_sweep": sweep, "at_min_l": at_min_l, "parity_gate": parity})
-        kernel = ("search_kernel_pq + rerank" if is_pq else "search_kernel_v4") + f"<{cfg['dtype']},{cfg['metric'].upper()}>"
+        kernel = ("search_kernel_pq + rerank_kernel" if is_pq else "search_kernel_v3 / v2") + f"<{cfg['dtype']},{cfg['metric'].upper()}>"
         result = {
             "metric": metric_name(cfg), "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
@@ -638,7 +639,7 @@ def prepare_only(args):
     l_search = args.l_search or cfg["l_search"]
     min_l = None
     if not args.l_search:
-        for L in L_SWEEP:
+        for L in (L_SWEEP_PQ if cfg["path"] == "pq" else L_SWEEP):
             r = g.search_batch_pq(queries, K, L, 1, rerank=True) if cfg["path"] == "pq" else g.search_batch(queries, K, L, 1)
             min_l = L
             if recall_of(gt_all[0], r[0], r[2]) >= TARGET_RECALL:

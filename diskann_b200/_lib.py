@@ -50,6 +50,7 @@ SYMBOLS = {
     "dab_robust_prune": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _f, _vp, _vp]),
     "dab_build": (_i, [_vp, _u32, _u32, _f, _u32]),
     "dab_flat_knn": (_i, [_vp, _vp, _u32, _u32, _vp, _vp]),
+    "dab_flat_knn_tc": (_i, [_vp, _vp, _u32, _u32, _vp, _vp]),
 }
 
 _lib = None

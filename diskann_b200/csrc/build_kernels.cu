@@ -530,7 +530,10 @@ int dab_build(dab_index* idx, uint32_t pruned_degree, uint32_t l_build, float al
     DAB_CUDA(cudaSetDevice(idx->device));
     const uint32_t n = (uint32_t)idx->n_points;
     if (batch_size == 0) batch_size = std::max<uint32_t>(1024, std::min<uint32_t>(65536, n / 16));
-    const uint32_t rec_cap = std::min<uint32_t>(kMaxOcclusion, 2 * l_build + 32);
+    // VisitedSearchRecord keeps every expanded node (index.rs:276-282; SortedNeighbors truncates to the 750
+    // closest afterwards): the record is sized generously and a search that still outgrows it is reported
+    const uint32_t rec_cap = std::min<uint32_t>(2048, 4 * l_build + 64);
+    idx->rec_truncated = 0;
     cudaStream_t st = idx->stream;
 
     DAB_CUDA(cudaMemsetAsync(idx->d_adj, 0, idx->n_total() * (size_t)idx->adj_stride * 4, st));
@@ -598,6 +601,9 @@ int dab_build(dab_index* idx, uint32_t pruned_degree, uint32_t l_build, float al
         inserted += b;
     }
     DAB_CUDA(cudaStreamSynchronize(st));
+    if (idx->rec_truncated)
+        return fail(DAB_ERR_INVALID_ARGUMENT, "dab_build: %llu insert searches expanded more than %u nodes; their prune pools were cut "
+                    "(the graph is usable but not the reference's)", (unsigned long long)idx->rec_truncated, rec_cap);
     return DAB_OK;
 }
 

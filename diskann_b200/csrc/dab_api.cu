@@ -144,6 +144,7 @@ void dab_destroy(dab_index* idx) {
     cudaSetDevice(idx->device);
     if (idx->own_stream) cudaStreamSynchronize(idx->own_stream);
     comm_release(idx);
+    tc_release(idx);
     cudaFree(idx->d_vectors);
     cudaFree(idx->d_adj);
     cudaFree(idx->d_pivots);
@@ -185,6 +186,7 @@ static int upload_rows(dab_index* idx, const void* rows, uint64_t first, uint64_
     }
     DAB_CUDA(cudaStreamSynchronize(idx->stream));
     idx->vectors_ready = true;
+    ++idx->vectors_version;
     return DAB_OK;
 }
 

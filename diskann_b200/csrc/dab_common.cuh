@@ -24,6 +24,7 @@ char* error_buffer();
 int fail(int code, const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 void comm_release(struct ::dab_index* idx);  // replicate.cu
+void tc_release(struct ::dab_index* idx);    // flat_tc.cu
 
 #define DAB_CUDA(expr)                                                                        \
     do {                                                                                      \
@@ -109,7 +110,13 @@ struct dab_index {
     size_t l2_window_bytes = 0;
     cudaStream_t l2_window_stream = nullptr;
 
+    uint64_t rec_truncated = 0;  // build: searches whose expanded-node record was cut at its capacity
     dab::Tuning tune;
+
+    // tensor-core exhaustive scan (flat_tc.cu): bf16 operand copy of the rows + score coefficients
+    void* d_tc_base = nullptr;
+    void* d_tc_coef = nullptr;
+    uint64_t tc_version = 0, vectors_version = 1;  // the copy is rebuilt when rows were uploaded since
 
     // replication (replicate.cu): NCCL communicator of a one-process-per-GPU host
     void* nccl_comm = nullptr;

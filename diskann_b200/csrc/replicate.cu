@@ -136,6 +136,7 @@ int broadcast_buffers(dab_index* idx, ncclComm_t comm, int root, bool is_root, I
     }
     DAB_CUDA(cudaStreamSynchronize(st));
     idx->vectors_ready = got.vectors_ready != 0;
+    if (got.vectors_ready && !is_root) ++idx->vectors_version;
     idx->graph_ready = got.graph_ready != 0;
     idx->pq_chunks = got.pq_chunks;
     idx->pq_centers = got.pq_centers;
@@ -263,6 +264,7 @@ int dab_broadcast(dab_index* const* per_gpu, int n_gpus) {
         cudaStreamSynchronize(per_gpu[i]->stream);
         if (status == DAB_OK && i) {
             per_gpu[i]->vectors_ready = want.vectors_ready != 0;
+            ++per_gpu[i]->vectors_version;
             per_gpu[i]->graph_ready = want.graph_ready != 0;
             per_gpu[i]->pq_chunks = want.pq_chunks;
             per_gpu[i]->pq_centers = want.pq_centers;

@@ -329,7 +329,10 @@ __global__ void __launch_bounds__(kSearchWarps * 32) search_kernel(const SearchP
                 if (p.out_counts) p.out_counts[qidx] = count;
                 if (p.out_cmps) p.out_cmps[qidx] = cmps;
                 if (p.out_hops) p.out_hops[qidx] = hops;
-                if (p.rec_counts) p.rec_counts[qidx] = min(nrec, p.rec_cap);
+                if (p.rec_counts) {
+                    p.rec_counts[qidx] = min(nrec, p.rec_cap);
+                    if (nrec > p.rec_cap) atomicAdd(p.counters + 3, 1u);  // expanded nodes beyond the record: reported by dab_build
+                }
             }
         }
     }
@@ -608,9 +611,10 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
 #undef DAB_FILL_FIRST
             DAB_LAUNCHED();
             DAB_CUDA(cudaGetLastError());
-            uint32_t h_counters[3] = {0, 0, 0};
-            DAB_CUDA(cudaMemcpyAsync(h_counters, d_counters, 12, cudaMemcpyDeviceToHost, idx->stream));
+            uint32_t h_counters[4] = {0, 0, 0, 0};
+            DAB_CUDA(cudaMemcpyAsync(h_counters, d_counters, 16, cudaMemcpyDeviceToHost, idx->stream));
             DAB_CUDA(cudaStreamSynchronize(idx->stream));
+            idx->rec_truncated += h_counters[3];
             const uint32_t n_over = h_counters[1];
             if (!rec_ids) {
                 if (l_search != idx->hint_l || beam != idx->hint_beam) {
@@ -679,9 +683,10 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
         }
         DAB_LAUNCHED();
         DAB_CUDA(cudaGetLastError());
-        uint32_t h_counters[3] = {0, 0, 0};
-        DAB_CUDA(cudaMemcpyAsync(h_counters, d_counters, 12, cudaMemcpyDeviceToHost, idx->stream));
+        uint32_t h_counters[4] = {0, 0, 0, 0};
+        DAB_CUDA(cudaMemcpyAsync(h_counters, d_counters, 16, cudaMemcpyDeviceToHost, idx->stream));
         DAB_CUDA(cudaStreamSynchronize(idx->stream));
+        idx->rec_truncated += h_counters[3];
         const uint32_t n_over = h_counters[1];
         if (use_v2 && p2.phase_cycles) {
             unsigned long long h_ph[8];

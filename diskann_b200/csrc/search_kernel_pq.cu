@@ -402,7 +402,7 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     if (idx->metric == DAB_COSINE)
         return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: Metric::Cosine traverses with DirectCosine (no table); use dab_pq_distances");
     const uint32_t cap = l_search + idx->n_start;
-    if (cap > 256) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: L + #start must be <= 256");
+    if (cap > 512) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: L + #start must be <= 512");
     SearchParamsPq p;
     memset(&p, 0, sizeof(p));
     p.adj = idx->d_adj;
@@ -446,7 +446,7 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     p.warp_smem = (uint32_t)round_up(off, 16);
     const size_t smem_block = (size_t)p.warp_smem * kPqWarps;
     if (smem_block > 200 * 1024) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: configuration needs %zu B shared memory per CTA", smem_block);
-    void (*kern)(const SearchParamsPq) = cap <= 128 ? search_kernel_pq<4> : search_kernel_pq<8>;
+    void (*kern)(const SearchParamsPq) = cap <= 128 ? search_kernel_pq<4> : cap <= 256 ? search_kernel_pq<8> : search_kernel_pq<16>;
     DAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block));
     int per_sm = 0;
     DAB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPqWarps * 32, smem_block));

@@ -754,7 +754,10 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                 if (p.out_counts) p.out_counts[qidx] = count;
                 if (p.out_cmps) p.out_cmps[qidx] = cmps;
                 if (p.out_hops) p.out_hops[qidx] = hops;
-                if (p.rec_counts) p.rec_counts[qidx] = min(nrec, p.rec_cap);
+                if (p.rec_counts) {
+                    p.rec_counts[qidx] = min(nrec, p.rec_cap);
+                    if (nrec > p.rec_cap) atomicAdd(p.counters + 3, 1u);  // expanded nodes beyond the record: reported by dab_build
+                }
             }
         }
         DAB_PHASE(7);  // output

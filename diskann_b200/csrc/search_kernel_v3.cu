@@ -35,6 +35,13 @@ namespace dab {
 
 namespace {
 
+#ifndef DAB_V3_LP16
+#define DAB_V3_LP16 0  // visited set: 1 = linear-probing 16-bit slots (measured slower: dependent probe steps), 0 = buckets of 16 tags
+#endif
+#ifndef DAB_V3_FAST_ONE
+#define DAB_V3_FAST_ONE 0  // fast f32 path: one 4-row pass per step instead of two
+#endif
+
 // ---- f32 rows of 32 * nm <= 128 elements (the headline shapes: 128-d, 96-d) ------------------
 // Same lane mapping and association as wide_distances, with the per-hop overheads removed: the
 // 16 query elements a lane ever multiplies live in registers (packed pairs), a step covers 8
@@ -48,6 +55,39 @@ __device__ __forceinline__ void wide_distances_f32_fast(const uint64_t (&q2)[8],
                                                         size_t row_stride, const uint32_t* __restrict__ cid, uint32_t n,
                                                         float* __restrict__ cd, int lane) {
     const int team = lane >> 3, tl = lane & 7;
+#if DAB_V3_FAST_ONE
+    // one pass (4 rows) per step: 16 fewer registers, for the 5-CTA (20 warps per SM) build
+    if (n > 4) prefetch_rows(vectors, row_stride, cid, n, (uint32_t)nm * 128u, lane);
+    for (uint32_t j0 = 0; j0 < n; j0 += 4) {
+        const uint8_t* row0 = vectors + (size_t)cid[min(j0 + team, n - 1)] * row_stride + 16 * tl;
+        uint4 v0[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            if (m < nm) v0[m] = ldg16(row0 + m * 128);
+        uint64_t a0[2] = {0ull, 0ull};
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            if (m < nm) {
+                a0[0] = step2<KIND>(a0[0], q2[2 * m], pack2(__uint_as_float(v0[m].x), __uint_as_float(v0[m].y)));
+                a0[1] = step2<KIND>(a0[1], q2[2 * m + 1], pack2(__uint_as_float(v0[m].z), __uint_as_float(v0[m].w)));
+            }
+        }
+        float acc[4];
+        unpack2(a0[0], acc[0], acc[1]);
+        unpack2(a0[1], acc[2], acc[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            acc[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], 2));
+            acc[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], 4));
+        }
+        float ts[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ts[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], 1));
+        const float r = __fadd_rn(__fadd_rn(ts[0], ts[2]), __fadd_rn(ts[1], ts[3]));
+        if (tl == 0 && j0 + team < n) cd[j0 + team] = post_op<POST>(r);
+    }
+    return;
+#endif
     const bool pA = (tl & 2) != 0, pB = (tl & 4) != 0, hh = (tl & 1) != 0;
     if (n > 8) prefetch_rows(vectors, row_stride, cid, n, (uint32_t)nm * 128u, lane);
     for (uint32_t j0 = 0; j0 < n; j0 += 8) {
@@ -99,9 +139,6 @@ struct IsInt {
 
 #ifndef DAB_V3_MIN_CTAS
 #define DAB_V3_MIN_CTAS 4
-#endif
-#ifndef DAB_V3_LP16
-#define DAB_V3_LP16 1  // visited set: linear-probing 16-bit slots (0: buckets of 16 tags)
 #endif
 #ifndef DAB_V3_P_F32
 #define DAB_V3_P_F32 2  // f32 rows: passes (of 4 rows, 4 x 16-byte loads per lane each) in flight
@@ -364,7 +401,10 @@ __global__ void __launch_bounds__(kV3Warps * 32, DAB_V3_MIN_CTAS) search_kernel_
                 if (p.out_counts) p.out_counts[qidx] = count;
                 if (p.out_cmps) p.out_cmps[qidx] = cmps;
                 if (p.out_hops) p.out_hops[qidx] = hops;
-                if (p.rec_counts) p.rec_counts[qidx] = min(nrec, p.rec_cap);
+                if (p.rec_counts) {
+                    p.rec_counts[qidx] = min(nrec, p.rec_cap);
+                    if (nrec > p.rec_cap) atomicAdd(p.counters + 3, 1u);  // expanded nodes beyond the record: reported by dab_build
+                }
             }
         }
     }

@@ -306,3 +306,11 @@ class GpuIndex:
         dists = np.empty((queries.shape[0], k), np.float32)
         check(_lib.lib().dab_flat_knn(self._h, _ptr(queries), queries.shape[0], k, _ptr(ids), _ptr(dists)))
         return ids, dists
+
+    def flat_knn_tc(self, queries, k):
+        """The exhaustive scan as a tcgen05 GEMM with fused candidate selection + exact re-scoring."""
+        queries = self._queries(queries)
+        ids = np.empty((queries.shape[0], k), np.uint32)
+        dists = np.empty((queries.shape[0], k), np.float32)
+        check(_lib.lib().dab_flat_knn_tc(self._h, _ptr(queries), queries.shape[0], k, _ptr(ids), _ptr(dists)))
+        return ids, dists

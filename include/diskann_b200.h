@@ -253,6 +253,16 @@ int dab_build(dab_index* idx, uint32_t pruned_degree, uint32_t l_build, float al
 int dab_flat_knn(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t* out_ids,
                  float* out_dists);
 
+/* The same scan on the tensor cores (BASELINE.json north_star: "the query x neighbour distance batch is a
+ * tcgen05 tensor-core GEMM ... with TMA-staged vector tiles and fused ||x||^2 + ||y||^2 expansion"):
+ * bf16 operands (f32 / f16 rows as a 3-product hi/lo split, i8 / u8 exact), fp32 accumulation in TMEM,
+ * fused score expansion and per-row candidate selection in the epilogue; the candidates are then
+ * re-scored with the exact reference-order kernel, so out_dists are bit-identical to dab_flat_knn and
+ * out_ids equal it unless approximate scores (~1e-5 relative) displace a true neighbour by more than
+ * the selection slack.  k <= 24. */
+int dab_flat_knn_tc(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t* out_ids,
+                    float* out_dists);
+
 #ifdef __cplusplus
 }
 #endif

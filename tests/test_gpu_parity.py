@@ -473,6 +473,23 @@ def test_device_build_graph_is_valid_and_searchable(dab, dt, metric, dim, n):
     assert rec > 0.95, rec
 
 
+@pytest.mark.parametrize("dt,metric,d,n,R,Lb", [(np.float32, O.L2, 32, 1500, 16, 30), (np.int8, O.L2, 64, 1200, 12, 24),
+                                                (np.float32, O.INNER_PRODUCT, 24, 1000, 8, 20)])
+def test_device_build_one_insert_at_a_time_reproduces_the_sequential_reference_build(dab, dt, metric, d, n, R, Lb):
+    """dab_build with batch_size = 1 is DiskANNIndex::insert for i = 0..n (index.rs:226-341: search with
+    a VisitedSearchRecord, robust_prune, set_neighbors, add_edge_and_prune per out-edge): the adjacency
+    must equal the oracle's sequential build (which the single-insert grid baselines pin) bit for bit."""
+    rng = np.random.default_rng(n + d)
+    vecs, want, maxdeg = make_index(rng, dt, metric, n, d, R, Lb)
+    with dab.GpuIndex(O.dtype_code(vecs), metric, d, n, 1, maxdeg) as g:
+        g.upload_vectors(vecs)
+        g.build(R, Lb, 1.2, batch_size=1)
+        got = g.download_graph()
+    assert np.array_equal(got[:, 0], want[:, 0]), "degrees differ"
+    for i in range(n + 1):
+        assert np.array_equal(got[i, 1:1 + got[i, 0]], want[i, 1:1 + want[i, 0]]), i
+
+
 # ---------------------------------------------------------------- PQ traversal (C4 shape) and C3 shape
 
 @pytest.mark.parametrize("dt,metric,d,chunks", [(np.int8, O.L2, 128, 32), (np.float32, O.L2, 96, 12), (np.float32, O.INNER_PRODUCT, 64, 16),
@@ -559,3 +576,29 @@ def test_search_c3_shape_f16_768_inner_product(dab):
             want = oidx.search_batch(queries, k, Ls, threads=4)
             for a, b in zip(got, want):
                 assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+# ---------------------------------------------------------------- tensor-core exhaustive scan
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("dt,metric,n,d,nq", [(np.float32, O.L2, 20000, 128, 300), (np.float32, O.INNER_PRODUCT, 5000, 96, 129),
+                                               (np.int8, O.L2, 30000, 128, 200), (np.float16, O.INNER_PRODUCT, 9000, 100, 64),
+                                               (np.uint8, O.COSINE, 7000, 40, 50), (np.float32, O.COSINE_NORMALIZED, 3001, 33, 17)])
+def test_tensor_core_flat_scan_equals_the_exact_scan(dab, dt, metric, n, d, nq):
+    """dab_flat_knn_tc (tcgen05 GEMM over bf16 hi/lo splits, fused candidate selection, exact
+    re-scoring) returns the exact scan's ids and bit-identical distances."""
+    rng = np.random.default_rng(n + d)
+    if dt in (np.float32, np.float16):
+        base = clustered(rng, n + 1, d, n_centers=50).astype(dt)
+        queries = clustered(rng, nq, d, n_centers=50).astype(dt)
+        if metric == O.COSINE_NORMALIZED:
+            base = (base / np.linalg.norm(base.astype(np.float32), axis=1, keepdims=True)).astype(dt)
+            queries = (queries / np.linalg.norm(queries.astype(np.float32), axis=1, keepdims=True)).astype(dt)
+    else:
+        base, queries = fuzz(rng, dt, (n + 1, d)), fuzz(rng, dt, (nq, d))
+    with dab.GpuIndex(O.dtype_code(base), metric, d, n, 1, 8) as g:
+        g.upload_vectors(base)
+        want_ids, want_d = g.flat_knn(queries, 10)
+        got_ids, got_d = g.flat_knn_tc(queries, 10)
+    assert np.array_equal(bits(got_d), bits(want_d))
+    assert np.array_equal(got_ids, want_ids)
