@@ -246,73 +246,42 @@ def recall_of(gt_ids, ids, counts):
 # ------------------------------------------------------------------------------------------ index preparation (GPU)
 
 def prepare_index(g, cfg, base, medoid, rank, world, dist, torch, log):
-    """Rank 0: upload, device build (+ PQ training / encoding).  All ranks: receive vectors, adjacency
-    (and PQ tables) by NCCL broadcast into the library's HBM snapshot."""
-    n, dim, md = cfg["n"], cfg["dim"], max_degree(cfg["R"])
+    """Rank 0: upload, device build (+ PQ training / encoding).  Then ONE NCCL broadcast per resident
+    buffer (vectors, adjacency, PQ table + codes) from rank 0, issued inside the library
+    (dab_comm_init / dab_broadcast_index); torch.distributed only ships the 128-byte NCCL id."""
+    n = cfg["n"]
     t = {}
     t0 = time.time()
     if rank == 0:
         g.upload_vectors(base)
         g.upload_vectors(medoid[None, :], first=n)
-    if world > 1:
-        # vectors: chunked broadcast straight into the index (no second full copy in HBM)
-        rows_per = max(1, (256 << 20) // (dim * ELEM[cfg["dtype"]]))
-        tdt = {"f32": torch.float32, "f16": torch.float16, "i8": torch.int8}[cfg["dtype"]]
-        allrows = n + 1
-        buf = torch.empty((rows_per, dim), dtype=tdt, device="cuda")
-        for first in range(0, allrows, rows_per):
-            cnt = min(rows_per, allrows - first)
-            if rank == 0:
-                src = base[first:first + cnt] if first + cnt <= n else np.concatenate([base[first:n], medoid[None, :]])
-                buf[:cnt].copy_(torch.from_numpy(np.ascontiguousarray(src)))
-            dist.broadcast(buf[:cnt], src=0)
-            if rank != 0:
-                torch.cuda.synchronize()
-                g.upload_vectors_device(buf.data_ptr(), cnt, first=first)
-        del buf
     t["upload_s"] = round(time.time() - t0, 2)
     t0 = time.time()
     if rank == 0:
         g.build(cfg["R"], cfg["l_build"], ALPHA)
     t["build_s"] = round(time.time() - t0, 2)
-    adj_host = g.download_graph() if rank == 0 else None
-    if world > 1:
-        rows_per = 1 << 22
-        buf = torch.empty((rows_per, md + 1), dtype=torch.int32, device="cuda")
-        for first in range(0, n + 1, rows_per):
-            cnt = min(rows_per, n + 1 - first)
-            if rank == 0:
-                buf[:cnt].copy_(torch.from_numpy(adj_host[first:first + cnt].view(np.int32)))
-            dist.broadcast(buf[:cnt], src=0)
-            if rank != 0:
-                torch.cuda.synchronize()
-                g.upload_graph_device(buf.data_ptr(), md + 1, cnt, first=first)
-        del buf
-    pq = None
-    if cfg["path"] == "pq":
+    if cfg["path"] == "pq" and rank == 0:
         t0 = time.time()
+        rng = np.random.default_rng(SEED_PQ & 0xFFFFFFFF)
+        sample = np.sort(rng.choice(n, size=min(cfg["pq_train"], n), replace=False))
+        g.pq_train(base[sample].astype(np.float32), cfg["pq_chunks"], 256, 5, SEED_PQ)
+        t["pq_train_s"] = round(time.time() - t0, 2)
+        t0 = time.time()
+        g.pq_encode_all()
+        t["pq_encode_s"] = round(time.time() - t0, 2)
+    if world > 1:
+        t0 = time.time()
+        ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
-            rng = np.random.default_rng(SEED_PQ & 0xFFFFFFFF)
-            sample = np.sort(rng.choice(n, size=min(cfg["pq_train"], n), replace=False))
-            g.pq_train(base[sample].astype(np.float32), cfg["pq_chunks"], 256, 12, SEED_PQ)
-            t["pq_train_s"] = round(time.time() - t0, 2)
-            t0 = time.time()
-            g.pq_encode_all()
-            t["pq_encode_s"] = round(time.time() - t0, 2)
-            pq = g.download_pq()
-        if world > 1:
-            shapes = [(256, dim), (cfg["pq_chunks"] + 1,), (n + 1, cfg["pq_chunks"])]
-            dts = [torch.float32, torch.int64, torch.uint8]
-            bufs = []
-            for i, (shp, dt_) in enumerate(zip(shapes, dts)):
-                b = torch.empty(shp, dtype=dt_, device="cuda")
-                if rank == 0:
-                    b.copy_(torch.from_numpy(pq[i].view(np.int64) if i == 1 else pq[i]))
-                dist.broadcast(b, src=0)
-                bufs.append(b.cpu().numpy())
-            if rank != 0:
-                pq = (bufs[0], bufs[1].view(np.uint64), bufs[2])
-                g.upload_pq(*pq)
+            ident.copy_(torch.frombuffer(bytearray(g.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(ident, src=0)
+        g.comm_init(bytes(ident.cpu().numpy().tobytes()), world, rank)
+        g.broadcast_index(0)
+        if cfg["path"] == "pq":
+            g.pq_chunks, g.pq_centers = cfg["pq_chunks"], 256
+        t["replicate_s"] = round(time.time() - t0, 2)
+    adj_host = g.download_graph() if rank == 0 else None
+    pq = g.download_pq() if (cfg["path"] == "pq" and rank == 0) else None
     return adj_host, pq, t
 
 
@@ -371,7 +340,9 @@ def run_gpu(args):
 
     # ground truth: exhaustive scan on the device (bit-identical distances), cross-checked below
     t0 = time.time()
-    gts = [g.flat_knn(q, K)[0] for q in batches]
+    # (large indexes: the tcgen05 scan — tensor-core candidate selection + exact re-scoring, same answer)
+    flat = g.flat_knn_tc if n >= 2_000_000 else g.flat_knn
+    gts = [flat(q, K)[0] for q in batches]
     t_gt = time.time() - t0
 
     # BASELINE.json names L_search=100; the sweep records the smallest L that already reaches the
@@ -519,7 +490,7 @@ def run_gpu(args):
                          + (", unit-normalised, cast to f16" if cfg.get("normalize") else "")
                          + (f", x{cfg['int_scale']} rounded and clamped to i8" if cfg["dtype"] == "i8" else "")
                          + f"; seeds base {SEED_BASE:#x} queries {SEED_QUERY:#x}+97*batch; start = copy of the medoid",
-            "index": "built on rank 0 by dab_build (device); vectors and adjacency replicated by NCCL broadcast",
+            "index": "built on rank 0 by dab_build (device); vectors, adjacency (and PQ) replicated by one NCCL broadcast each inside the library",
             "parallelism": f"replica x{world}, queries sharded ({args.scaling}), no collective on the search path",
             "l2_policy": f"no flush: index {(n * dim * ELEM[cfg['dtype']] + (n + 1) * 4 * (md + 1)) / 1e6:.0f} MB >> 126 MB L2, "
                          f"{NB} query batches rotate and each step gathers GBs of random rows",
@@ -635,7 +606,8 @@ def prepare_only(args):
     dt, mt = dab_enums(dab, cfg)
     g = dab.GpuIndex(dt, mt, dim, n, 1, md)
     adj, pq, _ = prepare_index(g, cfg, base, medoid, 0, 1, None, None, lambda *a: None)
-    gt_all = [g.flat_knn(make_data(cfg, SEED_QUERY + 97 * b, cfg["nq"], centers), K)[0] for b in range(NB)]
+    flat = g.flat_knn_tc if n >= 2_000_000 else g.flat_knn
+    gt_all = [flat(make_data(cfg, SEED_QUERY + 97 * b, cfg["nq"], centers), K)[0] for b in range(NB)]
     l_search = args.l_search or cfg["l_search"]
     min_l = None
     if not args.l_search:

@@ -42,6 +42,7 @@ SYMBOLS = {
     "dab_pq_populate_lut": (_i, [_vp, _vp, _u32, _i, _vp]),
     "dab_pq_distances": (_i, [_vp, _vp, _u32, _vp, _u32, _vp]),
     "dab_pq_encode": (_i, [_vp, _vp, _u64, _vp]),
+    "dab_pq_self_distances": (_i, [_vp, _vp, _vp, _u64, _vp]),
     "dab_search_batch_pq": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "dab_search_batch_pq_rerank": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "dab_search_batch_pq_device": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _i, _vp, _vp, _vp, _vp, _vp]),

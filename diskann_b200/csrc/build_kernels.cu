@@ -275,6 +275,7 @@ struct BackedgeParams {
     int prune_kind;
     uint32_t* adj;
     uint32_t adj_stride;
+    uint32_t* dropped;      // in-edges that did not fit the per-destination list of a batch
 };
 
 __global__ void make_pairs_kernel(const uint32_t* __restrict__ batch_ids, const uint32_t* __restrict__ nbr_ids,
@@ -289,8 +290,8 @@ __global__ void make_pairs_kernel(const uint32_t* __restrict__ batch_ids, const 
     }
 }
 
-// One warp per destination segment: add_edge_and_prune (index.rs:2264-2341) for each incoming
-// edge in order; on overflow robust_prune_list (index.rs:2397-2454).
+// One warp per destination segment: add_edge_and_prune (index.rs:2264-2341) with all the incoming
+// edges of the batch at once; on overflow robust_prune_list (index.rs:2397-2454).
 template <typename TD, int NA, int KIND, int POST, bool IS_INT, bool SIGNED>
 __global__ void __launch_bounds__(kPruneWarps * 32) backedge_kernel(const BackedgeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -315,6 +316,10 @@ __global__ void __launch_bounds__(kPruneWarps * 32) backedge_kernel(const Backed
             __syncwarp();
             for (uint32_t t = lane; t < deg; t += 32) list[t] = row[1 + t];
             __syncwarp();
+            // add_edge_and_prune(sorted sources, q) (index.rs:2264-2341, called once per target by
+            // multi_insert, index.rs:986-1003): extend_from_slice appends every source that is not yet
+            // in the list (sources arrive in ascending id order: the radix sort is stable and the
+            // pairs are generated in batch order) ...
             bool changed = false;
             for (uint32_t e = start; e < p.n_pairs && p.keys[e] == q; ++e) {
                 const uint32_t src = p.vals[e];
@@ -322,42 +327,47 @@ __global__ void __launch_bounds__(kPruneWarps * 32) backedge_kernel(const Backed
                 bool present = false;
                 for (uint32_t t = lane; t < deg; t += 32) present |= list[t] == src;
                 if (__any_sync(kFull, present)) continue;
+                if (deg >= p.P) {  // more in-edges in one batch than the list holds: counted, reported by dab_build
+                    if (lane == 0) atomicAdd(p.dropped, 1u);
+                    continue;
+                }
                 if (lane == 0) list[deg] = src;
                 ++deg;
                 changed = true;
                 __syncwarp();
-                if (deg > p.max_degree) {
-                    // robust_prune_list: pool = (id, Distance(q, id)) for id in list, id != q
-                    uint32_t n = 0;
-                    for (uint32_t t0 = 0; t0 < deg; t0 += kPairsPerPass) {
-                        uint32_t rows[kPairsPerPass];
+            }
+            // ... and if the extended list no longer fits, robust_prune_list runs ONCE over all of it:
+            // pool = (id, Distance(q, id)) for id in list, id != q (index.rs:2397-2454)
+            if (changed && deg > p.max_degree) {
+                uint32_t n = 0;
+                for (uint32_t t0 = 0; t0 < deg; t0 += kPairsPerPass) {
+                    uint32_t rows[kPairsPerPass];
 #pragma unroll
-                        for (int g = 0; g < kPairsPerPass; ++g) rows[g] = list[min(t0 + g, deg - 1)];
-                        float dist[kPairsPerPass];
-                        warp_row_distances<TD, NA, KIND, POST, IS_INT, SIGNED>(p.vectors, p.row_stride, p.dim, q, rows, lane, dist);
+                    for (int g = 0; g < kPairsPerPass; ++g) rows[g] = list[min(t0 + g, deg - 1)];
+                    float dist[kPairsPerPass];
+                    warp_row_distances<TD, NA, KIND, POST, IS_INT, SIGNED>(p.vectors, p.row_stride, p.dim, q, rows, lane, dist);
 #pragma unroll
-                        for (int g = 0; g < kPairsPerPass; ++g) {
-                            if (t0 + g < deg && rows[g] != q) {
-                                if (lane == 0) {
-                                    s.ids[n] = rows[g];
-                                    s.d[n] = dist[g];
-                                }
-                                ++n;
+                    for (int g = 0; g < kPairsPerPass; ++g) {
+                        if (t0 + g < deg && rows[g] != q) {
+                            if (lane == 0) {
+                                s.ids[n] = rows[g];
+                                s.d[n] = dist[g];
                             }
+                            ++n;
                         }
                     }
-                    __syncwarp();
-                    uint32_t P2 = 2;
-                    while (P2 < n) P2 <<= 1;
-                    warp_sort_pool(s, n, P2, lane);
-                    n = min(n, kMaxOcclusion);
-                    const uint32_t found = warp_robust_prune<TD, NA, KIND, POST, IS_INT, SIGNED>(
-                        s, n, q, p.degree, p.alpha, p.prune_kind, p.vectors, p.row_stride, p.dim, lane);
-                    __syncwarp();
-                    for (uint32_t f = lane; f < found; f += 32) list[f] = s.ids[s.nbr[f]];
-                    deg = found;
-                    __syncwarp();
                 }
+                __syncwarp();
+                uint32_t P2 = 2;
+                while (P2 < n) P2 <<= 1;
+                warp_sort_pool(s, n, P2, lane);
+                n = min(n, kMaxOcclusion);
+                const uint32_t found = warp_robust_prune<TD, NA, KIND, POST, IS_INT, SIGNED>(
+                    s, n, q, p.degree, p.alpha, p.prune_kind, p.vectors, p.row_stride, p.dim, lane);
+                __syncwarp();
+                for (uint32_t f = lane; f < found; f += 32) list[f] = s.ids[s.nbr[f]];
+                deg = found;
+                __syncwarp();
             }
             if (changed) {
                 for (uint32_t t = lane; t < deg; t += 32) row[1 + t] = list[t];
@@ -438,7 +448,8 @@ static int launch_backedges(const dab_index* idx, BackedgeParams& p) {
     p.row_stride = idx->row_stride;
     p.dim = (int)idx->dim;
     p.prune_kind = idx->metric == DAB_INNER_PRODUCT ? 1 : 0;
-    p.P = pow2_at_least(idx->max_degree + 2);
+    // the list of a destination holds its current neighbours plus every in-edge of the batch
+    p.P = std::max<uint32_t>(1024, pow2_at_least(idx->max_degree + 2));
     p.adj = idx->d_adj;
     p.adj_stride = idx->adj_stride;
     p.max_degree = idx->max_degree;
@@ -539,7 +550,7 @@ int dab_build(dab_index* idx, uint32_t pruned_degree, uint32_t l_build, float al
     DAB_CUDA(cudaMemsetAsync(idx->d_adj, 0, idx->n_total() * (size_t)idx->adj_stride * 4, st));
     idx->graph_ready = true;
 
-    DevBuf b_batch, b_rec_ids, b_rec_d, b_rec_n, b_nbr, b_nbr_n, b_keys, b_vals, b_keys2, b_vals2, b_tmp, b_res_ids, b_res_d;
+    DevBuf b_batch, b_rec_ids, b_rec_d, b_rec_n, b_nbr, b_nbr_n, b_keys, b_vals, b_keys2, b_vals2, b_tmp, b_res_ids, b_res_d, b_dropped;
     int rc;
     const size_t B = batch_size;
     if ((rc = b_batch.alloc(B * 4)) || (rc = b_rec_ids.alloc(B * rec_cap * 4)) || (rc = b_rec_d.alloc(B * rec_cap * 4)) ||
@@ -548,6 +559,8 @@ int dab_build(dab_index* idx, uint32_t pruned_degree, uint32_t l_build, float al
         (rc = b_keys2.alloc(B * pruned_degree * 4)) || (rc = b_vals2.alloc(B * pruned_degree * 4)) || (rc = b_res_ids.alloc(B * 4)) ||
         (rc = b_res_d.alloc(B * 4)))
         return rc;
+    if ((rc = b_dropped.alloc(4))) return rc;
+    DAB_CUDA(cudaMemsetAsync(b_dropped.p, 0, 4, st));
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t*)b_keys.p, (uint32_t*)b_keys2.p, (const uint32_t*)b_vals.p,
                                     (uint32_t*)b_vals2.p, (int)(B * pruned_degree), 0, 32, st);
@@ -597,10 +610,16 @@ int dab_build(dab_index* idx, uint32_t pruned_degree, uint32_t l_build, float al
         bp.n_pairs = n_pairs;
         bp.degree = pruned_degree;
         bp.alpha = alpha;
+        bp.dropped = (uint32_t*)b_dropped.p;
         if ((rc = launch_backedges(idx, bp))) return rc;
         inserted += b;
     }
+    uint32_t dropped = 0;
+    DAB_CUDA(cudaMemcpyAsync(&dropped, b_dropped.p, 4, cudaMemcpyDeviceToHost, st));
     DAB_CUDA(cudaStreamSynchronize(st));
+    if (dropped)
+        return fail(DAB_ERR_INVALID_ARGUMENT, "dab_build: %u back-edges exceeded the per-destination list of a batch and were dropped "
+                    "(the graph is usable but not the reference's; use a smaller batch_size)", dropped);
     if (idx->rec_truncated)
         return fail(DAB_ERR_INVALID_ARGUMENT, "dab_build: %llu insert searches expanded more than %u nodes; their prune pools were cut "
                     "(the graph is usable but not the reference's)", (unsigned long long)idx->rec_truncated, rec_cap);

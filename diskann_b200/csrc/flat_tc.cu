@@ -452,7 +452,8 @@ int dab_flat_knn_tc(dab_index* idx, const void* queries, uint32_t nq, uint32_t k
     DAB_LAUNCHED();
     // base ranges: enough CTAs to fill the machine, whole 128-column tiles each
     const uint32_t n_tiles = (uint32_t)((n + kBN - 1) / kBN);
-    uint32_t splits = std::max<uint32_t>(1, std::min<uint32_t>(n_tiles, (uint32_t)(idx->sm_count * 2 + m_tiles - 1) / m_tiles));
+    // (at most 48 ranges: the exact re-scoring handles splits x kKP candidates per query)
+    uint32_t splits = std::max<uint32_t>(1, std::min<uint32_t>(std::min<uint32_t>(n_tiles, 48), (uint32_t)(idx->sm_count * 2 + m_tiles - 1) / m_tiles));
     const uint32_t tiles_per_split = (n_tiles + splits - 1) / splits;
     splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
     const uint32_t c = splits * kKP;

@@ -115,6 +115,60 @@ pq_direct_cosine_kernel(const float* __restrict__ queries, uint32_t nq, const ui
     }
 }
 
+// DistanceComputer (pq/distance/dynamic.rs:101-140, VTable :117-131) over two CODES:
+// FixedChunkPQTable::{qq_l2_distance, qq_inner_product, qq_cosine_distance}
+// (fixed_chunk_pq_table.rs:285-361) = direct_distance_impl (:35-59) with both sides gathered from
+// the pivots: one Resumable accumulator across the chunks (simd.rs:1515-1547, 2240-2272,
+// 3163-3199: the combined 8-lane accumulator of every chunk is added lane-wise), sum_tree at the
+// end.  L2 -> value, InnerProduct -> -value, Cosine / CosineNormalized -> 1 - cos.
+// kind: 0 L2, 1 IP, 2 cosine.  One thread per pair.
+__global__ void __launch_bounds__(128)
+pq_self_distance_kernel(const uint32_t* __restrict__ ids_a, const uint32_t* __restrict__ ids_b, uint64_t n, int kind,
+                        const uint8_t* __restrict__ codes, const float* __restrict__ pivots, const uint32_t* __restrict__ offsets,
+                        uint32_t n_chunks, uint32_t dim, uint64_t n_total, float* __restrict__ out) {
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t ia = ids_a[t], ib = ids_b[t];
+        if (ia >= n_total || ib >= n_total) {
+            out[t] = __int_as_float(0x7FC00000);
+            continue;
+        }
+        const uint8_t* ca = codes + (size_t)ia * n_chunks;
+        const uint8_t* cb = codes + (size_t)ib * n_chunks;
+        float nx[8], ny[8], xy[8];
+#pragma unroll
+        for (int l = 0; l < 8; ++l) nx[l] = ny[l] = xy[l] = 0.0f;
+        for (uint32_t ch = 0; ch < n_chunks; ++ch) {
+            const uint32_t start = offsets[ch], stop = offsets[ch + 1];
+            const float* xc = pivots + (size_t)ca[ch] * dim + start;
+            const float* yc = pivots + (size_t)cb[ch] * dim + start;
+            const int len = (int)(stop - start);
+            float d[8];
+            if (kind == 0) {
+                thread_simd_combined<4, KIND_L2>(xc, yc, len, d);
+            } else if (kind == 1) {
+                thread_simd_combined<4, KIND_IP>(xc, yc, len, d);
+            } else {
+                float a[8], b[8];
+                thread_simd_combined<2, KIND_IP>(xc, xc, len, a);
+                thread_simd_combined<2, KIND_IP>(yc, yc, len, b);
+                thread_simd_combined<2, KIND_IP>(xc, yc, len, d);
+#pragma unroll
+                for (int l = 0; l < 8; ++l) {
+                    nx[l] = __fadd_rn(nx[l], a[l]);
+                    ny[l] = __fadd_rn(ny[l], b[l]);
+                }
+            }
+#pragma unroll
+            for (int l = 0; l < 8; ++l) xy[l] = __fadd_rn(xy[l], d[l]);
+        }
+        float v;
+        if (kind == 0) v = thread_tree8(xy);
+        else if (kind == 1) v = -thread_tree8(xy);
+        else v = __fsub_rn(1.0f, cosine_finish(thread_tree8(nx), thread_tree8(ny), thread_tree8(xy)));
+        out[t] = v;
+    }
+}
+
 // ------------------------------------------------------------------ encode
 // BasicTable::compress_into (product/tables/basic.rs:161-194): one warp per (vector, chunk),
 // lanes stride the pivots, strict `<` so the lowest pivot index among ties wins.
@@ -363,6 +417,30 @@ int dab_pq_encode(dab_index* idx, const float* vectors, uint64_t n, uint8_t* out
     if (bad != ~0ull)
         return fail(DAB_ERR_INVALID_ARGUMENT, "dab_pq_encode: vector %llu chunk %llu is infinitely far from every center (inf/NaN input)",
                     bad / idx->pq_chunks, bad % idx->pq_chunks);
+    return DAB_OK;
+}
+
+int dab_pq_self_distances(dab_index* idx, const uint32_t* ids_a, const uint32_t* ids_b, uint64_t n, float* out) {
+    int rc = require_pq(idx, "dab_pq_self_distances");
+    if (rc) return rc;
+    if (!idx->pq_codes_ready) return fail(DAB_ERR_NOT_READY, "dab_pq_self_distances: no PQ codes (dab_upload_pq with codes, or dab_pq_encode_all)");
+    if (n == 0) return DAB_OK;
+    if (!ids_a || !ids_b || !out) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_pq_self_distances: NULL argument");
+    DAB_CUDA(cudaSetDevice(idx->device));
+    if ((rc = idx->s_ids.reserve(n * 8))) return rc;
+    if ((rc = idx->s_out.reserve(n * 4))) return rc;
+    uint32_t* d_a = (uint32_t*)idx->s_ids.p;
+    uint32_t* d_b = d_a + n;
+    DAB_CUDA(cudaMemcpyAsync(d_a, ids_a, n * 4, cudaMemcpyHostToDevice, idx->stream));
+    DAB_CUDA(cudaMemcpyAsync(d_b, ids_b, n * 4, cudaMemcpyHostToDevice, idx->stream));
+    const int kind = idx->metric == DAB_L2 ? 0 : idx->metric == DAB_INNER_PRODUCT ? 1 : 2;  // VTable, dynamic.rs:117-131
+    const int grid = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)idx->sm_count * 16);
+    pq_self_distance_kernel<<<grid, 128, 0, idx->stream>>>(d_a, d_b, n, kind, idx->d_codes, idx->d_pivots, idx->d_offsets, idx->pq_chunks, idx->dim,
+                                                          idx->n_total(), (float*)idx->s_out.p);
+    DAB_LAUNCHED();
+    DAB_CUDA(cudaGetLastError());
+    DAB_CUDA(cudaMemcpyAsync(out, idx->s_out.p, n * 4, cudaMemcpyDeviceToHost, idx->stream));
+    DAB_CUDA(cudaStreamSynchronize(idx->stream));
     return DAB_OK;
 }
 

@@ -129,8 +129,12 @@ __device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterp
 // All candidate rows of a hop are requested from HBM at once with one bulk L2 prefetch per row
 // (no registers, no shared memory); the register passes below then overlap with the fills and
 // find all but the first rows in L2.
+#ifndef DAB_V3_PREFETCH
+#define DAB_V3_PREFETCH 1  // 0: no bulk L2 prefetch of the candidate rows (tuning)
+#endif
 __device__ __forceinline__ void prefetch_rows(const uint8_t* __restrict__ vectors, size_t row_stride, const uint32_t* __restrict__ cid,
                                               uint32_t n, uint32_t row_bytes16, int lane) {
+    if (!DAB_V3_PREFETCH) return;
     for (uint32_t j = lane; j < n; j += 32) {
         const uint8_t* src = vectors + (size_t)cid[j] * row_stride;
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(row_bytes16) : "memory");

@@ -275,6 +275,16 @@ class GpuIndex:
                                                     C.c_void_p(d_ids), C.c_void_p(d_dists), C.c_void_p(d_counts or None),
                                                     C.c_void_p(d_cmps or None), C.c_void_p(d_hops or None)))
 
+    def pq_self_distances(self, a, b):
+        """DistanceComputer over two stored codes (the PQ prune path): out[i] = d(code[a[i]], code[b[i]])."""
+        a = np.ascontiguousarray(a, np.uint32)
+        b = np.ascontiguousarray(b, np.uint32)
+        if a.shape != b.shape or a.ndim != 1:
+            raise DabError(1, "a and b must be 1-d u32 arrays of equal length")
+        out = np.empty(a.shape[0], np.float32)
+        check(_lib.lib().dab_pq_self_distances(self._h, _ptr(a), _ptr(b), a.shape[0], _ptr(out)))
+        return out
+
     def pq_encode(self, vectors):
         vectors = np.ascontiguousarray(vectors, np.float32)
         out = np.empty((vectors.shape[0], self.pq_chunks), np.uint8)

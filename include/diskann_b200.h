@@ -181,6 +181,12 @@ int dab_pq_populate_lut(dab_index* idx, const float* queries, uint32_t nq, int m
 int dab_pq_distances(dab_index* idx, const float* queries, uint32_t nq, const uint32_t* ids,
                      uint32_t c, float* out);
 
+/* DistanceComputer::evaluate_similarity(code, code) (pq/distance/dynamic.rs:101-140; the PQ prune path):
+ * FixedChunkPQTable::{qq_l2_distance, qq_inner_product, qq_cosine_distance}
+ * (fixed_chunk_pq_table.rs:285-361) between the stored codes of rows a[i] and b[i] under the index
+ * metric (CosineNormalized -> cosine, VTable dynamic.rs:126-131).  Resumable accumulation across chunks. */
+int dab_pq_self_distances(dab_index* idx, const uint32_t* ids_a, const uint32_t* ids_b, uint64_t n, float* out);
+
 /* The providers' PQ traversal: QuantAccessor::expand_beam with
  * `computer.evaluate_similarity(aux_vectors[i])`
  * (diskann-providers/src/model/graph/provider/async_/inmem/product.rs:311-340) inside

@@ -635,6 +635,100 @@ void orc_build(int dtype, int metric, uint32_t dim, uint64_t n_points, uint32_t 
     }
 }
 
+// DiskANNIndex::multi_insert (index.rs:815-1050) with intra_batch_candidates = None and the bootstrap
+// branch not taken (it is meant for the first batches of ~128 items and costs O(batch^2) distances;
+// the device build grows its batches instead, see orc_build_batch_size), one batch at a time:
+//   * candidate generation (search_and_prune, index.rs:341-430): every item is searched against the
+//     graph AS IT WAS BEFORE THE BATCH with a VisitedSearchRecord and pruned (robust_prune_with without
+//     extras); nothing is written yet;
+//   * aggregate_backedges (index.rs:123-143): target -> sources, sources sorted (index.rs:986-992);
+//   * set_neighbors_bulk of the new out-lists;
+//   * add_edge_and_prune(sorted sources, target) (index.rs:2264-2341): ALL new sources are appended
+//     (extend_from_slice skips the ones already present); if the list still fits max_degree it is
+//     kept, otherwise robust_prune_list runs ONCE over the whole extended list.
+// Batch size 1 is exactly DiskANNIndex::insert, i.e. orc_build.
+uint32_t orc_build_batch_size(uint32_t batch_size, uint64_t n_points, uint64_t inserted) {
+    if (batch_size == 0) batch_size = (uint32_t)std::max<uint64_t>(1024, std::min<uint64_t>(65536, n_points / 16));
+    // batches grow with the graph so that early points are not all inserted blind
+    uint64_t b = std::min<uint64_t>(batch_size, std::max<uint64_t>(1, inserted / 8));
+    return (uint32_t)std::min<uint64_t>(b, n_points - inserted);
+}
+
+void orc_build_batched(int dtype, int metric, uint32_t dim, uint64_t n_points, uint32_t n_start,
+                       const void* vectors, uint64_t row_stride, uint32_t pruned_degree,
+                       uint32_t max_degree, uint32_t l_build, float alpha, uint32_t batch_size,
+                       uint32_t* adj, uint32_t adj_stride) {
+    orc_index idx;
+    std::memset(&idx, 0, sizeof(idx));
+    idx.dtype = dtype;
+    idx.metric = metric;
+    idx.dim = dim;
+    idx.n_points = n_points;
+    idx.n_start = n_start;
+    idx.vectors = vectors;
+    idx.row_stride = row_stride;
+    idx.adj = adj;
+    idx.adj_stride = adj_stride;
+    const int flavour = ORC_FLAVOUR_AVX2;
+    auto row = [&](uint32_t id) { return adj + (size_t)id * adj_stride; };
+    std::vector<Visit> record, pool;
+    std::vector<uint32_t> pruned, list;
+    std::vector<std::vector<uint32_t>> edges;
+    std::vector<std::pair<uint32_t, uint32_t>> back;  // (target, source)
+    uint64_t inserted = 0;
+    while (inserted < n_points) {
+        const uint32_t b = orc_build_batch_size(batch_size, n_points, inserted);
+        edges.assign(b, {});
+        for (uint32_t i = 0; i < b; ++i) {
+            const uint32_t id = (uint32_t)(inserted + i);
+            const void* vec = (const char*)vectors + (size_t)id * row_stride;
+            QueryDist qd(&idx, vec, flavour);
+            Queue best((size_t)l_build + n_start);
+            uint32_t cmps = 0, hops = 0;
+            record.clear();
+            search_internal(&idx, qd, l_build, 1, best, &cmps, &hops, &record);
+            sort_pool(record, MAX_OCCLUSION);
+            occlude_list(&idx, record, id, pruned_degree, alpha, flavour, edges[i]);
+        }
+        back.clear();
+        for (uint32_t i = 0; i < b; ++i)
+            for (uint32_t t : edges[i]) back.emplace_back(t, (uint32_t)(inserted + i));
+        std::sort(back.begin(), back.end());
+        for (uint32_t i = 0; i < b; ++i) {
+            uint32_t* r = row((uint32_t)(inserted + i));
+            r[0] = (uint32_t)edges[i].size();
+            for (size_t j = 0; j < edges[i].size(); ++j) r[1 + j] = edges[i][j];
+        }
+        for (size_t e = 0; e < back.size();) {
+            const uint32_t target = back[e].first;
+            uint32_t* r = row(target);
+            list.assign(r + 1, r + 1 + r[0]);
+            size_t added = 0;
+            for (; e < back.size() && back[e].first == target; ++e) {
+                const uint32_t src = back[e].second;
+                if (std::find(list.begin(), list.end(), src) == list.end()) {
+                    list.push_back(src);
+                    ++added;
+                }
+            }
+            if (added == 0) continue;
+            if (list.size() <= max_degree) {
+                r[0] = (uint32_t)list.size();
+                for (size_t j = 0; j < list.size(); ++j) r[1 + j] = list[j];
+                continue;
+            }
+            pool.clear();
+            for (uint32_t other : list)
+                if (other != target) pool.push_back(Visit{other, pair_distance(&idx, flavour, target, other)});
+            sort_pool(pool, MAX_OCCLUSION);
+            occlude_list(&idx, pool, target, pruned_degree, alpha, flavour, pruned);
+            r[0] = (uint32_t)pruned.size();
+            for (size_t j = 0; j < pruned.size(); ++j) r[1 + j] = pruned[j];
+        }
+        inserted += b;
+    }
+}
+
 void orc_set_pool_tie_mode(int mode) { g_pool_tie_mode = mode; }
 
 void orc_last_build_counts(uint64_t* set_neighbors, uint64_t* append_neighbors) {

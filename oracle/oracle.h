@@ -170,6 +170,14 @@ void orc_build(int dtype, int metric, uint32_t dim, uint64_t n_points, uint32_t 
                const void* vectors, uint64_t row_stride, uint32_t pruned_degree,
                uint32_t max_degree, uint32_t l_build, float alpha, uint32_t* adj,
                uint32_t adj_stride);
+/* DiskANNIndex::multi_insert (index.rs:815-1050; intra_batch_candidates = None, bootstrap branch not
+ * taken) over consecutive id ranges whose sizes follow orc_build_batch_size — the schedule of the
+ * device build (batch_size 0: its default).  batch_size 1 == orc_build. */
+uint32_t orc_build_batch_size(uint32_t batch_size, uint64_t n_points, uint64_t inserted);
+void orc_build_batched(int dtype, int metric, uint32_t dim, uint64_t n_points, uint32_t n_start,
+                       const void* vectors, uint64_t row_stride, uint32_t pruned_degree,
+                       uint32_t max_degree, uint32_t l_build, float alpha, uint32_t batch_size,
+                       uint32_t* adj, uint32_t adj_stride);
 /* adjacency writes of the last orc_build: full-list writes and single-edge appends (what the
  * reference's test provider counts as set_neighbors / append_neighbors in the grid_insert baselines) */
 void orc_last_build_counts(uint64_t* set_neighbors, uint64_t* append_neighbors);

@@ -92,6 +92,8 @@ def lib():
     L.orc_robust_prune.argtypes = [C.POINTER(OrcIndex), vp, vp, vp, u32, u32, f, i, vp, vp]
     L.orc_build.restype = None
     L.orc_build.argtypes = [i, i, u32, u64, u32, vp, u64, u32, u32, u32, f, vp, u32]
+    L.orc_build_batched.restype = None
+    L.orc_build_batched.argtypes = [i, i, u32, u64, u32, vp, u64, u32, u32, u32, f, u32, vp, u32]
     L.orc_set_pool_tie_mode.restype = None
     L.orc_set_pool_tie_mode.argtypes = [i]
     L.orc_last_build_counts.restype = None
@@ -226,6 +228,16 @@ def build_graph(vectors, n_points, n_start, metric, pruned_degree, max_degree, l
     lib().orc_build(dtype_code(vectors), metric, vectors.shape[1], n_points, n_start, ptr(vectors),
                     vectors.strides[0], pruned_degree, max_degree, l_build, alpha, ptr(adj), stride)
     lib().orc_set_pool_tie_mode(0)
+    return adj
+
+
+def build_graph_batched(vectors, n_points, n_start, metric, pruned_degree, max_degree, l_build, alpha=1.2, batch_size=0):
+    """DiskANNIndex::multi_insert over the device build's batch schedule (batch_size 1 == build_graph)."""
+    vectors = np.ascontiguousarray(vectors)
+    stride = max_degree + 1
+    adj = np.zeros((n_points + n_start, stride), np.uint32)
+    lib().orc_build_batched(dtype_code(vectors), metric, vectors.shape[1], n_points, n_start, ptr(vectors),
+                            vectors.strides[0], pruned_degree, max_degree, l_build, alpha, batch_size, ptr(adj), stride)
     return adj
 
 

@@ -320,6 +320,13 @@ def test_pq_lut_adc_encode_bit_exact(dab, metric, dim, chunks):
             L.orc_pq_query_distances(O.ptr(piv), 256, dim, O.ptr(off), chunks, metric, O.ptr(queries[qi]), O.ptr(sel), c, O.ptr(want))
             assert same_bits(got[qi][valid], want[valid]), qi
             assert np.isnan(got[qi][~valid]).all()
+        # DistanceComputer (code x code, the PQ prune path): Resumable L2 / IP / cosine across chunks
+        a = rng.integers(0, n + 1, 300).astype(np.uint32)
+        b2 = rng.integers(0, n + 1, 300).astype(np.uint32)
+        got_self = g.pq_self_distances(a, b2)
+        want_self = np.array([L.orc_pq_self_distance(O.ptr(piv), dim, O.ptr(off), chunks, metric, O.ptr(codes[i]), O.ptr(codes[j]))
+                              for i, j in zip(a, b2)], np.float32)
+        assert same_bits(got_self, want_self)
         # inf input -> error naming the row/chunk (basic.rs:187-189)
         bad = base[:3].copy()
         bad[1, 0] = np.inf
@@ -484,6 +491,32 @@ def test_device_build_one_insert_at_a_time_reproduces_the_sequential_reference_b
     with dab.GpuIndex(O.dtype_code(vecs), metric, d, n, 1, maxdeg) as g:
         g.upload_vectors(vecs)
         g.build(R, Lb, 1.2, batch_size=1)
+        got = g.download_graph()
+    assert np.array_equal(got[:, 0], want[:, 0]), "degrees differ"
+    for i in range(n + 1):
+        assert np.array_equal(got[i, 1:1 + got[i, 0]], want[i, 1:1 + want[i, 0]]), i
+
+
+@pytest.mark.parametrize("dt,metric,d,n,R,Lb,bs", [(np.float32, O.L2, 32, 4000, 16, 30, 64), (np.float32, O.L2, 48, 6000, 16, 32, 0),
+                                                   (np.int8, O.L2, 64, 3000, 12, 24, 100), (np.float16, O.INNER_PRODUCT, 32, 2500, 12, 24, 50)])
+def test_device_batched_build_is_the_reference_multi_insert(dab, dt, metric, d, n, R, Lb, bs):
+    """dab_build == DiskANNIndex::multi_insert (index.rs:815-1050; intra_batch_candidates = None, bootstrap
+    branch not taken) over the same batch schedule: candidate generation against the graph as it was
+    before the batch, aggregated and sorted back-edges, one add_edge_and_prune per target — the
+    adjacency equals the oracle's restatement bit for bit."""
+    rng = np.random.default_rng(n + d + bs)
+    base = clustered(rng, n, d)
+    if dt == np.float16:
+        base = (base / np.linalg.norm(base, axis=1, keepdims=True)).astype(np.float16)
+    elif dt == np.int8:
+        base = np.clip(np.round(base * 40), -127, 127).astype(np.int8)
+    mean = base.astype(np.float32).mean(0)
+    vecs = np.concatenate([base, base[np.argmin(((base.astype(np.float32) - mean) ** 2).sum(1))][None]])
+    maxdeg = int(R * 1.3)
+    want = O.build_graph_batched(vecs, n, 1, metric, R, maxdeg, Lb, batch_size=bs)
+    with dab.GpuIndex(O.dtype_code(vecs), metric, d, n, 1, maxdeg) as g:
+        g.upload_vectors(vecs)
+        g.build(R, Lb, 1.2, batch_size=bs)
         got = g.download_graph()
     assert np.array_equal(got[:, 0], want[:, 0]), "degrees differ"
     for i in range(n + 1):
