@@ -311,7 +311,9 @@ def run_gpu(args):
     md = max_degree(R)
     strong = args.scaling == "strong"
     nq_total = cfg["nq"] if strong else cfg["nq"] * world
-    bounds = [nq_total * r // world for r in range(world + 1)]  # PartitionIter: contiguous ranges
+    from diskann_b200.sharding import partition, max_over_ranks
+    lo_hi = partition(nq_total, world)  # PartitionIter (benchmark-core/src/search/api.rs:410-419): contiguous ranges
+    bounds = [lo for lo, _ in lo_hi] + [lo_hi[-1][1]]
     nq = bounds[rank + 1] - bounds[rank]
     log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
 
@@ -415,9 +417,7 @@ def run_gpu(args):
         ms = e0.elapsed_time(e1)
         if world > 1:
             dist.barrier()
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            ms = max_over_ranks(ms, device="cuda")
         return ms
 
     sampler = ClockSampler(local)

@@ -65,13 +65,14 @@ __device__ __forceinline__ float update_occlude(int kind, float d_ik, float d_jk
 // Bitonic sort of the first n (padded to pow2 P2 <= P) entries by (distance, arrival order):
 // SortedNeighbors::new (graph/internal/sorted_neighbors.rs:26-44); ties are unspecified in the
 // reference (unstable sort), this kernel breaks them by arrival order (as do the parity tests).
-__device__ __forceinline__ void warp_sort_pool(PruneSmem s, uint32_t n, uint32_t P2, int lane) {
+__device__ __forceinline__ void warp_sort_pool(PruneSmem s, uint32_t n, uint32_t P2, int lane, bool preset_order = false) {
     for (uint32_t i = n + lane; i < P2; i += 32) {
         s.d[i] = __int_as_float(0x7F800000);
         s.ids[i] = kNoId;
         s.order[i] = 0xFFFFFFFFu;
     }
-    for (uint32_t i = lane; i < n; i += 32) s.order[i] = i;
+    if (!preset_order)
+        for (uint32_t i = lane; i < n; i += 32) s.order[i] = i;
     __syncwarp();
     for (uint32_t k = 2; k <= P2; k <<= 1) {
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
@@ -319,48 +320,84 @@ __global__ void __launch_bounds__(kPruneWarps * 32) backedge_kernel(const Backed
             // add_edge_and_prune(sorted sources, q) (index.rs:2264-2341, called once per target by
             // multi_insert, index.rs:986-1003): extend_from_slice appends every source that is not yet
             // in the list (sources arrive in ascending id order: the radix sort is stable and the
-            // pairs are generated in batch order) ...
-            bool changed = false;
+            // pairs are generated in batch order); if the extended list still fits it is kept,
+            // otherwise robust_prune_list (index.rs:2397-2454) runs ONCE over all of it: pool =
+            // (id, Distance(q, id)) for id in list, id != q, sorted by distance and cut to the 750
+            // closest (SortedNeighbors::new).  A hub can receive thousands of in-edges from one large
+            // batch, so the pool is streamed: whenever its P slots are full it is sorted by
+            // (distance, arrival index) and cut to 750 — the same 750 a single sort would keep.
+            const uint32_t deg0 = deg;
+            uint32_t n_new = 0;
             for (uint32_t e = start; e < p.n_pairs && p.keys[e] == q; ++e) {
                 const uint32_t src = p.vals[e];
                 if (src == q) continue;
                 bool present = false;
-                for (uint32_t t = lane; t < deg; t += 32) present |= list[t] == src;
-                if (__any_sync(kFull, present)) continue;
-                if (deg >= p.P) {  // more in-edges in one batch than the list holds: counted, reported by dab_build
-                    if (lane == 0) atomicAdd(p.dropped, 1u);
-                    continue;
-                }
-                if (lane == 0) list[deg] = src;
-                ++deg;
-                changed = true;
-                __syncwarp();
+                for (uint32_t t = lane; t < deg0; t += 32) present |= list[t] == src;
+                if (!__any_sync(kFull, present)) ++n_new;
             }
-            // ... and if the extended list no longer fits, robust_prune_list runs ONCE over all of it:
-            // pool = (id, Distance(q, id)) for id in list, id != q (index.rs:2397-2454)
-            if (changed && deg > p.max_degree) {
-                uint32_t n = 0;
-                for (uint32_t t0 = 0; t0 < deg; t0 += kPairsPerPass) {
+            if (n_new == 0) continue;
+            bool changed = true;
+            if (deg0 + n_new <= p.max_degree) {
+                for (uint32_t e = start; e < p.n_pairs && p.keys[e] == q; ++e) {
+                    const uint32_t src = p.vals[e];
+                    if (src == q) continue;
+                    bool present = false;
+                    for (uint32_t t = lane; t < deg0; t += 32) present |= list[t] == src;
+                    if (__any_sync(kFull, present)) continue;
+                    if (lane == 0) list[deg] = src;
+                    ++deg;
+                    __syncwarp();
+                }
+            } else {
+                uint32_t n = 0, arrival = 0;
+                uint32_t pend[kPairsPerPass];
+                int npend = 0;
+                auto flush = [&]() {  // distances of the pending ids, appended to the pool in order
+                    if (npend == 0) return;
                     uint32_t rows[kPairsPerPass];
 #pragma unroll
-                    for (int g = 0; g < kPairsPerPass; ++g) rows[g] = list[min(t0 + g, deg - 1)];
+                    for (int g = 0; g < kPairsPerPass; ++g) rows[g] = pend[g < npend ? g : npend - 1];
                     float dist[kPairsPerPass];
                     warp_row_distances<TD, NA, KIND, POST, IS_INT, SIGNED>(p.vectors, p.row_stride, p.dim, q, rows, lane, dist);
 #pragma unroll
                     for (int g = 0; g < kPairsPerPass; ++g) {
-                        if (t0 + g < deg && rows[g] != q) {
+                        if (g < npend) {
+                            if (n == p.P) {
+                                __syncwarp();
+                                warp_sort_pool(s, n, p.P, lane, true);
+                                n = kMaxOcclusion;
+                            }
                             if (lane == 0) {
                                 s.ids[n] = rows[g];
                                 s.d[n] = dist[g];
+                                s.order[n] = arrival;
                             }
                             ++n;
+                            ++arrival;
                         }
                     }
+                    npend = 0;
+                    __syncwarp();
+                };
+                for (uint32_t t = 0; t < deg0; ++t) {
+                    const uint32_t id = list[t];
+                    if (id == q) continue;
+                    pend[npend++] = id;
+                    if (npend == kPairsPerPass) flush();
                 }
-                __syncwarp();
+                for (uint32_t e = start; e < p.n_pairs && p.keys[e] == q; ++e) {
+                    const uint32_t src = p.vals[e];
+                    if (src == q) continue;
+                    bool present = false;
+                    for (uint32_t t = lane; t < deg0; t += 32) present |= list[t] == src;
+                    if (__any_sync(kFull, present)) continue;
+                    pend[npend++] = src;
+                    if (npend == kPairsPerPass) flush();
+                }
+                flush();
                 uint32_t P2 = 2;
                 while (P2 < n) P2 <<= 1;
-                warp_sort_pool(s, n, P2, lane);
+                warp_sort_pool(s, n, P2, lane, true);
                 n = min(n, kMaxOcclusion);
                 const uint32_t found = warp_robust_prune<TD, NA, KIND, POST, IS_INT, SIGNED>(
                     s, n, q, p.degree, p.alpha, p.prune_kind, p.vectors, p.row_stride, p.dim, lane);

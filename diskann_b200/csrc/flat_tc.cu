@@ -37,7 +37,7 @@ int launch_frontier(const dab_index* idx, const void* d_queries, uint32_t nq, co
 namespace {
 
 constexpr int kBM = 128, kBN = 128, kBK = 64;  // CTA tile; one k-block = 64 bf16 = one 128-byte swizzle row
-constexpr int kStages = 6;
+constexpr int kStages = 5;
 constexpr int kTcThreads = 192;                // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-5: epilogue
 constexpr int kKP = 32;                        // candidates kept per (query row, base range)
 constexpr uint32_t kTileBytes = kBM * kBK * 2; // 16 KB per operand tile
@@ -177,7 +177,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t* sa = smem;                              // kStages x 16 KB
     uint8_t* sb = smem + kStages * kTileBytes;       // kStages x 16 KB
     float* s_coef = reinterpret_cast<float*>(smem + 2 * kStages * kTileBytes);  // [2 accumulators][alpha 128 | beta 128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_coef + 2 * 2 * kBN);
+    float* s_scores = s_coef + 2 * 2 * kBN;                                      // [128 epilogue threads][33]: private scratch rows
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_scores + 128 * 33);  // 16896 bytes: stays 8-byte aligned
     uint64_t* full = bars;                  // [kStages] TMA -> MMA
     uint64_t* empty = bars + kStages;       // [kStages] MMA -> TMA
     uint64_t* tfull = bars + 2 * kStages;   // [2] MMA -> epilogue
@@ -264,6 +265,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t row = quarter * 32 + lane;  // row of the 128-row tile == TMEM lane
         const uint32_t q = m0 + row;
         const int et = (warp - 2) * 32 + lane;     // 0..127 among the epilogue threads
+        float* my_scores = s_scores + et * 33;      // stride 33: conflict-free rows
         float cd[kKP];
         uint32_t ci[kKP];
         uint32_t cn = 0;
@@ -286,30 +288,36 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int c0 = 0; c0 < kBN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(taddr + c0, r);
+                // fast path, branch-free: the 32 scores go to this thread's scratch row and a bit mask
+                // marks the ones that beat the current threshold (all of them while the set fills)
+                uint32_t mask = 0;
+                const float thr = cn < (uint32_t)kKP ? __int_as_float(0x7F800000) : worst;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float s = fmaf(__uint_as_float(r[j]), coef[c0 + j], coef[kBN + c0 + j]);
+                    const float sc = fmaf(__uint_as_float(r[j]), coef[c0 + j], coef[kBN + c0 + j]);
+                    my_scores[j] = sc;
+                    mask |= sc < thr ? (1u << j) : 0u;
+                }
+                // slow path (rare once the threshold has settled): one candidate at a time
+                while (mask) {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float sc = my_scores[j];
                     const uint32_t id = t * kBN + c0 + j;
-                    if (cn < kKP) {
-                        if (s < __int_as_float(0x7F800000)) {  // +inf marks columns beyond the base
-                            cd[cn] = s;
-                            ci[cn] = id;
-                            ++cn;
-                            if (cn == kKP) {
-                                worst = cd[0];
-                                worst_at = 0;
-                                for (int e = 1; e < kKP; ++e)
-                                    if (cd[e] > worst) worst = cd[e], worst_at = e;
-                            }
-                        }
-                    } else if (s < worst) {
-                        cd[worst_at] = s;
+                    if (cn < (uint32_t)kKP) {
+                        cd[cn] = sc;
+                        ci[cn] = id;
+                        if (++cn < (uint32_t)kKP) continue;
+                    } else if (sc < worst) {
+                        cd[worst_at] = sc;
                         ci[worst_at] = id;
-                        worst = cd[0];
-                        worst_at = 0;
-                        for (int e = 1; e < kKP; ++e)
-                            if (cd[e] > worst) worst = cd[e], worst_at = e;
+                    } else {
+                        continue;
                     }
+                    worst = cd[0];
+                    worst_at = 0;
+                    for (int e = 1; e < kKP; ++e)
+                        if (cd[e] > worst) worst = cd[e], worst_at = e;
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -472,7 +480,7 @@ int dab_flat_knn_tc(dab_index* idx, const void* queries, uint32_t nq, uint32_t k
     p.alpha = (const float*)idx->d_tc_coef;
     p.beta = (const float*)idx->d_tc_coef + n;
     p.cand = (uint32_t*)idx->s_ids.p;
-    const size_t smem = 1024 + 2 * (size_t)kStages * kTileBytes + 2 * 2 * kBN * 4 + (2 * kStages + 4) * 8 + 16;
+    const size_t smem = 1024 + 2 * (size_t)kStages * kTileBytes + 2 * 2 * kBN * 4 + 128 * 33 * 4 + (2 * kStages + 4) * 8 + 16;
     DAB_CUDA(cudaFuncSetAttribute(flat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     flat_tc_kernel<<<dim3(splits, m_tiles), kTcThreads, smem, st>>>(map_a, map_b, p);
     DAB_LAUNCHED();

@@ -129,7 +129,9 @@ __device__ __forceinline__ void store_empty_bucket(uint32_t* bp) {
 // One probe = one 32 B sector: returns true when `id` was newly inserted (HashSet::insert).
 // `s` holds the bucket's words as loaded by load_bucket(table + b * 8).
 __device__ __forceinline__ bool bucket_insert(uint32_t* table, uint32_t n_buckets, uint32_t b, uint32_t (&s)[8], uint32_t id) {
-    for (;;) {
+    // (the callers stop inserting at 87.5 % load, so a free slot always exists; the probe bound only
+    // guarantees that a completely full table can never hang the device)
+    for (uint32_t advanced = 0;;) {
         bool found = false;
         int empty = -1;
 #pragma unroll
@@ -145,6 +147,7 @@ __device__ __forceinline__ bool bucket_insert(uint32_t* table, uint32_t n_bucket
             if (old == id) return false;
             // another lane of this warp took the slot: re-read the bucket
         } else {
+            if (++advanced > n_buckets) return false;
             b = b + 1 == n_buckets ? 0 : b + 1;
             bp = table + (size_t)b * 8;
         }
@@ -152,9 +155,8 @@ __device__ __forceinline__ bool bucket_insert(uint32_t* table, uint32_t n_bucket
     }
 }
 
-// ---- experiment (DAB_V2_TAG16_BUILD, off by default): 16-bit quotient tags ---------------------
-// Halves the table footprint (the measured problem: 62 MB of tables do not stay in L2, 30 MB do,
-// profiles/r01_table_footprint.md) without giving up exactness.  Ids < 2^K are hashed with an odd
+// ---- 16-bit quotient tags (the shared-memory visited tables of search_kernel_v3, search_smem.cuh) ----
+// A table of 16-bit entries holds twice the ids per byte without giving up exactness.  Ids < 2^K are hashed with an odd
 // multiplier modulo 2^K (a bijection), h = tag * n_buckets + bucket, so (bucket, tag) identifies
 // the id and only the tag (< 2^K / n_buckets + 1 <= 2^14) is stored: 16 entries per 32-byte
 // bucket.  An entry displaced to the d-th following bucket (d <= 2) carries d in its top two
@@ -170,52 +172,6 @@ __device__ __forceinline__ void tag16_of(uint32_t id, const Tag16Map& m, uint32_
     const uint32_t h = (id * 0x9E3779B1u) & m.kmask;
     tag = (uint32_t)(((uint64_t)h * m.magic) >> m.shift);  // h / nbk
     bucket = h - tag * m.nbk;                              // h % nbk
-}
-
-// true when the tag was newly inserted; `ovf` is raised when three buckets in a row are full
-__device__ __forceinline__ bool bucket16_insert(uint32_t* table, uint32_t n_buckets, uint32_t b, uint32_t (&s)[8], uint32_t tag, bool& ovf) {
-    uint32_t d = 0;
-    for (;;) {
-        const uint32_t want = (d << 14) | tag, want2 = want * 0x10001u;
-        // "some 16-bit half of v is zero" <=> ((v - 0x00010001) & ~v & 0x80008000) != 0 (exact as
-        // a boolean; a borrow can only mis-flag the high half when the low half is itself zero)
-        uint32_t hit = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t x = s[k] ^ want2;
-            hit |= (x - 0x00010001u) & ~x & 0x80008000u;
-        }
-        const bool found = hit != 0;
-        int ew = -1;
-        uint32_t ehalf = 0;
-        if (!found) {
-#pragma unroll
-            for (int k = 7; k >= 0; --k) {
-                const uint32_t y = ~s[k];  // an empty entry (0xFFFF) is a zero half of ~s
-                if ((y - 0x00010001u) & s[k] & 0x80008000u) {
-                    ew = k;
-                    ehalf = (s[k] & 0xFFFFu) == 0xFFFFu ? 0u : 1u;
-                }
-            }
-        }
-        if (found) return false;
-        uint32_t* bp = table + (size_t)b * 8;
-        if (ew >= 0) {
-            unsigned short* slot = reinterpret_cast<unsigned short*>(bp + ew) + ehalf;
-            const unsigned short old = atomicCAS(slot, (unsigned short)0xFFFFu, (unsigned short)want);
-            if (old == 0xFFFFu) return true;
-            if (old == want) return false;
-            // another lane of this warp took the slot: re-read the bucket
-        } else {
-            if (++d > 2) {
-                ovf = true;
-                return false;
-            }
-            b = b + 1 == n_buckets ? 0 : b + 1;
-            bp = table + (size_t)b * 8;
-        }
-        load_bucket(bp, s);
-    }
 }
 
 }  // namespace dab

@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t hash_id(uint32_t id, uint32_t log2cap) {
 __device__ __forceinline__ bool visited_insert(uint32_t* table, uint32_t log2cap, uint32_t id) {
     const uint32_t mask = (1u << log2cap) - 1u;
     uint32_t h = hash_id(id, log2cap);
-    for (;;) {
+    for (uint32_t probes = 0; probes <= mask; ++probes) {  // bounded: a full table can never hang the device
         // plain L2 read first (L1 bypassed: the table is updated by L2 atomics): most probes hit
         // an id that is already present and must not dirty the sector
         uint32_t old = __ldcg(table + h);
@@ -84,6 +84,7 @@ __device__ __forceinline__ bool visited_insert(uint32_t* table, uint32_t log2cap
         if (old == id) return false;
         h = (h + 1) & mask;
     }
+    return false;
 }
 
 // NeighborPriorityQueue::insert, queue.rs:130-171 (warp-uniform arguments)
@@ -255,7 +256,10 @@ __global__ void __launch_bounds__(kSearchWarps * 32) search_kernel(const SearchP
                     ncand += __popc(mn);
                     nvisited += __popc(mi);
                 }
-                if (nvisited + p.max_degree + 32 > hlimit) overflow = true;
+                if (nvisited + p.max_degree + 32 > hlimit) {  // the next node could pass the load limit: stop expanding now
+                    overflow = true;
+                    break;
+                }
             }
             if (overflow) break;
             __syncwarp();
@@ -493,12 +497,7 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
     SearchParamsV2 p2;
     memset(&p2, 0, sizeof(p2));
     V2Launch v2;
-#if DAB_V2_TAG16_BUILD
-    const int grid_v1 = grid;  // overflow retries of the 16-bit-tag tables run the generic kernel
-    bool use_v2 = v2_prepare(idx, l_search, beam, p2, v2) == 0;
-#else
     const bool use_v2 = v2_prepare(idx, l_search, beam, p2, v2) == 0;
-#endif
     if (use_v2) {
         p2.vectors = p.vectors;
         p2.row_stride = p.row_stride;
@@ -551,27 +550,6 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
     p2.counters = d_counters;
     p2.overflow_list = d_overflow;
     Scratch retry_list;  // holds the overflow list of the previous pass
-#if DAB_V2_TAG16_BUILD
-    // experiment: 16 tags of 16 bits per 32-byte bucket (search_common.cuh, Tag16Map)
-    uint32_t tag_nbk = 0;
-    if (use_v2) {
-        uint32_t K = 8;
-        while (((uint64_t)1 << K) < idx->n_total()) ++K;
-        uint64_t nbk = std::max<uint64_t>(16, (slots + 15) / 16);
-        nbk = std::max<uint64_t>(nbk, (((uint64_t)1 << K) + 16383) >> 14);  // tags must fit 14 bits
-        uint32_t sbits = 0;
-        while (((uint64_t)1 << sbits) < nbk) ++sbits;
-        if (K + sbits > 32 || nbk * 32 > 96 * 1024) {
-            use_v2 = false;  // index too large for quotient tags at this table size
-            grid = grid_v1;
-        } else {
-            tag_nbk = (uint32_t)nbk;
-            p2.tag_kmask = (uint32_t)(((uint64_t)1 << K) - 1);
-            p2.tag_shift = K + sbits;
-            p2.tag_magic = (uint32_t)((((uint64_t)1 << (K + sbits)) + nbk - 1) / nbk);
-        }
-    }
-#endif
 
     // ---- first pass with the visited sets in shared memory (search_kernel_v3); queries that
     // outgrow their table are collected in the overflow list and re-run below on global tables
@@ -643,11 +621,7 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
     for (int pass = 0; pass < 6; ++pass) {
         const uint32_t warps = (uint32_t)grid * (use_v2 ? kV2WarpsHost : kSearchWarps);
         const uint32_t hlog = std::max<uint32_t>(use_v2 ? 8 : 10, next_pow2_log2(slots));
-#if DAB_V2_TAG16_BUILD
-        const uint32_t n_buckets = use_v2 ? tag_nbk : (uint32_t)((slots + 7) / 8);
-#else
         const uint32_t n_buckets = (uint32_t)((slots + 7) / 8);
-#endif
         const size_t words_per_warp = use_v2 ? (size_t)n_buckets * 8 : ((size_t)1 << hlog);
         if ((rc = idx->s_tables.reserve((size_t)warps * words_per_warp * 4))) {
             retry_list.release();
@@ -724,12 +698,6 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
         p.n_work = n_over;
         slots *= 4;
         if (slots > 4 * idx->n_total() + 4096) slots = 2 * idx->n_total() + 2048;
-#if DAB_V2_TAG16_BUILD
-        if (use_v2) {
-            use_v2 = false;
-            grid = grid_v1;
-        }
-#endif
     }
     retry_list.release();
     return fail(DAB_ERR_VISITED_OVERFLOW, "search: visited set still overflowing after 6 passes");

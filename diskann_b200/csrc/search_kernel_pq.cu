@@ -202,7 +202,10 @@ __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchPa
                     ncand += __popc(mn);
                     nvisited += __popc(mi);
                 }
-                if (nvisited + p.max_degree > hlimit) overflow = true;
+                if (nvisited + p.max_degree > hlimit) {
+                    overflow = true;
+                    break;
+                }
             }
             if (overflow) break;
             __syncwarp();

@@ -38,23 +38,11 @@ constexpr int kGroup = 8;  // rows reduced together
 #ifndef DAB_V2_ADJ_SMEM
 #define DAB_V2_ADJ_SMEM 1  // speculative adjacency row into shared memory (0: L2 prefetch)
 #endif
-#ifndef DAB_V2_SPLIT_WAIT
-#define DAB_V2_SPLIT_WAIT 0  // experiment for the next round: compute the first 8 rows while the rest land
-#endif
-#ifndef DAB_V2_DEFER_CAS
-#define DAB_V2_DEFER_CAS 0  // experiment: visited-set CAS after the row copies are issued (its outcome is known)
-#endif
-#ifndef DAB_V2_WIDE_LDS
-#define DAB_V2_WIDE_LDS 0   // experiment: 16-byte shared-memory reads with per-lane accumulator chains (needs DAB_V2_F32X2)
-#endif
 #ifndef DAB_V2_INT_BUILD
 #define DAB_V2_INT_BUILD 1  // i8 / u8 rows in search_kernel_v2 (exact integer distances); GPU-validated in round 2
 #endif
 #ifndef DAB_V2_F32X2
 #define DAB_V2_F32X2 1     // packed FADD2 / FFMA2 distance arithmetic
-#endif
-#if DAB_V2_DEFER_CAS && DAB_V2_SPLIT_WAIT
-#error "DAB_V2_DEFER_CAS runs its postponed inserts in the single-group wait path only: do not combine it with DAB_V2_SPLIT_WAIT"
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -159,80 +147,6 @@ __device__ __forceinline__ float group_distance(const float* __restrict__ q, con
     return a;
 }
 
-#if DAB_V2_WIDE_LDS
-// Experiment: the lane mapping of frontier_wide_kernel (distance_kernels.cu) applied to the staged
-// rows — every lane reads 16 bytes of its row and of the query per step and owns the FMA chains of
-// those slots, so 4 (f16) / 8 (f32) lanes cover a row and a pass covers 8 / 4 rows.  Returns the
-// value of row `lane / (32 / EPL)` of the pass on all lanes of that team.  Same association as
-// group_distance: block k of 8 elements -> accumulator k mod 4, (s0+s1)+(s2+s3), zero-filled
-// remainder on the combined vector, sum_tree.
-template <typename TD, int KIND>
-__device__ __forceinline__ float wide_pass(const float* __restrict__ q, const uint8_t* __restrict__ rows, uint32_t row_slot, int dim,
-                                           int lane) {
-    constexpr int EPL = 16 / (int)sizeof(TD), LPR = 32 / EPL, HALVES = 8 / EPL;
-    const int team = lane / LPR, tl = lane % LPR;
-    const int a = tl / HALVES, h = tl % HALVES;
-    const uint8_t* row = rows + (size_t)team * row_slot;
-    const int nb8 = dim >> 3, full8 = dim & ~7, rem = dim & 7;
-    uint64_t acc2[EPL / 2];
-#pragma unroll
-    for (int i = 0; i < EPL / 2; ++i) acc2[i] = 0ull;
-    for (int k = a; k < nb8; k += 4) {
-        const int e0 = 8 * k + EPL * h;
-        const uint4 v = *reinterpret_cast<const uint4*>(row + (size_t)e0 * sizeof(TD));
-        float y[EPL];
-        if constexpr (sizeof(TD) == 2) {
-            const __half2* hp = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(hp[i]);
-                y[2 * i] = f.x;
-                y[2 * i + 1] = f.y;
-            }
-        } else {
-            y[0] = __uint_as_float(v.x), y[1] = __uint_as_float(v.y), y[2] = __uint_as_float(v.z), y[3] = __uint_as_float(v.w);
-        }
-#pragma unroll
-        for (int i = 0; i < EPL; i += 4) {
-            const float4 x = *reinterpret_cast<const float4*>(q + e0 + i);
-            acc2[i / 2] = step2<KIND>(acc2[i / 2], pack2(x.x, x.y), pack2(y[i], y[i + 1]));
-            acc2[i / 2 + 1] = step2<KIND>(acc2[i / 2 + 1], pack2(x.z, x.w), pack2(y[i + 2], y[i + 3]));
-        }
-    }
-    float acc[EPL];
-#pragma unroll
-    for (int i = 0; i < EPL / 2; ++i) unpack2(acc2[i], acc[2 * i], acc[2 * i + 1]);
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-        acc[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], HALVES));
-        acc[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], 2 * HALVES));
-    }
-    if (rem) {
-        const TD* tail = reinterpret_cast<const TD*>(row) + full8;
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) {
-            const int l = EPL * h + i;
-            const float x = l < rem ? q[full8 + l] : 0.0f;
-            const float yv = l < rem ? to_f32(tail[l]) : 0.0f;
-            if (KIND == KIND_L2) {
-                const float d = __fsub_rn(x, yv);
-                acc[i] = __fmaf_rn(d, d, acc[i]);
-            } else {
-                acc[i] = __fmaf_rn(x, yv, acc[i]);
-            }
-        }
-    }
-    if constexpr (HALVES == 1) {
-        return __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[4]), __fadd_rn(acc[2], acc[6])),
-                         __fadd_rn(__fadd_rn(acc[1], acc[5]), __fadd_rn(acc[3], acc[7])));
-    } else {
-        float t[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) t[i] = __fadd_rn(acc[i], __shfl_xor_sync(kFull, acc[i], 1));  // x_i + x_{i+4}
-        return __fadd_rn(__fadd_rn(t[0], t[2]), __fadd_rn(t[1], t[3]));
-    }
-}
-#endif
 
 #if DAB_V2_INT_BUILD
 // Experiment: i8 / u8 rows through the same hop structure.  Integer distances are exact in i32
@@ -315,12 +229,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
     const uint32_t warp_slot = blockIdx.x * kV2Warps + wib;
     const uint32_t nbk = p.n_buckets;
     uint32_t* table = p.tables + (size_t)warp_slot * nbk * 8;
-#if DAB_V2_TAG16_BUILD
-    const Tag16Map tmap{p.tag_kmask, nbk, p.tag_magic, p.tag_shift};
-    const uint32_t hlimit = nbk * 14;  // 87.5 % of 16 tags per bucket
-#else
     const uint32_t hlimit = nbk * 7;  // 87.5 % load: 8-way buckets stay short
-#endif
     const uint64_t n_total = p.n_points + p.n_start;
     const int dim = (int)p.dim;
 #if DAB_L2_HINTS
@@ -381,33 +290,10 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
         uint32_t pred = kEmptyV2;  // node whose adjacency row sits in adjbuf
         bool overflow = false;
 
-#if DAB_V2_DEFER_CAS && !DAB_V2_TAG16_BUILD
-        // visited-set inserts of the current hop whose outcome is already known (see the probe code)
-        // (the bucket images are re-read — an L2 hit by now — rather than kept in registers)
-        uint32_t d_bk[3], d_id[3];
-        bool d_need[3] = {false, false, false};
-        bool d_pending = false;
-        auto run_deferred = [&]() {
-            if (!d_pending) return;
-            d_pending = false;
-            uint32_t im[3][8];
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                if (d_need[c]) load_bucket(table + (size_t)d_bk[c] * 8, im[c]);
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                if (d_need[c]) bucket_insert(table, nbk, d_bk[c], im[c], d_id[c]);
-            __syncwarp();
-        };
-#endif
 
         // stage `n` candidate rows (ids cid[c0..)) with per-lane 16 B async copies and compute
         // their distances into cd[]
-#if DAB_V2_DEFER_CAS && !DAB_V2_TAG16_BUILD
-        auto distances = [&](uint32_t c0, uint32_t n, auto with_deferred) {
-#else
         auto distances = [&](uint32_t c0, uint32_t n) {
-#endif
             // eight lanes per row, 16 B each: one warp instruction moves 128 B of four different
             // rows, and every lane forms its own source address (no cross-lane traffic)
 #if DAB_V2_COPY8
@@ -452,49 +338,17 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                 } else
 #endif
                 {
-#if DAB_V2_WIDE_LDS
-                    constexpr int ROWS = 16 / (int)sizeof(TD), LPR = 32 / ROWS;
-#pragma unroll
-                    for (int pass = 0; pass < kGroup / ROWS; ++pass) {
-                        const float r = wide_pass<TD, KIND>(qf, rows + (size_t)(g0 + pass * ROWS) * p.row_slot, p.row_slot, dim, lane);
-                        const uint32_t u = (uint32_t)(pass * ROWS + lane / LPR);
-                        if (lane % LPR == 0 && g0 + u < n) cd[c0 + g0 + u] = post_op<POST>(r);
-                    }
-#else
                     const float r = group_distance<TD, KIND>(qf, rows + (size_t)g0 * p.row_slot, p.row_slot, dim, lane);
                     const uint32_t u = (((lane >> 3) & 1) << 2) | (((lane >> 4) & 1) << 1) | ((lane >> 2) & 1);
                     if ((lane & 3) == 0 && g0 + u < n) cd[c0 + g0 + u] = post_op<POST>(r);
-#endif
                 }
             };
-#if DAB_V2_SPLIT_WAIT
-            // the first reduce group is copied as its own cp.async group: its arithmetic runs
-            // while the remaining rows of the stage are still in flight
-            const bool split = n > kGroup;
-            issue(0, split ? kGroup : n);
-            if (split) issue(kGroup, n);
-            DAB_PHASE(3);  // issue of the row copies
-            if (split) asm volatile("cp.async.wait_group 1;" ::: "memory");
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            DAB_PHASE(4);  // waiting for the rows
-            compute(0);
-            if (split) {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                __syncwarp();
-                for (uint32_t g0 = kGroup; g0 < n; g0 += kGroup) compute(g0);
-            }
-#else
             issue(0, n);
-#if DAB_V2_DEFER_CAS && !DAB_V2_TAG16_BUILD
-            if constexpr (decltype(with_deferred)::value) run_deferred();  // the postponed CAS round trip runs while the rows are in flight
-#endif
             DAB_PHASE(3);  // issue of the row copies
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
             DAB_PHASE(4);  // waiting for the rows
             for (uint32_t g0 = 0; g0 < n; g0 += kGroup) compute(g0);
-#endif
             __syncwarp();
         };
 
@@ -505,24 +359,12 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                 const uint32_t id = (uint32_t)p.n_points + s0 + lane;
                 cid[lane] = id;
                 uint32_t bs[8];
-#if DAB_V2_TAG16_BUILD
-                uint32_t b, tg;
-                bool ovf = false;  // start points cannot fill three buckets in a row
-                tag16_of(id, tmap, b, tg);
-                load_bucket(table + (size_t)b * 8, bs);
-                bucket16_insert(table, nbk, b, bs, tg, ovf);
-#else
                 const uint32_t b = bucket_of(id, nbk);
                 load_bucket(table + (size_t)b * 8, bs);
                 bucket_insert(table, nbk, b, bs, id);
-#endif
             }
             __syncwarp();
-#if DAB_V2_DEFER_CAS && !DAB_V2_TAG16_BUILD
-            for (uint32_t c0 = 0; c0 < n; c0 += p.stage_rows) distances(c0, min(p.stage_rows, n - c0), std::false_type{});
-#else
             for (uint32_t c0 = 0; c0 < n; c0 += p.stage_rows) distances(c0, min(p.stage_rows, n - c0));
-#endif
             merge_round<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, 0, n, lane);
             nvisited += n;
             cmps += n;
@@ -599,69 +441,17 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                 bool valid[3];
                 uint32_t bk[3];
                 uint32_t bs[3][8];
-#if DAB_V2_TAG16_BUILD
-                uint32_t tg[3];
-                bool ovf = false;
-#endif
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const uint32_t j = c * 32 + lane;
-#if DAB_V2_TAG16_BUILD
-                    // ids beyond 2^K cannot be in bounds and never reach the outputs: not tracked
-                    valid[c] = j >= 1 && j <= deg && wd[c] <= tmap.kmask;
-                    tag16_of(wd[c], tmap, bk[c], tg[c]);
-#else
                     valid[c] = j >= 1 && j <= deg;
                     bk[c] = bucket_of(wd[c], nbk);
-#endif
                     if (valid[c]) load_bucket(table + (size_t)bk[c] * 8, bs[c]);
                 }
-#if DAB_V2_DEFER_CAS && !DAB_V2_TAG16_BUILD
-                // An id that is absent from its home bucket while that bucket still has a free
-                // slot is new for certain (a displaced copy exists only if the home bucket was
-                // full when it was inserted, and buckets never lose entries).  With one node per
-                // hop the candidate list is therefore known before any CAS has run: the inserts
-                // are postponed until the row copies have been issued (run_deferred) and their
-                // round trip overlaps the row fetch.
-                bool need[3], defer = nb == 1 && deg <= 95;
-                {
-                    bool full = false, cand = false;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        bool found = false, has_empty = false;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            found |= bs[c][k] == wd[c];
-                            has_empty |= bs[c][k] == kEmptyV2;
-                        }
-                        need[c] = valid[c] && !found;
-                        full |= need[c] && !has_empty;
-                        cand |= need[c] && wd[c] < n_total;
-                    }
-                    // (a hop without in-bounds candidates stages no rows: nothing to overlap with)
-                    defer = defer && !__any_sync(kFull, full) && __any_sync(kFull, cand);
-                }
-                if (defer) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        d_need[c] = need[c];
-                        d_bk[c] = bk[c];
-                        d_id[c] = wd[c];
-                    }
-                    d_pending = true;
-                }
-#endif
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     bool inserted = false;
-#if DAB_V2_TAG16_BUILD
-                    if (valid[c]) inserted = bucket16_insert(table, nbk, bk[c], bs[c], tg[c], ovf);
-#elif DAB_V2_DEFER_CAS
-                    if (defer) inserted = need[c];
-                    else if (valid[c]) inserted = bucket_insert(table, nbk, bk[c], bs[c], wd[c]);
-#else
                     if (valid[c]) inserted = bucket_insert(table, nbk, bk[c], bs[c], wd[c]);
-#endif
                     const bool isnew = inserted && wd[c] < n_total;  // is_in_bounds
                     const unsigned mi = __ballot_sync(kFull, inserted);
                     const unsigned mn = __ballot_sync(kFull, isnew);
@@ -674,21 +464,12 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                     const uint32_t j = c0 + lane;
                     const uint32_t word = j < p.adj_stride ? __ldg(row + j) : kEmptyV2;
                     bool inserted = false;
-#if DAB_V2_TAG16_BUILD
-                    if (j <= deg && word <= tmap.kmask) {
-                        uint32_t b2, t2, bs2[8];
-                        tag16_of(word, tmap, b2, t2);
-                        load_bucket(table + (size_t)b2 * 8, bs2);
-                        inserted = bucket16_insert(table, nbk, b2, bs2, t2, ovf);
-                    }
-#else
                     if (j <= deg) {
                         const uint32_t b2 = bucket_of(word, nbk);
                         uint32_t bs2[8];
                         load_bucket(table + (size_t)b2 * 8, bs2);
                         inserted = bucket_insert(table, nbk, b2, bs2, word);
                     }
-#endif
                     const bool isnew = inserted && word < n_total;
                     const unsigned mi = __ballot_sync(kFull, inserted);
                     const unsigned mn = __ballot_sync(kFull, isnew);
@@ -696,20 +477,16 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                     ncand += __popc(mn);
                     nvisited += __popc(mi);
                 }
-                if (nvisited + p.max_degree > hlimit) overflow = true;
-#if DAB_V2_TAG16_BUILD
-                if (__any_sync(kFull, ovf)) overflow = true;  // three full buckets in a row: re-run with the 32-bit table
-#endif
+                if (nvisited + p.max_degree > hlimit) {  // the next node could pass the load limit: stop expanding now
+                    overflow = true;
+                    break;
+                }
             }
             if (overflow) break;
             __syncwarp();
             DAB_PHASE(2);  // adjacency fetch + visited filter
 
-#if DAB_V2_DEFER_CAS && !DAB_V2_TAG16_BUILD
-            for (uint32_t c0 = 0; c0 < ncand; c0 += p.stage_rows) distances(c0, min(p.stage_rows, ncand - c0), std::true_type{});
-#else
             for (uint32_t c0 = 0; c0 < ncand; c0 += p.stage_rows) distances(c0, min(p.stage_rows, ncand - c0));
-#endif
             DAB_PHASE(5);  // distance arithmetic
 
             // best.insert for every neighbour in adjacency order (index.rs:1986-1988)

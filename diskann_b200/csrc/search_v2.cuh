@@ -10,9 +10,6 @@ namespace dab {
 #define DAB_V2_WARPS 1
 #endif
 constexpr int kV2Warps = DAB_V2_WARPS;  // warps per CTA (each warp owns a query)
-#ifndef DAB_V2_TAG16_BUILD
-#define DAB_V2_TAG16_BUILD 0  // experiment: 16-bit quotient-tag visited tables (search_common.cuh)
-#endif
 
 struct SearchParamsV2 {
     const uint8_t* vectors;
@@ -35,9 +32,6 @@ struct SearchParamsV2 {
     uint32_t* out_hops;
     uint32_t* tables;
     uint32_t n_buckets;   // visited table: buckets of 8 ids (32 B) per warp, any count >= 16
-#if DAB_V2_TAG16_BUILD
-    uint32_t tag_kmask, tag_magic, tag_shift;  // Tag16Map (buckets then hold 16 tags)
-#endif
     uint32_t* counters;
     uint32_t* overflow_list;
     uint32_t* rec_ids;
