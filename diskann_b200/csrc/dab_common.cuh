@@ -64,6 +64,8 @@ struct Tuning {
     int v2_stage_bytes = 0;        // DAB_V2_STAGE_BYTES
     int v2_ctas_per_sm = 0;        // DAB_V2_CTAS_PER_SM
     int v3_table_bytes = 0;        // DAB_V3_TABLE_BYTES: visited-table bytes per warp
+    int pq_ctas_per_sm = 0;        // DAB_PQ_CTAS_PER_SM: resident CTAs (4 warps) per SM of the PQ traversal kernel (default 6)
+    int v3_max_cap = 0;            // DAB_V3_MAX_CAP: largest L + #start that still runs search_kernel_v3 (default 24)
     bool v3_generic = false;       // DAB_V3_GENERIC: generic distance loop also for 32 / 64 / 96 / 128-d f32 rows
     int v3_ctas_per_sm = 0;        // DAB_V3_CTAS_PER_SM: cap on resident CTAs
     int test_visited_log2 = 0;     // DAB_TEST_VISITED_LOG2: tests force the overflow / retry path
@@ -104,6 +106,7 @@ struct dab_index {
 
     // search-side state learned across calls
     uint32_t hint_l = 0, hint_beam = 0, hint_visited = 0;  // largest visited set seen at (L, beam)
+    uint32_t pq_hint_l = 0, pq_hint_beam = 0, pq_hint_visited = 0;  // the same for the PQ traversal kernel
     uint32_t v3_overflow_l = 0, v3_overflow_beam = 0;      // share of queries that outgrew the shared-memory
     float v3_overflow_frac = 0.0f;                         // tables at (L, beam): search_kernel_v3 is skipped when large
     void* l2_window_ptr = nullptr;       // current persisting-L2 window (visited tables)

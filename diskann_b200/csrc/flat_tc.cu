@@ -37,9 +37,11 @@ int launch_frontier(const dab_index* idx, const void* d_queries, uint32_t nq, co
 namespace {
 
 constexpr int kBM = 128, kBN = 128, kBK = 64;  // CTA tile; one k-block = 64 bf16 = one 128-byte swizzle row
-constexpr int kStages = 5;
+constexpr int kStages = 5;                    // streaming mode: stages of (A k-block, B k-block)
+constexpr int kStagesRes = 6;                 // A-resident mode: stages of B k-blocks only
+constexpr int kMaxResKb = 6;                  // A stays in shared memory when K' <= 6 x 64 (e.g. 3 x 128)
 constexpr int kTcThreads = 192;                // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-5: epilogue
-constexpr int kKP = 32;                        // candidates kept per (query row, base range)
+constexpr int kKP = 32;                        // largest candidate set per (query row, base range); k <= 10 uses 16
 constexpr uint32_t kTileBytes = kBM * kBK * 2; // 16 KB per operand tile
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -106,8 +108,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
           "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- operand preparation --------------------------------------------------------------------
 // rows of the index dtype -> bf16 [n][kp]: f32 / f16: (hi, hi, lo) for queries, (hi, lo, hi) for base
@@ -170,20 +172,27 @@ struct TcParams {
     uint32_t* cand;            // [nq][n_splits][kKP]
 };
 
+// RES: the 128 x K' query tile of the CTA is loaded once and stays in shared memory (K' <= 384), so only
+// base tiles stream from L2 — the operand traffic, which is what bounds this kernel, is halved.
+template <bool RES, int KP>
 __global__ void __launch_bounds__(kTcThreads, 1)
 flat_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+    constexpr int kSt = RES ? kStagesRes : kStages;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sa = smem;                              // kStages x 16 KB
-    uint8_t* sb = smem + kStages * kTileBytes;       // kStages x 16 KB
-    float* s_coef = reinterpret_cast<float*>(smem + 2 * kStages * kTileBytes);  // [2 accumulators][alpha 128 | beta 128]
+    uint8_t* sa = smem;                                              // RES: kMaxResKb x 16 KB (whole A tile); else kStages x 16 KB
+    uint8_t* sb = smem + (RES ? kMaxResKb : kStages) * kTileBytes;   // kSt x 16 KB
+    float* s_coef = reinterpret_cast<float*>(sb + kSt * kTileBytes);  // [2 accumulators][alpha 128 | beta 128]
     float* s_scores = s_coef + 2 * 2 * kBN;                                      // [128 epilogue threads][33]: private scratch rows
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_scores + 128 * 33);  // 16896 bytes: stays 8-byte aligned
-    uint64_t* full = bars;                  // [kStages] TMA -> MMA
-    uint64_t* empty = bars + kStages;       // [kStages] MMA -> TMA
-    uint64_t* tfull = bars + 2 * kStages;   // [2] MMA -> epilogue
+    float* s_cd = s_scores + 128 * 33;                                           // [kKP][128]: candidate scores, entry-major (conflict-free)
+    uint32_t* s_ci = reinterpret_cast<uint32_t*>(s_cd + kKP * 128);              // [kKP][128]: candidate ids
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ci + kKP * 128);              // offsets stay 8-byte aligned
+    uint64_t* full = bars;                  // [kSt] TMA -> MMA
+    uint64_t* empty = bars + kSt;           // [kSt] MMA -> TMA
+    uint64_t* tfull = bars + 2 * kSt;       // [2] MMA -> epilogue
     uint64_t* tempty = tfull + 2;           // [2] epilogue -> MMA
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* afull = tempty + 2;           // [1] resident A tile has landed
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(afull + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t m0 = blockIdx.y * kBM;
@@ -193,10 +202,11 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t kblocks = p.kp / kBK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kSt; ++s) {
             mbar_init(full + s, 1);
             mbar_init(empty + s, 1);
         }
+        mbar_init(afull, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull + a, 1);
             mbar_init(tempty + a, 4);  // one arrival per epilogue warp
@@ -218,13 +228,17 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===== TMA producer (one lane) =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            if (RES) {
+                mbar_expect_tx(afull, kblocks * kTileBytes);
+                for (uint32_t kb = 0; kb < kblocks; ++kb) tma_load_2d(&map_a, afull, sa + kb * kTileBytes, (int32_t)(kb * kBK), (int32_t)m0);
+            }
             for (uint32_t t = t0; t < t1; ++t) {
                 for (uint32_t kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(empty + stage, phase ^ 1);
-                    mbar_expect_tx(full + stage, 2 * kTileBytes);
-                    tma_load_2d(&map_a, full + stage, sa + stage * kTileBytes, (int32_t)(kb * kBK), (int32_t)m0);
+                    mbar_expect_tx(full + stage, (RES ? 1 : 2) * kTileBytes);
+                    if (!RES) tma_load_2d(&map_a, full + stage, sa + stage * kTileBytes, (int32_t)(kb * kBK), (int32_t)m0);
                     tma_load_2d(&map_b, full + stage, sb + stage * kTileBytes, (int32_t)(kb * kBK), (int32_t)(t * kBN));
-                    if (++stage == kStages) {
+                    if (++stage == kSt) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -236,6 +250,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0) {
             const uint32_t idesc = umma_idesc();
             uint32_t stage = 0, phase = 0;
+            if (RES) mbar_wait(afull, 0);
             for (uint32_t t = t0; t < t1; ++t) {
                 const uint32_t acc = (t - t0) & 1, use = (t - t0) >> 1;
                 mbar_wait(tempty + acc, (use & 1) ^ 1);  // the epilogue has drained this accumulator
@@ -246,12 +261,12 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
-                        const uint64_t da = umma_desc(sa + stage * kTileBytes, k * 32);
+                        const uint64_t da = umma_desc(sa + (RES ? kb : stage) * kTileBytes, k * 32);
                         const uint64_t db = umma_desc(sb + stage * kTileBytes, k * 32);
                         umma_f16(tmem_d, da, db, idesc, (kb | (uint32_t)k) != 0 ? 1u : 0u);
                     }
                     umma_commit(empty + stage);  // frees the stage once these MMAs have read it
-                    if (++stage == kStages) {
+                    if (++stage == kSt) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -266,32 +281,45 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t q = m0 + row;
         const int et = (warp - 2) * 32 + lane;     // 0..127 among the epilogue threads
         float* my_scores = s_scores + et * 33;      // stride 33: conflict-free rows
-        float cd[kKP];
-        uint32_t ci[kKP];
+        float* cd = s_cd + et;        // entry e of this thread: cd[e * 128]
+        uint32_t* ci = s_ci + et;
         uint32_t cn = 0;
-        float worst = -1.0f;   // largest kept score (valid when cn == kKP)
+        float worst = -1.0f;   // largest kept score (valid when cn == KP)
         int worst_at = 0;
+        // per-column score coefficients (alpha, beta): tile t's are in s_coef[t & 1]; the next tile's are
+        // fetched from global memory while this tile is processed
+        auto load_coef = [&](uint32_t t, float& a, float& b) {
+            const uint32_t col = t * kBN + et;
+            a = col < p.n_base ? p.alpha[col] : 0.0f;
+            b = col < p.n_base ? p.beta[col] : __int_as_float(0x7F800000);
+        };
+        {
+            float a, b;
+            load_coef(t0, a, b);
+            s_coef[et] = a;
+            s_coef[kBN + et] = b;
+        }
         for (uint32_t t = t0; t < t1; ++t) {
             const uint32_t acc = (t - t0) & 1, use = (t - t0) >> 1;
-            // per-column score coefficients of this tile (alpha, beta)
             float* coef = s_coef + acc * 2 * kBN;
-            {
-                const uint32_t col = t * kBN + et;
-                coef[et] = col < p.n_base ? p.alpha[col] : 0.0f;
-                coef[kBN + et] = col < p.n_base ? p.beta[col] : __int_as_float(0x7F800000);
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            float a_next = 0.0f, b_next = 0.0f;
+            if (t + 1 < t1) load_coef(t + 1, a_next, b_next);
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // coef[acc] written by everyone; coef[acc ^ 1] no longer read
             mbar_wait(tfull + acc, use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + acc * kBN + ((quarter * 32u) << 16);
-#pragma unroll 1
-            for (int c0 = 0; c0 < kBN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c0, r);
+            uint32_t rbuf[2][32];
+            tmem_ld32(taddr, rbuf[0]);
+#pragma unroll
+            for (int cc = 0; cc < kBN / 32; ++cc) {
+                const int c0 = cc * 32;
+                uint32_t (&r)[32] = rbuf[cc & 1];
+                tmem_ld_wait();
+                if (cc + 1 < kBN / 32) tmem_ld32(taddr + c0 + 32, rbuf[(cc + 1) & 1]);  // next chunk in flight during this one
                 // fast path, branch-free: the 32 scores go to this thread's scratch row and a bit mask
                 // marks the ones that beat the current threshold (all of them while the set fills)
                 uint32_t mask = 0;
-                const float thr = cn < (uint32_t)kKP ? __int_as_float(0x7F800000) : worst;
+                const float thr = cn < (uint32_t)KP ? __int_as_float(0x7F800000) : worst;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float sc = fmaf(__uint_as_float(r[j]), coef[c0 + j], coef[kBN + c0 + j]);
@@ -304,29 +332,39 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     mask &= mask - 1;
                     const float sc = my_scores[j];
                     const uint32_t id = t * kBN + c0 + j;
-                    if (cn < (uint32_t)kKP) {
-                        cd[cn] = sc;
-                        ci[cn] = id;
-                        if (++cn < (uint32_t)kKP) continue;
+                    if (cn < (uint32_t)KP) {
+                        cd[cn * 128] = sc;
+                        ci[cn * 128] = id;
+                        if (++cn < (uint32_t)KP) continue;
                     } else if (sc < worst) {
-                        cd[worst_at] = sc;
-                        ci[worst_at] = id;
+                        cd[worst_at * 128] = sc;
+                        ci[worst_at * 128] = id;
                     } else {
                         continue;
                     }
-                    worst = cd[0];
+                    // new threshold: the largest kept score (independent loads, then a max tree)
+                    float v[KP];
+#pragma unroll
+                    for (int e = 0; e < KP; ++e) v[e] = cd[e * 128];
+                    worst = v[0];
                     worst_at = 0;
-                    for (int e = 1; e < kKP; ++e)
-                        if (cd[e] > worst) worst = cd[e], worst_at = e;
+#pragma unroll
+                    for (int e = 1; e < KP; ++e)
+                        if (v[e] > worst) worst = v[e], worst_at = e;
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty + acc);
+            if (t + 1 < t1) {
+                float* nxt = s_coef + (acc ^ 1u) * 2 * kBN;
+                nxt[et] = a_next;
+                nxt[kBN + et] = b_next;
+            }
         }
         if (q < p.nq) {
-            uint32_t* out = p.cand + ((size_t)q * p.n_splits + split) * kKP;
-            for (uint32_t e = 0; e < (uint32_t)kKP; ++e) out[e] = e < cn ? ci[e] : kNoId;
+            uint32_t* out = p.cand + ((size_t)q * p.n_splits + split) * KP;
+            for (uint32_t e = 0; e < (uint32_t)KP; ++e) out[e] = e < cn ? ci[e * 128] : kNoId;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -464,7 +502,8 @@ int dab_flat_knn_tc(dab_index* idx, const void* queries, uint32_t nq, uint32_t k
     uint32_t splits = std::max<uint32_t>(1, std::min<uint32_t>(std::min<uint32_t>(n_tiles, 48), (uint32_t)(idx->sm_count * 2 + m_tiles - 1) / m_tiles));
     const uint32_t tiles_per_split = (n_tiles + splits - 1) / splits;
     splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
-    const uint32_t c = splits * kKP;
+    const uint32_t kp_sel = k <= 10 ? 16u : (uint32_t)kKP;  // per-range candidates: k plus slack for the approximate scores
+    const uint32_t c = splits * kp_sel;
     if ((rc = idx->s_ids.reserve((size_t)nq * c * 4))) return rc;
     if ((rc = idx->s_out2.reserve((size_t)nq * c * 4))) return rc;
     if ((rc = idx->s_out.reserve((size_t)nq * k * 8))) return rc;
@@ -480,9 +519,24 @@ int dab_flat_knn_tc(dab_index* idx, const void* queries, uint32_t nq, uint32_t k
     p.alpha = (const float*)idx->d_tc_coef;
     p.beta = (const float*)idx->d_tc_coef + n;
     p.cand = (uint32_t*)idx->s_ids.p;
-    const size_t smem = 1024 + 2 * (size_t)kStages * kTileBytes + 2 * 2 * kBN * 4 + 128 * 33 * 4 + (2 * kStages + 4) * 8 + 16;
-    DAB_CUDA(cudaFuncSetAttribute(flat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    flat_tc_kernel<<<dim3(splits, m_tiles), kTcThreads, smem, st>>>(map_a, map_b, p);
+    // (the resident-query-tile mode halves the operand traffic — 12.4 -> 7.1 GB for 1000 x 1M — but measured slower,
+    // 3.34 vs 2.63 ms: the kernel is bound by its epilogue, not by L2 -> SM traffic; kept for larger M per CTA later)
+    const bool resident = false && kp / kBK <= (uint32_t)kMaxResKb;
+    const size_t tiles_smem = resident ? (size_t)(kMaxResKb + kStagesRes) * kTileBytes : 2 * (size_t)kStages * kTileBytes;
+    const size_t smem = 1024 + tiles_smem + 2 * 2 * kBN * 4 + 128 * 33 * 4 + 2 * (size_t)kKP * 128 * 4 + (2 * (size_t)kStagesRes + 5) * 8 + 16;
+#define DAB_TC_LAUNCH(RES_, KP_)                                                                                        \
+    do {                                                                                                                \
+        DAB_CUDA(cudaFuncSetAttribute(flat_tc_kernel<RES_, KP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        flat_tc_kernel<RES_, KP_><<<dim3(splits, m_tiles), kTcThreads, smem, st>>>(map_a, map_b, p);                    \
+    } while (0)
+    if (resident) {
+        if (kp_sel == 16) DAB_TC_LAUNCH(true, 16);
+        else DAB_TC_LAUNCH(true, 32);
+    } else {
+        if (kp_sel == 16) DAB_TC_LAUNCH(false, 16);
+        else DAB_TC_LAUNCH(false, 32);
+    }
+#undef DAB_TC_LAUNCH
     DAB_LAUNCHED();
     DAB_CUDA(cudaGetLastError());
     // exact distances of the candidates in the reference's SIMD order, then the final top-k

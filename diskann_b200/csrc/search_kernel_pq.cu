@@ -454,11 +454,20 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     int per_sm = 0;
     DAB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPqWarps * 32, smem_block));
     if (per_sm < 1) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: kernel does not fit");
-    per_sm = std::min(per_sm, 6);  // keeps the per-warp tables (32 KB each at 32 x 256) inside the L2
+    // every resident warp owns a LUT (n_chunks x n_centers f32: 32 KB at 32 x 256) and a visited table in
+    // global memory; ADC terms and probes are L2 hits only while all of them stay L2-resident
+    per_sm = std::min(per_sm, idx->tune.pq_ctas_per_sm ? idx->tune.pq_ctas_per_sm : 6);
     const int grid = (int)std::min<uint64_t>((uint64_t)per_sm * idx->sm_count, ((uint64_t)nq + kPqWarps - 1) / kPqWarps);
     const uint32_t warps = (uint32_t)grid * kPqWarps;
 
+    // visited-table capacity: the reference's estimate (scratch.rs:186-192) on the first call, then 1.15x the
+    // largest visited set seen at this (or a larger) L at 87.5 % load — the estimate is ~10x what a search
+    // touches, and every query clears its table; queries that still overflow are re-run below
     uint64_t slots = std::max<uint64_t>(256, (uint64_t)(1.1 * idx->max_degree * 1.3 * (double)l_search) + 1);
+    if (idx->pq_hint_visited > 0 && l_search <= idx->pq_hint_l && beam <= idx->pq_hint_beam && !idx->tune.test_visited_log2) {
+        const uint64_t seen = (uint64_t)(((double)idx->pq_hint_visited * 1.15 + idx->max_degree) / 0.875) + 8;
+        slots = std::min(slots, std::max<uint64_t>(256, seen));
+    }
     if (slots > 2 * idx->n_total() + 2048) slots = 2 * idx->n_total() + 2048;
     int rc;
     if ((rc = idx->s_counters.reserve(16 + (size_t)nq * 4))) return rc;
@@ -491,6 +500,12 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
         uint32_t h[3] = {0, 0, 0};
         DAB_CUDA(cudaMemcpyAsync(h, d_counters, 12, cudaMemcpyDeviceToHost, idx->stream));
         DAB_CUDA(cudaStreamSynchronize(idx->stream));
+        if (l_search != idx->pq_hint_l || beam != idx->pq_hint_beam) {
+            idx->pq_hint_l = l_search;
+            idx->pq_hint_beam = beam;
+            idx->pq_hint_visited = 0;
+        }
+        idx->pq_hint_visited = std::max(idx->pq_hint_visited, h[2]);
         if (h[1] == 0) {
             retry.release();
             if (rerank) return launch_rerank(idx, d_queries, nq, k, cap, p.list_ids, p.list_counts, d_ids, d_dists, d_counts);

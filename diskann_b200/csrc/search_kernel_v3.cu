@@ -39,7 +39,7 @@ namespace {
 #define DAB_V3_LP16 0  // visited set: 1 = linear-probing 16-bit slots (measured slower: dependent probe steps), 0 = buckets of 16 tags
 #endif
 #ifndef DAB_V3_FAST_ONE
-#define DAB_V3_FAST_ONE 0  // fast f32 path: one 4-row pass per step instead of two
+#define DAB_V3_FAST_ONE 1  // fast f32 path: one 4-row pass per step (measured best: 2.71 vs 2.90 ms on C2); 0: two passes + butterfly
 #endif
 
 // ---- f32 rows of 32 * nm <= 128 elements (the headline shapes: 128-d, 96-d) ------------------
@@ -413,6 +413,10 @@ __global__ void __launch_bounds__(kV3Warps * 32, DAB_V3_MIN_CTAS) search_kernel_
 // ------------------------------------------------------------------ host side
 int v3_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, uint32_t visited_need, SearchParamsV3& p, V3Launch& out) {
     if (idx->tune.disable_v3) return 1;
+    // v3 wins for short candidate lists (C2: 1.11 vs 1.67 ms at L = 15) and loses at the headline L = 100
+    // (2.94 vs 2.68 ms); the measured crossover is L ~ 25 on both the 128-d f32 and the 768-d f16 shape
+    // (profiles/r02_sweep_l.txt): longer lists go to the global-table kernel
+    if (l_search + idx->n_start > (uint32_t)(idx->tune.v3_max_cap ? idx->tune.v3_max_cap : 24)) return 1;
     const bool is_int = idx->dtype == DAB_I8 || idx->dtype == DAB_U8;
     const MetricPlan plan = plan_for(idx->metric, is_int);
     if (plan.kind == KIND_COS && !is_int) return 1;  // float cosine: NA = 2 schema, generic kernel

@@ -25,6 +25,13 @@ for dt, ddt, metric, d in ((np.float32, dab.DType.f32, dab.Metric.L2, 100), (np.
         got = g.search_batch(base[:64], 5, 64, 1)                # search_kernel_v2 / generic
         got4 = g.search_batch(base[:64], 5, 40, 4)
         knn = g.flat_knn(base[:16], 5)
+        knn_tc = g.flat_knn_tc(base[:16], 5)                     # tcgen05 + TMA + TMEM path
+        assert np.array_equal(knn[0], knn_tc[0])
+        if dt != np.float16:
+            g.pq_train(base[:1500].astype(np.float32), 4, 32, 2, 7)  # k-means++ / Lloyd kernels
+            g.pq_encode_all()
+            pq = g.search_batch_pq(base[:32], 5, 40, 1, rerank=True)  # PQ traversal + rerank kernel
+            g.pq_self_distances(ids[4, :20], ids[5, :20])
         print(dt.__name__, "deg max", int(adj[:, 0].max()), "search ok", int(got[2].min()), int(got4[2].min()),
               "finite", bool(np.isfinite(out[1:]).all() and np.isfinite(pairs).all() and np.isfinite(block).all()), knn[0].shape)
 print("sanitize_check done")
