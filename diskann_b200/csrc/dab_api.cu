@@ -72,6 +72,7 @@ void Tuning::load() {
     disable_v2 = flag("DAB_DISABLE_V2");
     disable_v3 = flag("DAB_DISABLE_V3");
     v3_generic = flag("DAB_V3_GENERIC");
+    tc_stream = flag("DAB_TC_STREAM");
     v3_max_cap = num("DAB_V3_MAX_CAP", 1, 512);
     pq_ctas_per_sm = num("DAB_PQ_CTAS_PER_SM", 1, 16);
     frontier_narrow = flag("DAB_FRONTIER_NARROW");

@@ -64,6 +64,7 @@ struct Tuning {
     int v2_stage_bytes = 0;        // DAB_V2_STAGE_BYTES
     int v2_ctas_per_sm = 0;        // DAB_V2_CTAS_PER_SM
     int v3_table_bytes = 0;        // DAB_V3_TABLE_BYTES: visited-table bytes per warp
+    bool tc_stream = false;        // DAB_TC_STREAM: tensor-core scan streams the query tile too (no resident copy)
     int pq_ctas_per_sm = 0;        // DAB_PQ_CTAS_PER_SM: resident CTAs (4 warps) per SM of the PQ traversal kernel (default 6)
     int v3_max_cap = 0;            // DAB_V3_MAX_CAP: largest L + #start that still runs search_kernel_v3 (default 24)
     bool v3_generic = false;       // DAB_V3_GENERIC: generic distance loop also for 32 / 64 / 96 / 128-d f32 rows

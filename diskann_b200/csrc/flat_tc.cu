@@ -38,7 +38,7 @@ namespace {
 
 constexpr int kBM = 128, kBN = 128, kBK = 64;  // CTA tile; one k-block = 64 bf16 = one 128-byte swizzle row
 constexpr int kStages = 5;                    // streaming mode: stages of (A k-block, B k-block)
-constexpr int kStagesRes = 6;                 // A-resident mode: stages of B k-blocks only
+constexpr int kStagesRes = 4;                 // A-resident mode: stages of B k-blocks only
 constexpr int kMaxResKb = 6;                  // A stays in shared memory when K' <= 6 x 64 (e.g. 3 x 128)
 constexpr int kTcThreads = 192;                // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-5: epilogue
 constexpr int kKP = 32;                        // largest candidate set per (query row, base range); k <= 10 uses 16
@@ -184,9 +184,9 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t* sb = smem + (RES ? kMaxResKb : kStages) * kTileBytes;   // kSt x 16 KB
     float* s_coef = reinterpret_cast<float*>(sb + kSt * kTileBytes);  // [2 accumulators][alpha 128 | beta 128]
     float* s_scores = s_coef + 2 * 2 * kBN;                                      // [128 epilogue threads][33]: private scratch rows
-    float* s_cd = s_scores + 128 * 33;                                           // [kKP][128]: candidate scores, entry-major (conflict-free)
-    uint32_t* s_ci = reinterpret_cast<uint32_t*>(s_cd + kKP * 128);              // [kKP][128]: candidate ids
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ci + kKP * 128);              // offsets stay 8-byte aligned
+    float* s_cd = s_scores + 128 * 33;                                           // [KP][128]: candidate scores, entry-major (conflict-free)
+    uint32_t* s_ci = reinterpret_cast<uint32_t*>(s_cd + KP * 128);               // [KP][128]: candidate ids
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ci + KP * 128);               // offsets stay 8-byte aligned
     uint64_t* full = bars;                  // [kSt] TMA -> MMA
     uint64_t* empty = bars + kSt;           // [kSt] MMA -> TMA
     uint64_t* tfull = bars + 2 * kSt;       // [2] MMA -> epilogue
@@ -519,11 +519,11 @@ int dab_flat_knn_tc(dab_index* idx, const void* queries, uint32_t nq, uint32_t k
     p.alpha = (const float*)idx->d_tc_coef;
     p.beta = (const float*)idx->d_tc_coef + n;
     p.cand = (uint32_t*)idx->s_ids.p;
-    // (the resident-query-tile mode halves the operand traffic — 12.4 -> 7.1 GB for 1000 x 1M — but measured slower,
-    // 3.34 vs 2.63 ms: the kernel is bound by its epilogue, not by L2 -> SM traffic; kept for larger M per CTA later)
-    const bool resident = false && kp / kBK <= (uint32_t)kMaxResKb;
+    // resident query tile: halves the L2 -> SM operand traffic (12.4 -> 7.1 GB for 1000 x 1M), which bounds the
+    // kernel once the epilogue is out of the way (9.3 TB/s measured in streaming mode)
+    const bool resident = !idx->tune.tc_stream && kp / kBK <= (uint32_t)kMaxResKb;
     const size_t tiles_smem = resident ? (size_t)(kMaxResKb + kStagesRes) * kTileBytes : 2 * (size_t)kStages * kTileBytes;
-    const size_t smem = 1024 + tiles_smem + 2 * 2 * kBN * 4 + 128 * 33 * 4 + 2 * (size_t)kKP * 128 * 4 + (2 * (size_t)kStagesRes + 5) * 8 + 16;
+    const size_t smem = 1024 + tiles_smem + 2 * 2 * kBN * 4 + 128 * 33 * 4 + 2 * (size_t)kp_sel * 128 * 4 + (2 * (size_t)kStages + 5) * 8 + 16;
 #define DAB_TC_LAUNCH(RES_, KP_)                                                                                        \
     do {                                                                                                                \
         DAB_CUDA(cudaFuncSetAttribute(flat_tc_kernel<RES_, KP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
