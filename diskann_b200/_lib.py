@@ -48,6 +48,11 @@ SYMBOLS = {
     "dab_search_batch_pq_device": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _i, _vp, _vp, _vp, _vp, _vp]),
     "dab_sq_compress": (_i, [_i, _vp, _f, _u32, _i, _vp, _u64, _vp, _vp]),
     "dab_sq_distances": (_i, [_i, _i, _i, _f, _f, _u32, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "dab_upload_sq": (_i, [_vp, _i, _vp, _f, _f, _f, _vp]),
+    "dab_sq_encode_all": (_i, [_vp]),
+    "dab_sq_download": (_i, [_vp, _vp]),
+    "dab_search_batch_sq": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _i, _vp, _vp, _vp, _vp, _vp]),
+    "dab_search_batch_sq_device": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _i, _vp, _vp, _vp, _vp, _vp]),
     "dab_robust_prune": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _f, _vp, _vp]),
     "dab_build": (_i, [_vp, _u32, _u32, _f, _u32]),
     "dab_flat_knn": (_i, [_vp, _vp, _u32, _u32, _vp, _vp]),

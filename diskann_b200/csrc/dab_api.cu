@@ -72,7 +72,7 @@ void Tuning::load() {
     disable_v2 = flag("DAB_DISABLE_V2");
     disable_v3 = flag("DAB_DISABLE_V3");
     v3_generic = flag("DAB_V3_GENERIC");
-    tc_stream = flag("DAB_TC_STREAM");
+    tc_resident = flag("DAB_TC_RESIDENT");
     v3_max_cap = num("DAB_V3_MAX_CAP", 1, 512);
     pq_ctas_per_sm = num("DAB_PQ_CTAS_PER_SM", 1, 16);
     frontier_narrow = flag("DAB_FRONTIER_NARROW");
@@ -153,6 +153,9 @@ void dab_destroy(dab_index* idx) {
     cudaFree(idx->d_pivots);
     cudaFree(idx->d_offsets);
     cudaFree(idx->d_codes);
+    cudaFree(idx->d_sq_shift);
+    cudaFree(idx->d_sq_codes);
+    cudaFree(idx->d_sq_comp);
     idx->s_queries.release();
     idx->s_ids.release();
     idx->s_out.release();

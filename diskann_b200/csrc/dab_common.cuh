@@ -64,7 +64,7 @@ struct Tuning {
     int v2_stage_bytes = 0;        // DAB_V2_STAGE_BYTES
     int v2_ctas_per_sm = 0;        // DAB_V2_CTAS_PER_SM
     int v3_table_bytes = 0;        // DAB_V3_TABLE_BYTES: visited-table bytes per warp
-    bool tc_stream = false;        // DAB_TC_STREAM: tensor-core scan streams the query tile too (no resident copy)
+    bool tc_resident = false;      // DAB_TC_RESIDENT: tensor-core scan keeps the query tile in shared memory (measured equal to streaming it)
     int pq_ctas_per_sm = 0;        // DAB_PQ_CTAS_PER_SM: resident CTAs (4 warps) per SM of the PQ traversal kernel (default 6)
     int v3_max_cap = 0;            // DAB_V3_MAX_CAP: largest L + #start that still runs search_kernel_v3 (default 24)
     bool v3_generic = false;       // DAB_V3_GENERIC: generic distance loop also for 32 / 64 / 96 / 128-d f32 rows
@@ -100,6 +100,15 @@ struct dab_index {
     uint8_t* d_codes = nullptr;    // [n_total][n_chunks]
     uint32_t pq_chunks = 0, pq_centers = 0;
     bool pq_codes_ready = false;   // codes uploaded (dab_upload_pq) or produced (dab_pq_encode_all)
+    // scalar-quantized store (providers inmem/scalar.rs SQStore<NBITS>): dense N-bit codes, one 16 B-aligned
+    // row per point, compensations apart (only the inner-product epilogue reads them)
+    int sq_nbits = 0;
+    float sq_scale = 0.0f, sq_shift_square_norm = 0.0f, sq_mean_norm = 0.0f;
+    float* d_sq_shift = nullptr;   // [dim]
+    uint8_t* d_sq_codes = nullptr; // [n_total][sq_stride]
+    float* d_sq_comp = nullptr;    // [n_total]
+    uint32_t sq_row_bytes = 0, sq_stride = 0;
+    bool sq_codes_ready = false;
 
     // scratch (grow-only)
     dab::Scratch s_queries, s_ids, s_out, s_out2, s_tables, s_counters, s_stats;
@@ -107,7 +116,7 @@ struct dab_index {
 
     // search-side state learned across calls
     uint32_t hint_l = 0, hint_beam = 0, hint_visited = 0;  // largest visited set seen at (L, beam)
-    uint32_t pq_hint_l = 0, pq_hint_beam = 0, pq_hint_visited = 0;  // the same for the PQ traversal kernel
+    uint32_t pq_hint_l = 0, pq_hint_beam = 0, pq_hint_visited = 0; int pq_hint_mode = 0;  // the same for the PQ traversal kernel
     uint32_t v3_overflow_l = 0, v3_overflow_beam = 0;      // share of queries that outgrew the shared-memory
     float v3_overflow_frac = 0.0f;                         // tables at (L, beam): search_kernel_v3 is skipped when large
     void* l2_window_ptr = nullptr;       // current persisting-L2 window (visited tables)

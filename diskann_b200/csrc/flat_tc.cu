@@ -521,7 +521,7 @@ int dab_flat_knn_tc(dab_index* idx, const void* queries, uint32_t nq, uint32_t k
     p.cand = (uint32_t*)idx->s_ids.p;
     // resident query tile: halves the L2 -> SM operand traffic (12.4 -> 7.1 GB for 1000 x 1M), which bounds the
     // kernel once the epilogue is out of the way (9.3 TB/s measured in streaming mode)
-    const bool resident = !idx->tune.tc_stream && kp / kBK <= (uint32_t)kMaxResKb;
+    const bool resident = idx->tune.tc_resident && kp / kBK <= (uint32_t)kMaxResKb;
     const size_t tiles_smem = resident ? (size_t)(kMaxResKb + kStagesRes) * kTileBytes : 2 * (size_t)kStages * kTileBytes;
     const size_t smem = 1024 + tiles_smem + 2 * 2 * kBN * 4 + 128 * 33 * 4 + 2 * (size_t)kp_sel * 128 * 4 + (2 * (size_t)kStages + 5) * 8 + 16;
 #define DAB_TC_LAUNCH(RES_, KP_)                                                                                        \

@@ -1,4 +1,5 @@
-// search_kernel_pq.cu — batched greedy search whose traversal distances are PQ ADC lookups.
+// search_kernel_pq.cu — batched greedy search whose traversal distances come from a quantized store:
+// PQ ADC lookups (MODE 0) or scalar-quantized codes (MODE 1, see the SQ notes below).
 //
 // Restates the providers' quant accessor (diskann-providers/src/model/graph/provider/async_/
 // inmem/product.rs:311-340: expand_beam with `computer.evaluate_similarity(aux_vectors[i])`)
@@ -13,6 +14,16 @@
 //     (pq_dist_lookup_single, fixed_chunk_pq_table.rs:82-98) -> bit-identical ADC distances;
 //   * visited set, sorted list and post-processing are the shared exact helpers.
 // No tensor cores: LUT gather + byte loads, HBM traffic is n_chunks code bytes per candidate.
+//
+// MODE 1 — the scalar-quantized accessor (providers inmem/scalar.rs:449-570): the query is
+// compressed once per search with the store's own quantizer (SQStore::query_computer, :227-253:
+// as_f32, rescale to the mean norm for InnerProduct, ScalarQuantizer::compress) into the same
+// dense N-bit layout as the rows (bits/slice.rs:261-323), and every candidate distance is
+// Compensated{SquaredL2, IP, CosineNormalized} (scalar/vectors.rs:206-460): an exact integer core
+// over the packed words (bits/distances.rs:397, 979 — here vabsdiffu4 + dp4a on masked fields,
+// popc for 1 bit) and the reference's f32 epilogue.  One lane per candidate, 16 B code loads,
+// the query words broadcast from shared memory; traffic is ceil(dim * N / 8) bytes per candidate
+// (+ 4 B compensation for InnerProduct).
 #include "dab_common.cuh"
 #include "quant_device.cuh"
 #include "search_common.cuh"
@@ -57,10 +68,51 @@ struct SearchParamsPq {
     uint32_t* list_ids;     // [nq][list_cap]
     uint32_t* list_counts;  // [nq]
     uint32_t list_cap;
-    uint32_t warp_smem, off_q, off_qd, off_qi, off_cid, off_cd, off_beam;
+    // MODE 1: scalar-quantized store
+    const uint8_t* sq_codes;  // [n_total][sq_stride], dense N-bit codes, zero padded to 16 B
+    const float* sq_comp;     // [n_total]
+    const float* sq_shift;    // [dim]
+    uint32_t sq_stride;
+    int sq_nbits, sq_metric;
+    float sq_scale, sq_scale_squared, sq_shift_square_norm, sq_mean_norm;
+    uint32_t warp_smem, off_q, off_qd, off_qi, off_cid, off_cd, off_beam, off_qc;
 };
 
-template <int QT>
+// integer cores over one 32-bit word of dense NBITS codes (fields never straddle bytes for 1/2/4/8 bits)
+template <int NBITS>
+__device__ __forceinline__ void sq_word(uint32_t a, uint32_t b, bool want_ip, uint32_t& l2, uint32_t& ip) {
+    if (NBITS == 1) {
+        if (want_ip) ip += __popc(a & b);
+        else l2 += __popc(a ^ b);
+        return;
+    }
+    constexpr uint32_t kMask = NBITS == 8 ? 0xFFFFFFFFu : NBITS == 4 ? 0x0F0F0F0Fu : 0x03030303u;
+#pragma unroll
+    for (int sh = 0; sh < 8; sh += NBITS) {
+        const uint32_t x = (a >> sh) & kMask, y = (b >> sh) & kMask;
+        if (want_ip) {
+            ip = __dp4a(x, y, ip);
+        } else {
+            const uint32_t d = __vabsdiffu4(x, y);
+            l2 = __dp4a(d, d, l2);
+        }
+    }
+}
+
+template <int NBITS>
+__device__ __forceinline__ void sq_row(const uint4* __restrict__ row, const uint4* qc, uint32_t vecs, bool want_ip, uint32_t& l2,
+                                       uint32_t& ip) {
+    for (uint32_t v = 0; v < vecs; ++v) {
+        const uint4 a = __ldg(row + v);
+        const uint4 b = qc[v];
+        sq_word<NBITS>(a.x, b.x, want_ip, l2, ip);
+        sq_word<NBITS>(a.y, b.y, want_ip, l2, ip);
+        sq_word<NBITS>(a.z, b.z, want_ip, l2, ip);
+        sq_word<NBITS>(a.w, b.w, want_ip, l2, ip);
+    }
+}
+
+template <int QT, int MODE>
 __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchParamsPq p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -71,6 +123,8 @@ __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchPa
     uint32_t* cid = reinterpret_cast<uint32_t*>(base + p.off_cid);
     float* cd = reinterpret_cast<float*>(base + p.off_cd);
     uint32_t* beam_ids = reinterpret_cast<uint32_t*>(base + p.off_beam);
+    uint32_t* qc = reinterpret_cast<uint32_t*>(base + p.off_qc);  // MODE 1: the query's packed codes
+    float q_comp = 0.0f;
 
     const uint32_t warp_slot = blockIdx.x * kPqWarps + wib;
     const uint32_t nbk = p.n_buckets;
@@ -81,11 +135,41 @@ __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchPa
     float* lut = p.luts + (size_t)warp_slot * entries;
     const int dim = (int)p.dim;
 
-    // ADC distances of candidates cid[0..n) -> cd[]: one lane per candidate
+    // quantized distances of candidates cid[0..n) -> cd[]: one lane per candidate
     auto adc = [&](uint32_t n) {
         for (uint32_t c0 = 0; c0 < n; c0 += 32) {
             const uint32_t c = c0 + lane;
-            if (c < n) {
+            if (MODE == 1) {
+                if (c < n) {
+                    const uint32_t id = cid[c];
+                    const uint4* row = reinterpret_cast<const uint4*>(p.sq_codes + (size_t)id * p.sq_stride);
+                    const uint4* q4 = reinterpret_cast<const uint4*>(qc);
+                    const uint32_t vecs = p.sq_stride >> 4;
+                    const bool want_ip = p.sq_metric == DAB_INNER_PRODUCT;
+                    uint32_t l2 = 0, ip = 0;
+                    switch (p.sq_nbits) {
+                        case 8: sq_row<8>(row, q4, vecs, want_ip, l2, ip); break;
+                        case 4: sq_row<4>(row, q4, vecs, want_ip, l2, ip); break;
+                        case 2: sq_row<2>(row, q4, vecs, want_ip, l2, ip); break;
+                        default: sq_row<1>(row, q4, vecs, want_ip, l2, ip); break;
+                    }
+                    // epilogues: scalar/vectors.rs:206-237 (L2), 310-376 (IP), 380-460 (CosineNormalized)
+                    const float ibs = __fdiv_rn(1.0f, (float)((1u << p.sq_nbits) - 1u));
+                    const float bit_scale = __fmul_rn(ibs, ibs);
+                    const float mul = __fmul_rn(bit_scale, p.sq_scale_squared);
+                    float r;
+                    if (want_ip) {
+                        const float m = __fadd_rn(__fmaf_rn(mul, (float)ip, p.sq_shift_square_norm), __fadd_rn(__ldg(p.sq_comp + id), q_comp));
+                        r = -m;
+                    } else if (p.sq_metric == DAB_L2) {
+                        r = __fmul_rn(mul, (float)l2);
+                    } else {
+                        const float l = __fmul_rn(mul, (float)l2);
+                        r = __fsub_rn(1.0f, __fsub_rn(1.0f, __fdiv_rn(l, 2.0f)));
+                    }
+                    cd[c] = r;
+                }
+            } else if (c < n) {
                 const uint8_t* code = p.codes + (size_t)cid[c] * p.n_chunks;
                 float accum = 0.0f;
                 uint32_t ch = 0;
@@ -130,7 +214,50 @@ __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchPa
         }
         for (uint32_t i = lane; i < nbk; i += 32) store_empty_bucket(table + (size_t)i * 8);
         __syncwarp();
-        for (uint32_t t = lane; t < entries; t += 32) {
+        if (MODE == 1) {
+            // rescale (scalar/quantizer.rs:300-310): InnerProduct::evaluate(x, x), sqrt, x *= to_norm / norm
+            if (p.sq_metric == DAB_INNER_PRODUCT && p.sq_mean_norm != 0.0f) {
+                float norm = 0.0f;
+                if (lane == 0) norm = __fsqrt_rn(thread_simd_l2ip<KIND_IP>(qf, qf, dim));
+                norm = __shfl_sync(kFull, norm, 0);
+                if (norm != 0.0f) {
+                    const float sc = __fdiv_rn(p.sq_mean_norm, norm);
+                    for (int e = lane; e < dim; e += 32) qf[e] = __fmul_rn(qf[e], sc);
+                }
+                __syncwarp();
+            }
+            // ScalarQuantizer::compress (scalar/quantizer.rs:190-239): codes in parallel ...
+            const float maxv = (float)((1u << p.sq_nbits) - 1u);
+            const float inverse_scale = __fdiv_rn(maxv, p.sq_scale);
+            for (int e = lane; e < dim; e += 32) {
+                const float t = __fmul_rn(__fsub_rn(qf[e], __ldg(p.sq_shift + e)), inverse_scale);
+                const float code = t != t ? t : (t < 0.0f ? 0.0f : (t > maxv ? maxv : t));
+                qf[e] = roundf(code);
+            }
+            __syncwarp();
+            // ... the compensation is one sequential FMA chain over the dimensions (:407-430)
+            if (lane == 0) {
+                float dot = 0.0f;
+                for (int e = 0; e < dim; ++e) dot = __fmaf_rn(qf[e], __ldg(p.sq_shift + e), dot);
+                q_comp = __fmul_rn(__fmul_rn(p.sq_scale, __fdiv_rn(1.0f, maxv)), dot);
+            }
+            q_comp = __shfl_sync(kFull, q_comp, 0);
+            // dense packing, value i at bit i * nbits (bits/slice.rs:261-305); padding words are zero
+            const uint32_t per_word = 32u / (uint32_t)p.sq_nbits;
+            for (uint32_t wd = lane; wd < (p.sq_stride >> 2); wd += 32) {
+                uint32_t acc = 0;
+                for (uint32_t j = 0; j < per_word; ++j) {
+                    const uint32_t e = wd * per_word + j;
+                    if (e < (uint32_t)dim) {
+                        const float c = qf[e];
+                        acc |= (c != c ? 0u : (uint32_t)c) << (j * (uint32_t)p.sq_nbits);
+                    }
+                }
+                qc[wd] = acc;
+            }
+            __syncwarp();
+        }
+        for (uint32_t t = lane; MODE == 0 && t < entries; t += 32) {
             const uint32_t chunk = t / p.n_centers, center = t % p.n_centers;
             const uint32_t start = p.offsets[chunk], stop = p.offsets[chunk + 1];
             const float* piv = p.pivots + (size_t)center * dim + start;
@@ -397,13 +524,19 @@ static int launch_rerank(dab_index* idx, const void* d_queries, uint32_t nq, uin
 }
 
 static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam,
-                         uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cmps, uint32_t* d_hops, bool rerank) {
+                         uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cmps, uint32_t* d_hops, bool rerank,
+                         int mode = 0) {
     if (!idx->graph_ready) return fail(DAB_ERR_NOT_READY, "dab_search_batch_pq: graph must be uploaded first");
-    if (!idx->d_pivots || !idx->d_codes || !idx->pq_codes_ready)
+    if (mode == 0 && (!idx->d_pivots || !idx->d_codes || !idx->pq_codes_ready))
         return fail(DAB_ERR_NOT_READY, "dab_search_batch_pq: no PQ codes (dab_upload_pq with codes, or dab_pq_encode_all)");
+    if (mode == 1 && (!idx->d_sq_codes || !idx->sq_codes_ready))
+        return fail(DAB_ERR_NOT_READY, "dab_search_batch_sq: no scalar-quantized rows (dab_upload_sq with rows, or dab_sq_encode_all)");
     if (k == 0 || l_search == 0 || beam == 0 || beam > 64) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: bad k / l_search / beam_width");
-    if (idx->metric == DAB_COSINE)
+    if (mode == 0 && idx->metric == DAB_COSINE)
         return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: Metric::Cosine traverses with DirectCosine (no table); use dab_pq_distances");
+    // SQStore::distance_computer (providers inmem/scalar.rs:214-226): UnsupportedDistanceMetric
+    if (mode == 1 && idx->metric == DAB_COSINE)
+        return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_sq: the scalar-quantized store supports L2, InnerProduct and CosineNormalized");
     const uint32_t cap = l_search + idx->n_start;
     if (cap > 512) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: L + #start must be <= 512");
     SearchParamsPq p;
@@ -425,6 +558,19 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     p.n_chunks = idx->pq_chunks;
     p.n_centers = idx->pq_centers;
     p.ip_table = idx->metric == DAB_INNER_PRODUCT ? 1 : 0;  // L2 and CosineNormalized use TableL2 (dynamic.rs:80-85)
+    if (mode == 1) {
+        p.sq_codes = idx->d_sq_codes;
+        p.sq_comp = idx->d_sq_comp;
+        p.sq_shift = idx->d_sq_shift;
+        p.sq_stride = idx->sq_stride;
+        p.sq_nbits = idx->sq_nbits;
+        p.sq_metric = idx->metric;
+        p.sq_scale = idx->sq_scale;
+        p.sq_scale_squared = idx->sq_scale * idx->sq_scale;  // AsFunctor (scalar/quantizer.rs:316-335)
+        p.sq_shift_square_norm = idx->sq_shift_square_norm;
+        p.sq_mean_norm = idx->sq_mean_norm;
+        p.n_chunks = 0;
+    }
     p.out_ids = d_ids;
     p.out_dists = d_dists;
     p.out_counts = d_counts;
@@ -446,17 +592,22 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     off += round_up(ncand_max * 4, 16);
     p.off_beam = (uint32_t)off;
     off += round_up((size_t)beam * 4, 16);
+    p.off_qc = (uint32_t)off;
+    if (mode == 1) off += idx->sq_stride;
     p.warp_smem = (uint32_t)round_up(off, 16);
     const size_t smem_block = (size_t)p.warp_smem * kPqWarps;
     if (smem_block > 200 * 1024) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: configuration needs %zu B shared memory per CTA", smem_block);
-    void (*kern)(const SearchParamsPq) = cap <= 128 ? search_kernel_pq<4> : cap <= 256 ? search_kernel_pq<8> : search_kernel_pq<16>;
+    void (*kern)(const SearchParamsPq);
+    if (mode == 1) kern = cap <= 128 ? search_kernel_pq<4, 1> : cap <= 256 ? search_kernel_pq<8, 1> : search_kernel_pq<16, 1>;
+    else kern = cap <= 128 ? search_kernel_pq<4, 0> : cap <= 256 ? search_kernel_pq<8, 0> : search_kernel_pq<16, 0>;
     DAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block));
     int per_sm = 0;
     DAB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPqWarps * 32, smem_block));
     if (per_sm < 1) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: kernel does not fit");
     // every resident warp owns a LUT (n_chunks x n_centers f32: 32 KB at 32 x 256) and a visited table in
     // global memory; ADC terms and probes are L2 hits only while all of them stay L2-resident
-    per_sm = std::min(per_sm, idx->tune.pq_ctas_per_sm ? idx->tune.pq_ctas_per_sm : 6);
+    // (the SQ kernel has no LUT: it keeps the occupancy the shared memory allows unless the knob is set)
+    if (mode == 0 || idx->tune.pq_ctas_per_sm) per_sm = std::min(per_sm, idx->tune.pq_ctas_per_sm ? idx->tune.pq_ctas_per_sm : 6);
     const int grid = (int)std::min<uint64_t>((uint64_t)per_sm * idx->sm_count, ((uint64_t)nq + kPqWarps - 1) / kPqWarps);
     const uint32_t warps = (uint32_t)grid * kPqWarps;
 
@@ -464,7 +615,8 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     // largest visited set seen at this (or a larger) L at 87.5 % load — the estimate is ~10x what a search
     // touches, and every query clears its table; queries that still overflow are re-run below
     uint64_t slots = std::max<uint64_t>(256, (uint64_t)(1.1 * idx->max_degree * 1.3 * (double)l_search) + 1);
-    if (idx->pq_hint_visited > 0 && l_search <= idx->pq_hint_l && beam <= idx->pq_hint_beam && !idx->tune.test_visited_log2) {
+    if (idx->pq_hint_visited > 0 && l_search <= idx->pq_hint_l && beam <= idx->pq_hint_beam && mode == idx->pq_hint_mode &&
+        !idx->tune.test_visited_log2) {
         const uint64_t seen = (uint64_t)(((double)idx->pq_hint_visited * 1.15 + idx->max_degree) / 0.875) + 8;
         slots = std::min(slots, std::max<uint64_t>(256, seen));
     }
@@ -474,7 +626,7 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     uint32_t* d_counters = (uint32_t*)idx->s_counters.p;
     p.counters = d_counters;
     p.overflow_list = d_counters + 4;
-    const size_t lut_bytes = (size_t)warps * idx->pq_chunks * idx->pq_centers * 4;
+    const size_t lut_bytes = mode == 0 ? (size_t)warps * idx->pq_chunks * idx->pq_centers * 4 : 16;
     if ((rc = idx->s_out2.reserve(lut_bytes))) return rc;
     p.luts = (float*)idx->s_out2.p;
     p.n_work = nq;
@@ -500,9 +652,10 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
         uint32_t h[3] = {0, 0, 0};
         DAB_CUDA(cudaMemcpyAsync(h, d_counters, 12, cudaMemcpyDeviceToHost, idx->stream));
         DAB_CUDA(cudaStreamSynchronize(idx->stream));
-        if (l_search != idx->pq_hint_l || beam != idx->pq_hint_beam) {
+        if (l_search != idx->pq_hint_l || beam != idx->pq_hint_beam || mode != idx->pq_hint_mode) {
             idx->pq_hint_l = l_search;
             idx->pq_hint_beam = beam;
+            idx->pq_hint_mode = mode;
             idx->pq_hint_visited = 0;
         }
         idx->pq_hint_visited = std::max(idx->pq_hint_visited, h[2]);
@@ -532,7 +685,8 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
 using namespace dab;
 
 static int search_pq_host(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam_width,
-                          uint32_t* out_ids, float* out_dists, uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops, bool rerank) {
+                          uint32_t* out_ids, float* out_dists, uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops, bool rerank,
+                          int mode = 0) {
     if (!idx) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: idx is NULL");
     if (nq == 0) return DAB_OK;
     if (!queries || !out_ids || !out_dists) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: NULL argument");
@@ -550,7 +704,7 @@ static int search_pq_host(dab_index* idx, const void* queries, uint32_t nq, uint
     uint32_t* d_cmps = d_counts + nq;
     uint32_t* d_hops = d_cmps + nq;
     DAB_CUDA(cudaMemcpyAsync(idx->s_queries.p, queries, qbytes, cudaMemcpyHostToDevice, idx->stream));
-    if ((rc = run_search_pq(idx, idx->s_queries.p, nq, k, l_search, beam_width, d_ids, d_dists, d_counts, d_cmps, d_hops, rerank))) return rc;
+    if ((rc = run_search_pq(idx, idx->s_queries.p, nq, k, l_search, beam_width, d_ids, d_dists, d_counts, d_cmps, d_hops, rerank, mode))) return rc;
     DAB_CUDA(cudaMemcpyAsync(out_ids, d_ids, rbytes, cudaMemcpyDeviceToHost, idx->stream));
     DAB_CUDA(cudaMemcpyAsync(out_dists, d_dists, rbytes, cudaMemcpyDeviceToHost, idx->stream));
     if (out_counts) DAB_CUDA(cudaMemcpyAsync(out_counts, d_counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, idx->stream));
@@ -580,6 +734,21 @@ int dab_search_batch_pq_device(dab_index* idx, const void* d_queries, uint32_t n
     if (!d_queries || !d_out_ids || !d_out_dists) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq_device: NULL argument");
     DAB_CUDA(cudaSetDevice(idx->device));
     return run_search_pq(idx, d_queries, nq, k, l_search, beam_width, d_out_ids, d_out_dists, d_out_counts, d_out_cmps, d_out_hops, rerank != 0);
+}
+
+int dab_search_batch_sq(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam_width,
+                        int rerank, uint32_t* out_ids, float* out_dists, uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops) {
+    return search_pq_host(idx, queries, nq, k, l_search, beam_width, out_ids, out_dists, out_counts, out_cmps, out_hops, rerank != 0, 1);
+}
+
+int dab_search_batch_sq_device(dab_index* idx, const void* d_queries, uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam_width,
+                               int rerank, uint32_t* d_out_ids, float* d_out_dists, uint32_t* d_out_counts, uint32_t* d_out_cmps,
+                               uint32_t* d_out_hops) {
+    if (!idx) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_sq_device: idx is NULL");
+    if (nq == 0) return DAB_OK;
+    if (!d_queries || !d_out_ids || !d_out_dists) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_sq_device: NULL argument");
+    DAB_CUDA(cudaSetDevice(idx->device));
+    return run_search_pq(idx, d_queries, nq, k, l_search, beam_width, d_out_ids, d_out_dists, d_out_counts, d_out_cmps, d_out_hops, rerank != 0, 1);
 }
 
 }  // extern "C"

@@ -285,6 +285,49 @@ class GpuIndex:
         check(_lib.lib().dab_pq_self_distances(self._h, _ptr(a), _ptr(b), a.shape[0], _ptr(out)))
         return out
 
+    # -- scalar-quantized store
+    def upload_sq(self, nbits, shift, scale, shift_square_norm, mean_norm=0.0, rows=None):
+        """SQStore<NBITS>: the quantizer and (optionally) the canonical-front rows
+        (f32 compensation | dense N-bit codes) of every point including the start points."""
+        shift = np.ascontiguousarray(shift, np.float32)
+        if shift.shape != (self.dim,):
+            raise DabError(1, "shift must have dim entries")
+        row_bytes = 4 + (self.dim * nbits + 7) // 8
+        if rows is not None:
+            rows = np.ascontiguousarray(rows, np.uint8)
+            if rows.shape != (self.n_points + self.n_start, row_bytes):
+                raise DabError(1, "rows must be (n_points + n_start) x (4 + ceil(dim * nbits / 8)) bytes")
+        check(_lib.lib().dab_upload_sq(self._h, int(nbits), _ptr(shift), float(scale), float(shift_square_norm),
+                                       float(mean_norm), _ptr(rows) if rows is not None else None))
+        self.sq_nbits = int(nbits)
+
+    def sq_encode_all(self):
+        check(_lib.lib().dab_sq_encode_all(self._h))
+
+    def download_sq(self):
+        rows = np.empty((self.n_points + self.n_start, 4 + (self.dim * self.sq_nbits + 7) // 8), np.uint8)
+        check(_lib.lib().dab_sq_download(self._h, _ptr(rows)))
+        return rows
+
+    def search_batch_sq(self, queries, k, l_search, beam_width=1, rerank=False):
+        """KNN::search through the scalar-quantized accessor; rerank=True adds the full-precision Rerank."""
+        queries = self._queries(queries)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), np.uint32)
+        dists = np.empty((nq, k), np.float32)
+        counts = np.empty(nq, np.uint32)
+        cmps = np.empty(nq, np.uint32)
+        hops = np.empty(nq, np.uint32)
+        check(_lib.lib().dab_search_batch_sq(self._h, _ptr(queries), nq, k, l_search, beam_width, int(bool(rerank)),
+                                             _ptr(ids), _ptr(dists), _ptr(counts), _ptr(cmps), _ptr(hops)))
+        return ids, dists, counts, cmps, hops
+
+    def search_batch_sq_device(self, d_queries, nq, k, l_search, beam_width, d_ids, d_dists, d_counts=0, d_cmps=0, d_hops=0,
+                               rerank=True):
+        check(_lib.lib().dab_search_batch_sq_device(self._h, C.c_void_p(d_queries), nq, k, l_search, beam_width, int(bool(rerank)),
+                                                    C.c_void_p(d_ids), C.c_void_p(d_dists), C.c_void_p(d_counts or None),
+                                                    C.c_void_p(d_cmps or None), C.c_void_p(d_hops or None)))
+
     def pq_encode(self, vectors):
         vectors = np.ascontiguousarray(vectors, np.float32)
         out = np.empty((vectors.shape[0], self.pq_chunks), np.uint8)

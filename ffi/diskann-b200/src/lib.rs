@@ -116,6 +116,28 @@ impl<T: Element> GpuIndex<T> {
         check(unsafe { sys::dab_pq_encode_all(self.raw) })
     }
 
+    /// The scalar-quantized store (`SQStore<NBITS>`): hand over the quantizer, encode every resident row on the device.
+    pub fn set_scalar_quantizer(&mut self, nbits: i32, shift: &[f32], scale: f32, shift_square_norm: f32, mean_norm: Option<f32>) -> Result<()> {
+        assert_eq!(shift.len(), self.dim);
+        check(unsafe {
+            sys::dab_upload_sq(self.raw, nbits, shift.as_ptr(), scale, shift_square_norm, mean_norm.unwrap_or(0.0), std::ptr::null())
+        })?;
+        check(unsafe { sys::dab_sq_encode_all(self.raw) })
+    }
+
+    /// Traversal over the scalar-quantized rows; `rerank` adds `Pipeline<FilterStartPoints, Rerank>`.
+    pub fn search_batch_sq(&self, queries: &[T], k: usize, l_search: u32, beam_width: u32, rerank: bool) -> Result<Batch> {
+        assert_eq!(queries.len() % self.dim, 0);
+        let nq = queries.len() / self.dim;
+        let mut b = Batch { k, ids: vec![0; nq * k], dists: vec![0.0; nq * k], counts: vec![0; nq], cmps: vec![0; nq], hops: vec![0; nq] };
+        check(unsafe {
+            sys::dab_search_batch_sq(self.raw, queries.as_ptr() as *const c_void, nq as u32, k as u32, l_search, beam_width, rerank as i32,
+                                     b.ids.as_mut_ptr(), b.dists.as_mut_ptr(), b.counts.as_mut_ptr(), b.cmps.as_mut_ptr(),
+                                     b.hops.as_mut_ptr())
+        })?;
+        Ok(b)
+    }
+
     /// One process per GPU: join the communicator described by `id` (from `unique_id()` on rank 0) …
     pub fn comm_init(&mut self, id: &[u8; 128], n_ranks: i32, rank: i32) -> Result<()> {
         check(unsafe { sys::dab_comm_init(self.raw, id.as_ptr() as *const _, n_ranks, rank) })

@@ -232,6 +232,35 @@ int dab_sq_distances(int device, int metric, int nbits, float scale_squared, flo
                      uint32_t dim, const uint8_t* x, const float* comp_x, const uint8_t* y,
                      const float* comp_y, uint64_t n, float* out);
 
+/* The scalar-quantized store of an index (diskann-providers/src/model/graph/provider/async_/inmem/
+ * scalar.rs:60-258, SQStore<NBITS>): the quantizer (ScalarQuantizer: shift[dim], scale, and the two
+ * derived fields quantizer.shift_square_norm() and quantizer.mean_norm(), 0 when None) and one row
+ * per point (data + start points) in the reference's canonical-front layout (diskann-quantization/
+ * src/meta/vector.rs:478-507): 4 bytes f32 compensation, then ceil(dim * nbits / 8) bytes of
+ * Dense-packed codes (bits/slice.rs:261-323) — what set_quant_vector (:193-212) stores.  rows may
+ * be NULL when dab_sq_encode_all follows.  nbits in {1, 2, 4, 8}. */
+int dab_upload_sq(dab_index* idx, int nbits, const float* shift, float scale, float shift_square_norm,
+                  float mean_norm, const uint8_t* rows);
+/* SQStore::set_vector (scalar.rs:150-175) for every resident row (any dtype, as_f32 first). */
+int dab_sq_encode_all(dab_index* idx);
+/* rows back in the canonical-front layout: (n_points + n_start) x (4 + ceil(dim * nbits / 8)) */
+int dab_sq_download(dab_index* idx, uint8_t* rows);
+
+/* KNN::search through the scalar-quantized accessor (scalar.rs:449-570): the query is compressed
+ * with the store's quantizer (query_computer, :227-253; rescaled to mean_norm for InnerProduct) and
+ * every traversal distance is Compensated{SquaredL2, IP, CosineNormalized} over the packed codes
+ * (scalar/vectors.rs:206-460; integer cores bits/distances.rs:397, 979).  rerank = 0: the
+ * quant-only strategy (RemoveDeletedIdsAndCopy: first k of the candidate list with their quantized
+ * distances, scalar.rs:640-670); rerank = 1: Pipeline<FilterStartPoints, Rerank> with the
+ * full-precision rows (:596-610).  Metric::Cosine is rejected like SQStore::distance_computer
+ * (:214-226).  Outputs as dab_search_batch. */
+int dab_search_batch_sq(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search,
+                        uint32_t beam_width, int rerank, uint32_t* out_ids, float* out_dists,
+                        uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops);
+int dab_search_batch_sq_device(dab_index* idx, const void* d_queries, uint32_t nq, uint32_t k, uint32_t l_search,
+                               uint32_t beam_width, int rerank, uint32_t* d_out_ids, float* d_out_dists,
+                               uint32_t* d_out_counts, uint32_t* d_out_cmps, uint32_t* d_out_hops);
+
 /* ------------------------------------------------------------------ build-side reuse */
 
 /* PruneAccessor::fill + robust_prune (diskann/src/graph/index.rs:2349-2380, 2565-2650;

@@ -80,7 +80,10 @@ struct QueryDist {
     const void* q;        // prepared query
     std::vector<float> widened;  // f16 query -> f32 (layers/full.rs:421-423)
     std::vector<float> lut;      // PQ table (TableL2 / TableIP)
-    std::vector<float> qf32;     // PQ: f32 view of the query
+    std::vector<float> qf32;     // PQ / SQ: f32 view of the query
+    std::vector<uint8_t> sq_query;          // SQ: the compressed query, one code per byte
+    mutable std::vector<uint8_t> sq_row;    // SQ: unpacked codes of the row being compared
+    float sq_query_comp = 0.0f;
 
     QueryDist(const orc_index* i, const void* query, int fl) : idx(i), flavour(fl) {
         dq = idx->dtype;
@@ -92,7 +95,7 @@ struct QueryDist {
             dq = ORC_F32;
             q = widened.data();
         }
-        if (idx->pq_codes) {
+        if (idx->pq_codes || idx->sq_rows) {
             // providers QuantAccessor: query converted to f32 (T: Into<f32>), then
             // QueryComputer::new (pq/distance/dynamic.rs:63-87)
             qf32.resize(idx->dim);
@@ -104,7 +107,7 @@ struct QueryDist {
                     default: qf32[k] = (float)((const uint8_t*)query)[k]; break;
                 }
             }
-            if (idx->metric != ORC_COSINE) {
+            if (idx->pq_codes && idx->metric != ORC_COSINE) {
                 lut.resize((size_t)idx->pq_chunks * idx->pq_centers);
                 orc_pq_populate_lut(idx->pq_pivots, idx->pq_centers, idx->dim, idx->pq_offsets,
                                     idx->pq_chunks,
@@ -112,9 +115,41 @@ struct QueryDist {
                                     qf32.data(), lut.data());
             }
         }
+        if (idx->sq_rows) {
+            // SQStore::query_computer(query, is_search = true) (providers inmem/scalar.rs:227-253):
+            // for metrics other than L2 / CosineNormalized the query is rescaled to the mean norm
+            // of the training data (scalar/quantizer.rs:165-173, 300-310), then compressed with the
+            // store's own quantizer into a CompensatedVector<NBITS>.
+            if (idx->metric != ORC_L2 && idx->metric != ORC_COSINE_NORMALIZED && idx->sq_mean_norm != 0.0f) {
+                const float norm_square = -orc_distance(flavour, ORC_F32, ORC_F32, ORC_INNER_PRODUCT, qf32.data(),
+                                                        qf32.data(), idx->dim, nullptr);
+                const float norm = std::sqrt(norm_square);
+                if (norm != 0.0f) {
+                    const float s = idx->sq_mean_norm / norm;
+                    for (float& v : qf32) v *= s;
+                }
+            }
+            sq_query.resize(idx->dim);
+            sq_row.resize(idx->dim);
+            sq_query_comp = orc_sq_compress(idx->sq_shift, idx->sq_scale, idx->dim, idx->sq_nbits, qf32.data(),
+                                            sq_query.data(), nullptr);
+        }
     }
 
     float operator()(uint32_t id) const {
+        if (idx->sq_rows) {
+            // QueryComputer::evaluate_similarity (scalar.rs:310-321) -> DistanceComputer (:267-297)
+            const size_t nb = (size_t)idx->sq_nbits, stride = 4 + ((size_t)idx->dim * nb + 7) / 8;
+            const uint8_t* row = idx->sq_rows + (size_t)id * stride;
+            float comp;
+            memcpy(&comp, row, 4);
+            for (uint32_t i = 0; i < idx->dim; ++i) {
+                const size_t bit = (size_t)i * nb;
+                sq_row[i] = (uint8_t)((row[4 + bit / 8] >> (bit % 8)) & ((1u << nb) - 1u));
+            }
+            return orc_sq_distance(idx->metric, idx->sq_nbits, idx->sq_scale * idx->sq_scale, idx->sq_shift_square_norm,
+                                   sq_query.data(), sq_query_comp, sq_row.data(), comp, idx->dim);
+        }
         if (idx->pq_codes) {
             const uint8_t* code = idx->pq_codes + (size_t)id * idx->pq_chunks;
             if (idx->metric == ORC_COSINE)
@@ -232,10 +267,11 @@ void search_internal(const orc_index* idx, const QueryDist& qd, uint32_t l_searc
     std::vector<uint32_t>& list = scratch.list;
     std::vector<Visit>& neighbors = scratch.neighbors;
     // what one distance evaluation reads (the row, or the PQ code of the point)
-    const char* fetch_base = idx->pq_codes ? (const char*)idx->pq_codes : (const char*)idx->vectors;
-    const size_t fetch_stride = idx->pq_codes ? (size_t)idx->pq_chunks : (size_t)idx->row_stride;
+    const size_t sq_stride = idx->sq_rows ? 4 + ((size_t)idx->dim * (size_t)idx->sq_nbits + 7) / 8 : 0;
+    const char* fetch_base = idx->sq_rows ? (const char*)idx->sq_rows : idx->pq_codes ? (const char*)idx->pq_codes : (const char*)idx->vectors;
+    const size_t fetch_stride = idx->sq_rows ? sq_stride : idx->pq_codes ? (size_t)idx->pq_chunks : (size_t)idx->row_stride;
     size_t fetch_bytes = fetch_stride;
-    if (!idx->pq_codes) {
+    if (!idx->pq_codes && !idx->sq_rows) {
         const size_t es = idx->dtype == ORC_F32 ? 4 : idx->dtype == ORC_F16 ? 2 : 1;
         fetch_bytes = (size_t)idx->dim * es;
     }

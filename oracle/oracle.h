@@ -102,6 +102,10 @@ float orc_sq_compress(const float* shift, float scale, size_t dim, int nbits, co
 float orc_sq_distance(int metric, int nbits, float scale_squared, float shift_square_norm,
                       const uint8_t* x, float comp_x, const uint8_t* y, float comp_y, size_t dim);
 
+/* SQStore::set_vector (providers inmem/scalar.rs:150-175): compress `vec` into one canonical-front row
+ * (4 + ceil(dim * nbits / 8) bytes). */
+void orc_sq_encode_row(const float* shift, float scale, size_t dim, int nbits, const float* vec, uint8_t* row);
+
 /* PQ codebook training (diskann-providers/src/index/diskann_async.rs:61-89 -> pq_construction.rs:163-243
  * -> diskann-quantization/src/product/train.rs): per chunk k-means++ (algorithms/kmeans/plusplus.rs)
  * and `lloyds_reps` Lloyd iterations (lloyds.rs), arithmetic in the reference's order; the random draws
@@ -128,6 +132,16 @@ typedef struct orc_index {
     uint32_t pq_chunks;
     uint32_t pq_centers;
     const uint8_t* pq_codes; /* (n_points + n_start) x pq_chunks */
+    /* optional scalar-quantized traversal (providers inmem/scalar.rs QuantAccessor): when
+     * sq_rows != NULL search distances are Compensated{SquaredL2,IP,CosineNormalized} between the
+     * compressed query and the stored rows.  Rows are in the reference's canonical-front layout
+     * (meta/vector.rs:478-507): f32 compensation, then the dense N-bit codes (bits/slice.rs:261-323). */
+    const uint8_t* sq_rows;  /* (n_points + n_start) x (4 + ceil(dim * sq_nbits / 8)) */
+    int sq_nbits;
+    const float* sq_shift;   /* [dim] */
+    float sq_scale;
+    float sq_shift_square_norm;
+    float sq_mean_norm;      /* 0: no rescale (quantizer trained without the mean norm) */
 } orc_index;
 
 /* diskann/src/graph/index.rs:1933-2000 + neighbor/queue.rs:130-318 + knn_search.rs:170-190.

@@ -4,6 +4,7 @@
 #include "oracle.h"
 
 #include <cmath>
+#include <cstring>
 #include <limits>
 #include <vector>
 
@@ -164,6 +165,21 @@ float orc_sq_compress(const float* shift, float scale, size_t dim, int nbits, co
     }
     if (had_nan) *had_nan = nan;
     return scale * inverse_bit_scale * dot;
+}
+
+// SQStore::set_vector -> compress_into(MutCompensatedVectorRef::from_canonical_front_mut):
+// compensation first (meta/vector.rs:495-507), then Dense-packed codes, value i at bit i * nbits
+// (bits/slice.rs:261-305).
+void orc_sq_encode_row(const float* shift, float scale, size_t dim, int nbits, const float* vec, uint8_t* row) {
+    std::vector<uint8_t> codes(dim);
+    const float comp = orc_sq_compress(shift, scale, dim, nbits, vec, codes.data(), nullptr);
+    memcpy(row, &comp, 4);
+    const size_t bytes = (dim * (size_t)nbits + 7) / 8;
+    memset(row + 4, 0, bytes);
+    for (size_t i = 0; i < dim; ++i) {
+        const size_t bit = i * (size_t)nbits;
+        row[4 + bit / 8] |= (uint8_t)(codes[i] << (bit % 8));
+    }
 }
 
 // scalar/vectors.rs:206-237 (CompensatedSquaredL2), :310-376 (CompensatedIP, Result<f32>

@@ -31,6 +31,8 @@ class OrcIndex(C.Structure):
         ("adj", C.c_void_p), ("adj_stride", C.c_uint32),
         ("pq_pivots", C.c_void_p), ("pq_offsets", C.c_void_p), ("pq_chunks", C.c_uint32),
         ("pq_centers", C.c_uint32), ("pq_codes", C.c_void_p),
+        ("sq_rows", C.c_void_p), ("sq_nbits", C.c_int), ("sq_shift", C.c_void_p), ("sq_scale", C.c_float),
+        ("sq_shift_square_norm", C.c_float), ("sq_mean_norm", C.c_float),
     ]
 
 
@@ -74,6 +76,8 @@ def lib():
     L.orc_pq_self_distance.argtypes = [vp, sz, vp, sz, i, vp, vp]
     L.orc_pq_encode.restype = i
     L.orc_pq_encode.argtypes = [vp, sz, sz, vp, sz, vp, vp]
+    L.orc_sq_encode_row.restype = None
+    L.orc_sq_encode_row.argtypes = [vp, f, sz, i, vp, vp]
     L.orc_pq_train.restype = i
     L.orc_pq_train.argtypes = [vp, u64, u32, u32, u32, u32, u64, vp, vp]
     L.orc_sq_compress.restype = f
@@ -145,6 +149,18 @@ def distance_rows(query, rows, metric, flavour=SIMD):
     return out
 
 
+def sq_encode_rows(vectors_f32, shift, scale, nbits):
+    """SQStore::set_vector for every row: canonical-front rows (f32 compensation | dense N-bit codes)."""
+    vectors_f32 = np.ascontiguousarray(vectors_f32, np.float32)
+    shift = np.ascontiguousarray(shift, np.float32)
+    n, dim = vectors_f32.shape
+    rows = np.zeros((n, 4 + (dim * nbits + 7) // 8), np.uint8)
+    L = lib()
+    for i in range(n):
+        L.orc_sq_encode_row(ptr(shift), scale, dim, nbits, ptr(vectors_f32[i]), ptr(rows[i]))
+    return rows
+
+
 def pq_offsets(dim, n_chunks):
     out = np.zeros(n_chunks + 1, np.uint64)
     lib().orc_pq_chunk_offsets(dim, n_chunks, ptr(out))
@@ -163,7 +179,7 @@ def pq_train(data, n_chunks, n_centers=256, lloyds_reps=5, seed=0):
 class Index:
     """Host-side view of an index for the oracle (keeps the numpy arrays alive)."""
 
-    def __init__(self, vectors, adj, n_points, n_start, metric, pq=None):
+    def __init__(self, vectors, adj, n_points, n_start, metric, pq=None, sq=None):
         self.vectors = np.ascontiguousarray(vectors)
         self.adj = np.ascontiguousarray(adj, dtype=np.uint32)
         assert self.vectors.shape[0] == n_points + n_start == self.adj.shape[0]
@@ -189,6 +205,18 @@ class Index:
             s.pq_chunks = self._codes.shape[1]
             s.pq_centers = self._piv.shape[0]
             s.pq_codes = self._codes.ctypes.data
+        if sq is not None:
+            # (rows u8 [n_total, 4 + ceil(dim * nbits / 8)], nbits, shift f32 [dim], scale, shift_square_norm, mean_norm)
+            rows, nbits, shift, scale, ssn, mean_norm = sq
+            self._sq_rows = np.ascontiguousarray(rows, np.uint8)
+            self._sq_shift = np.ascontiguousarray(shift, np.float32)
+            assert self._sq_rows.shape == (n_points + n_start, 4 + (self.vectors.shape[1] * nbits + 7) // 8)
+            s.sq_rows = self._sq_rows.ctypes.data
+            s.sq_nbits = nbits
+            s.sq_shift = self._sq_shift.ctypes.data
+            s.sq_scale = scale
+            s.sq_shift_square_norm = ssn
+            s.sq_mean_norm = mean_norm
         self.c = s
 
     def search_batch(self, queries, k, l_search, beam=1, flavour=AVX2, threads=1):

@@ -569,6 +569,68 @@ def test_pq_traversal_search_identical_to_oracle(dab, dt, metric, d, chunks):
             g.search_batch_pq(f32[:2], 5, 10)  # DirectCosine has no table: rejected loudly
 
 
+def sq_quantizer(f32, metric):
+    """A ScalarQuantizer in the shape of scalar/train.rs: shift below the per-dimension mean, one scale."""
+    mean = f32.mean(0).astype(np.float32)
+    std = float(f32.std())
+    shift = (mean - np.float32(2.5 * std)).astype(np.float32)
+    scale = np.float32(5.0 * std)
+    ssn = np.float32(-O.distance(shift, shift, O.INNER_PRODUCT))  # InnerProduct::evaluate(shift, shift)
+    mean_norm = np.float32(np.linalg.norm(f32, axis=1).mean()) if metric == O.INNER_PRODUCT else np.float32(0)
+    return shift, float(scale), float(ssn), float(mean_norm)
+
+
+@pytest.mark.parametrize("dt,metric,d,nbits", [(np.float32, O.L2, 128, 8), (np.float32, O.L2, 100, 4), (np.float32, O.INNER_PRODUCT, 64, 8),
+                                               (np.float32, O.INNER_PRODUCT, 96, 4), (np.float16, O.COSINE_NORMALIZED, 48, 2),
+                                               (np.uint8, O.L2, 128, 1), (np.int8, O.L2, 72, 2), (np.float32, O.L2, 37, 4)])
+def test_sq_traversal_search_identical_to_oracle(dab, dt, metric, d, nbits):
+    """dab_search_batch_sq: greedy search through the scalar-quantized accessor (providers inmem/scalar.rs:449-570):
+    rows encoded on the device == SQStore::set_vector restated on the CPU (canonical-front layout, dense N-bit codes),
+    and ids / distance bits / cmps / hops == the oracle's search with sq_rows set, with and without Rerank."""
+    rng = np.random.default_rng(d * 10 + nbits)
+    n = 4000
+    vecs, adj, maxdeg = make_index(rng, dt, O.L2 if metric == O.COSINE_NORMALIZED else metric, n, d, 24, 40)
+    f32 = vecs.astype(np.float32)
+    shift, scale, ssn, mean_norm = sq_quantizer(f32, metric)
+    rows = O.sq_encode_rows(f32, shift, scale, nbits)
+    nq = 200
+    queries = vecs[rng.integers(0, n, nq)].copy()
+    if metric == O.INNER_PRODUCT:
+        queries = (queries.astype(np.float32) * rng.uniform(0.3, 3.0, (nq, 1))).astype(vecs.dtype)  # exercise the rescale
+    oidx = O.Index(vecs, adj, n, 1, metric, sq=(rows, nbits, shift, scale, ssn, mean_norm))
+    with dab.GpuIndex(O.dtype_code(vecs), metric, d, n, 1, maxdeg) as g:
+        g.upload_vectors(vecs)
+        g.upload_graph(adj)
+        g.upload_sq(nbits, shift, scale, ssn, mean_norm)
+        with pytest.raises(dab.DabError):
+            g.search_batch_sq(queries[:2], 5, 10)  # no rows yet
+        g.sq_encode_all()
+        assert np.array_equal(g.download_sq(), rows)
+        for (k, Ls, beam) in [(10, 30, 1), (5, 64, 2), (10, 150, 1)]:
+            got = g.search_batch_sq(queries, k, Ls, beam)
+            want = oidx.search_batch(queries, k, Ls, beam=beam, threads=4)
+            for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, k, Ls, beam)
+            if vecs.dtype != np.float16:
+                got = g.search_batch_sq(queries, k, Ls, beam, rerank=True)
+                want = oidx.search_batch_rerank(queries, k, Ls, beam=beam, threads=4)
+                for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
+                    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), ("rerank", name, k, Ls, beam)
+        # rows handed over by the host (set_quant_vector) give the same searches
+        g.upload_sq(nbits, shift, scale, ssn, mean_norm, rows=rows)
+        assert np.array_equal(g.download_sq(), rows)
+        got = g.search_batch_sq(queries, 10, 50, 1)
+        want = oidx.search_batch(queries, 10, 50, beam=1, threads=4)
+        for a, b in zip(got, want):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    with dab.GpuIndex(dab.DType.f32, dab.Metric.Cosine, d, n, 1, maxdeg) as g:
+        g.upload_vectors(f32)
+        g.upload_graph(adj)
+        g.upload_sq(nbits, shift, scale, ssn, mean_norm, rows=rows)
+        with pytest.raises(dab.DabError):
+            g.search_batch_sq(f32[:2], 5, 10)  # SQStore::distance_computer: UnsupportedDistanceMetric
+
+
 @pytest.mark.parametrize("dim,chunks,centers,n", [(24, 5, 32, 3000), (128, 32, 256, 6000), (40, 1, 16, 1500)])
 def test_pq_training_on_the_device_is_bit_identical_to_the_cpu_restatement(dab, dim, chunks, centers, n):
     """train_pq (k-means++ + 5 Lloyd iterations per chunk) and the encoding of every stored row:
