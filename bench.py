@@ -399,9 +399,42 @@ def run_gpu(args):
             dab._lib.check(lib.dab_search_batch(g._h, C.c_void_p(h_q[b].data_ptr()), nq, K, l_search, 1, C.c_void_p(h_ids.data_ptr()),
                                                 C.c_void_p(h_dists.data_ptr()), None, None, None))
 
-    def timed(fn, steps, warmup):
+    # ---- batches in flight (dab_search_batch_async / dab_wait): SLOTS consecutive steps overlap, each on its own
+    # slot (stream + visited tables + result buffers), so the draining tail of one batch is filled by the CTAs of
+    # the next and, end to end, the copies of one batch run under the kernel of another
+    slots = 1 if is_pq else max(1, min(args.in_flight, dab.MAX_SLOTS))
+    sd = [dict(ids=torch.empty((nq, K), dtype=torch.int32, device="cuda"), dists=torch.empty((nq, K), dtype=torch.float32, device="cuda"),
+               counts=torch.empty(nq, dtype=torch.int32, device="cuda"), cmps=torch.empty(nq, dtype=torch.int32, device="cuda"),
+               hops=torch.empty(nq, dtype=torch.int32, device="cuda"),
+               h_ids=torch.empty((nq, K), dtype=torch.int32).pin_memory(), h_dists=torch.empty((nq, K), dtype=torch.float32).pin_memory())
+          for _ in range(slots)] if slots > 1 else []
+
+    def step_device_async():
+        i = step_no[0]
+        step_no[0] += 1
+        s, b = i % slots, i % NB
+        g.wait(s)
+        o = sd[s]
+        g.search_batch_device_async(s, d_q[b].data_ptr(), nq, K, l_search, 1, o["ids"].data_ptr(), o["dists"].data_ptr(),
+                                    o["counts"].data_ptr(), o["cmps"].data_ptr(), o["hops"].data_ptr())
+
+    def step_e2e_async():
+        i = step_no[0]
+        step_no[0] += 1
+        s, b = i % slots, i % NB
+        g.wait(s)
+        o = sd[s]
+        dab._lib.check(lib.dab_search_batch_async(g._h, s, C.c_void_p(h_q[b].data_ptr()), nq, K, l_search, 1,
+                                                  C.c_void_p(o["h_ids"].data_ptr()), C.c_void_p(o["h_dists"].data_ptr()), None, None, None))
+
+    def drain():
+        for s in range(slots):
+            g.wait(s)
+
+    def timed(fn, steps, warmup, drain=lambda: None):
         for _ in range(warmup):
             fn()
+        drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -411,6 +444,7 @@ def run_gpu(args):
         e0.record(stream)
         for _ in range(steps):
             fn()
+        drain()  # joins every batch in flight (host-side wait), so e1 is recorded after the last kernel has finished
         e1.record(stream)
         torch.cuda.synchronize()
         timed.launches = dab.launch_count() - l0
@@ -426,10 +460,17 @@ def run_gpu(args):
     if args.profile_range:  # ncu --profile-from-start off: only the timed region is captured
         torch.cuda.profiler.start()
     step_no[0] = 0
-    ms_dev = timed(step_device, args.steps, args.warmup)
+    ms_dev_serial = timed(step_device, args.steps, args.warmup)
     launches = timed.launches
     step_no[0] = 0
-    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e_serial = timed(step_e2e, args.steps, args.warmup)
+    ms_dev, ms_e2e = ms_dev_serial, ms_e2e_serial
+    if slots > 1:
+        step_no[0] = 0
+        ms_dev = timed(step_device_async, args.steps, args.warmup, drain)
+        launches = timed.launches
+        step_no[0] = 0
+        ms_e2e = timed(step_e2e_async, args.steps, args.warmup, drain)
     if args.profile_range:
         torch.cuda.profiler.stop()
     clocks = sampler.stop() if rank == 0 else None
@@ -444,6 +485,18 @@ def run_gpu(args):
     step_device()
     torch.cuda.synchronize()
     assert np.array_equal(d_ids.cpu().numpy().view(np.uint32), res[0][0]), "device-resident and host C-ABI results differ"
+    if slots > 1:  # what the pipelined loops left in their buffers is the answer of the batch each slot ran last
+        for s_ in range(slots):
+            last = max(i for i in range(args.warmup + args.steps) if i % slots == s_) % NB
+            assert np.array_equal(sd[s_]["h_ids"].numpy().view(np.uint32), res[last][0]), "async host-buffer results differ"
+            assert np.array_equal(sd[s_]["h_dists"].numpy().view(np.uint32), res[last][1].view(np.uint32)), "async host-buffer distances differ"
+        step_no[0] = 0
+        for _ in range(slots):
+            step_device_async()
+        drain()
+        for s_ in range(slots):
+            assert np.array_equal(sd[s_]["ids"].cpu().numpy().view(np.uint32), res[s_ % NB][0]), "async device-resident results differ"
+            assert np.array_equal(sd[s_]["cmps"].cpu().numpy().view(np.uint32), res[s_ % NB][3]), "async device-resident cmps differ"
     if world > 1:  # recall is asserted on the worst rank
         t = torch.tensor([recall], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -494,6 +547,10 @@ def run_gpu(args):
             "parallelism": f"replica x{world}, queries sharded ({args.scaling}), no collective on the search path",
             "l2_policy": f"no flush: index {(n * dim * ELEM[cfg['dtype']] + (n + 1) * 4 * (md + 1)) / 1e6:.0f} MB >> 126 MB L2, "
                          f"{NB} query batches rotate and each step gathers GBs of random rows",
+            "batches_in_flight": slots,
+            "serial": {"ms_per_step": ms_dev_serial / args.steps, "e2e_ms_per_step": ms_e2e_serial / args.steps,
+                       "roofline_frac": alg_bytes / (ms_dev_serial / args.steps / 1e3) / 1e9 / peak,
+                       "note": "one batch at a time (dab_search_batch_device / dab_search_batch): launch, wait, next"},
             "setup_s": dict(t_prep, data=round(t_data, 1), ground_truth=round(t_gt, 2)),
             "l_sweep": sweep, "at_min_l": at_min_l, "parity_gate": parity})
         kernel = ("search_kernel_pq + rerank_kernel" if is_pq else "search_kernel_v3 / v2") + f"<{cfg['dtype']},{cfg['metric'].upper()}>"
@@ -509,7 +566,8 @@ def run_gpu(args):
                          "peak_source": peak_src,
                          "note": f"achieved = algorithmic bytes (cmps*{unit_bytes(cfg)} + hops*{(md + 1) * 4} + query + k*8 per query"
                                  + (" + L rerank rows" if is_pq else "") + ", run's own counters, mean over the rotated batches) "
-                                 "/ CUDA-event step time on this rank"},
+                                 "/ CUDA-event step time on this rank (timed region / steps; with batches_in_flight > 1 "
+                                 "consecutive launches overlap, config.serial has the one-at-a-time figure)"},
         }
         if not args.no_cpu_baseline and world == 1:
             result["cpu_baseline"] = cpu_baseline(cfg, base, medoid, adj_host, pq, batches, gts, l_search)
@@ -726,6 +784,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--n-points", type=int, default=0, help="override the workload's point count (C5-shaped runs)")
     ap.add_argument("--l-search", type=int, default=0, help="skip the sweep and use this L")
+    ap.add_argument("--in-flight", type=int, default=2, help="batches kept in flight by the timed loops (1: one at a time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity gate (tuning runs only)")
     ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed region (for ncu)")

@@ -7,5 +7,7 @@ works anywhere, but every compute entry point needs the CUDA library and a GPU.
 from .index import DabError, DType, GpuIndex, Metric, distance_comparer, launch_count, pair_distances  # noqa: F401
 from ._lib import LIB_PATH, SYMBOLS, lib  # noqa: F401
 
+MAX_SLOTS = 4  # DAB_MAX_SLOTS (include/diskann_b200.h): batches that can be in flight on one index
+
 __all__ = ["DabError", "DType", "GpuIndex", "Metric", "distance_comparer", "launch_count", "pair_distances",
-           "LIB_PATH", "SYMBOLS", "lib"]
+           "LIB_PATH", "SYMBOLS", "lib", "MAX_SLOTS"]

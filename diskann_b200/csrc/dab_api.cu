@@ -81,6 +81,7 @@ void Tuning::load() {
     v3_table_bytes = num("DAB_V3_TABLE_BYTES", 512, 200 * 1024);
     v3_ctas_per_sm = num("DAB_V3_CTAS_PER_SM", 1, 32);
     test_visited_log2 = num("DAB_TEST_VISITED_LOG2", 8, 30);
+    phase_profile = flag("DAB_PHASE_PROFILE");
 }
 
 }  // namespace dab
@@ -121,6 +122,7 @@ int dab_create(dab_index** out, int dtype, int metric, uint32_t dim, uint64_t n_
     idx->row_stride = round_up((size_t)dim * elem_size(dtype), 32);
     idx->adj_stride = (uint32_t)round_up((size_t)max_degree + 1, 8);
     idx->h_stage.pinned_host = true;
+    idx->h_counters.pinned_host = true;
     idx->tune.load();
     cudaError_t e = cudaStreamCreateWithFlags(&idx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -146,8 +148,10 @@ void dab_destroy(dab_index* idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
     if (idx->own_stream) cudaStreamSynchronize(idx->own_stream);
+    search_slots_release(idx);
     comm_release(idx);
     tc_release(idx);
+    cudaFree(idx->d_phase_cycles);
     cudaFree(idx->d_vectors);
     cudaFree(idx->d_adj);
     cudaFree(idx->d_pivots);
@@ -164,6 +168,7 @@ void dab_destroy(dab_index* idx) {
     idx->s_counters.release();
     idx->s_stats.release();
     idx->h_stage.release();
+    idx->h_counters.release();
     if (idx->own_stream) cudaStreamDestroy(idx->own_stream);
     delete idx;
 }

@@ -25,6 +25,7 @@ int fail(int code, const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 void comm_release(struct ::dab_index* idx);  // replicate.cu
 void tc_release(struct ::dab_index* idx);    // flat_tc.cu
+void search_slots_release(struct ::dab_index* idx);  // search_kernel.cu
 
 #define DAB_CUDA(expr)                                                                        \
     do {                                                                                      \
@@ -70,6 +71,7 @@ struct Tuning {
     bool v3_generic = false;       // DAB_V3_GENERIC: generic distance loop also for 32 / 64 / 96 / 128-d f32 rows
     int v3_ctas_per_sm = 0;        // DAB_V3_CTAS_PER_SM: cap on resident CTAs
     int test_visited_log2 = 0;     // DAB_TEST_VISITED_LOG2: tests force the overflow / retry path
+    bool phase_profile = false;    // DAB_PHASE_PROFILE: per-phase cycle sums of search_kernel_v2 (needs a -DDAB_PHASE_PROFILE_BUILD library)
     void load();
 };
 
@@ -113,6 +115,9 @@ struct dab_index {
     // scratch (grow-only)
     dab::Scratch s_queries, s_ids, s_out, s_out2, s_tables, s_counters, s_stats;
     dab::Scratch h_stage;  // pinned host staging
+    dab::Scratch h_counters;  // pinned: the four counters a search pass reports
+    void* slots[DAB_MAX_SLOTS] = {};  // batches in flight (dab_search_batch_async), search_kernel.cu
+    unsigned long long* d_phase_cycles = nullptr;
 
     // search-side state learned across calls
     uint32_t hint_l = 0, hint_beam = 0, hint_visited = 0;  // largest visited set seen at (L, beam)

@@ -402,18 +402,54 @@ static int launch_one(K kern, const dab_index* idx, SearchParams& p, size_t smem
     return DAB_OK;
 }
 
-// Runs the search over work items; device pointers only.  `rec_*` optional.
-int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_rows, uint32_t nq, uint32_t k,
-               uint32_t l_search, uint32_t beam, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cmps,
-               uint32_t* d_hops, uint32_t* rec_ids, float* rec_dists, uint32_t* rec_counts, uint32_t rec_cap) {
-    if (!idx->vectors_ready || !idx->graph_ready) return fail(DAB_ERR_NOT_READY, "search: vectors and graph must be uploaded first");
-    if (k == 0 || l_search == 0 || beam == 0) return fail(DAB_ERR_INVALID_ARGUMENT, "search: k, l_search and beam_width must be > 0");
-    if (beam > 64) return fail(DAB_ERR_INVALID_ARGUMENT, "search: beam_width %u > 64", beam);
-    if (nq == 0) return DAB_OK;
+// ---- one batch of searches as a resumable job ------------------------------------------------
+// A batch is launched (`launch`: kernel + read-back of the four counters into pinned memory, nothing
+// waits) and later completed (`finish`: waits, learns the visited-set size, re-runs the few queries
+// whose visited set outgrew its table).  The synchronous entry points run launch + finish on the
+// handle's stream; dab_search_batch_async / dab_wait keep several batches in flight on slot-owned
+// streams so the tail of one batch (workers running out of queries) is filled by the next batch's
+// CTAs and the host<->device copies of neighbouring batches overlap the kernel.
+struct SearchJob {
+    dab_index* idx = nullptr;
+    cudaStream_t stream = nullptr;
+    Scratch* tables = nullptr;
+    Scratch* counters = nullptr;
+    uint32_t* h_counters = nullptr;  // pinned, 4 words
+    bool use_window = false;         // persisting-L2 window for the generic kernel's tables (default stream only)
+
+    uint32_t nq = 0, l_search = 0, beam = 0;
+    bool recording = false;
+    SearchParams p;
+    SearchParamsV2 p2;
+    SearchParamsV3 p3;
+    void (*kern)(const SearchParams) = nullptr;
+    size_t smem_block = 0;
+    int grid = 0;
+    bool use_v2 = false;
+    V2Launch v2;
+    V3Launch v3;
+    uint64_t slots = 0;
+    int stage = 1;  // 0: search_kernel_v3 pass in flight, 1: global-table pass in flight
+    int pass = 0;
+    Scratch retry_list;
+    uint32_t *d_counters = nullptr, *d_overflow = nullptr;
+
+    int prepare(const void* d_queries, const uint32_t* d_query_rows, uint32_t nq_, uint32_t k, uint32_t l_search_, uint32_t beam_,
+                uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cmps, uint32_t* d_hops, uint32_t* rec_ids,
+                float* rec_dists, uint32_t* rec_counts, uint32_t rec_cap);
+    int launch();
+    int finish();
+    ~SearchJob() { retry_list.release(); }
+};
+
+int SearchJob::prepare(const void* d_queries, const uint32_t* d_query_rows, uint32_t nq_, uint32_t k, uint32_t l_search_,
+                       uint32_t beam_, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cmps, uint32_t* d_hops,
+                       uint32_t* rec_ids, float* rec_dists, uint32_t* rec_counts, uint32_t rec_cap) {
+    nq = nq_, l_search = l_search_, beam = beam_;
+    recording = rec_ids != nullptr;
     const bool is_int = idx->dtype == DAB_I8 || idx->dtype == DAB_U8;
     const MetricPlan plan = plan_for(idx->metric, is_int);
 
-    SearchParams p;
     memset(&p, 0, sizeof(p));
     p.vectors = idx->d_vectors;
     p.row_stride = idx->row_stride;
@@ -454,15 +490,13 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
     p.off_beam = (uint32_t)off;
     off += round_up((size_t)beam * 4, 16);
     p.warp_smem = (uint32_t)off;
-    const size_t smem_block = off * kSearchWarps;
+    smem_block = off * kSearchWarps;
     if (smem_block > 220 * 1024)
         return fail(DAB_ERR_INVALID_ARGUMENT, "search: L=%u, beam=%u, dim=%u need %zu B shared memory per CTA (> 220 KiB)",
                     l_search, beam, idx->dim, smem_block);
 
-    // pick the kernel
-    int grid = 0;
+    // the generic kernel (every dtype / metric / L; also the target of overflow re-runs)
     int rc = DAB_OK;
-    void (*kern)(const SearchParams) = nullptr;
 #define PICK(TD, NA, K, P, II, SG)                               \
     do {                                                         \
         kern = search_kernel<TD, NA, K, P, II, SG>;              \
@@ -492,12 +526,9 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
 #undef PICK_INT
     if (rc) return rc;
 
-    // the latency-restructured kernel covers float rows with NA = 4 schemas; everything else
-    // runs the generic kernel above
-    SearchParamsV2 p2;
+    // the latency-restructured kernel covers the NA = 4 schemas up to L + S = 256
     memset(&p2, 0, sizeof(p2));
-    V2Launch v2;
-    const bool use_v2 = v2_prepare(idx, l_search, beam, p2, v2) == 0;
+    use_v2 = v2_prepare(idx, l_search, beam, p2, v2) == 0;
     if (use_v2) {
         p2.vectors = p.vectors;
         p2.row_stride = p.row_stride;
@@ -525,113 +556,73 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
     }
 
     // visited-table capacity: the reference's estimate (scratch.rs:186-192:
-    // 1.1 * max_degree * 1.3 * L), never more than the index, at least 1024 slots
+    // 1.1 * max_degree * 1.3 * L), never more than the index, at least 256 slots
     double est = 1.1 * idx->max_degree * 1.3 * (double)l_search;
-    if (idx->hint_visited > 0 && l_search <= idx->hint_l && beam <= idx->hint_beam) {
-        // later batches: 1.5x the largest visited set seen at this (or a larger) L, at 75 % load
-        // (visited sets grow monotonically with L); queries that still overflow are re-run
-        // below with a larger table
+    const bool hinted = idx->hint_visited > 0 && l_search <= idx->hint_l && beam <= idx->hint_beam;
+    if (hinted) {
+        // later batches: 1.15x the largest visited set seen at this (or a larger) L (visited sets
+        // grow monotonically with L); queries that still overflow are re-run with a larger table
         const double seen = ((double)idx->hint_visited * 1.15 + idx->max_degree) / (use_v2 ? 0.875 : 0.75) + 8.0;
         if (seen < est) est = seen;
     }
     if (est > (double)idx->n_total() * 1.34) est = (double)idx->n_total() * 1.34;
-    // slots per warp: a power of two for the generic kernel, any multiple of 8 (32-byte buckets)
-    // for v2 so that the tables of all resident warps stay inside the L2
-    uint64_t slots = std::max<uint64_t>(256, (uint64_t)est + 1);
+    slots = std::max<uint64_t>(256, (uint64_t)est + 1);
     if (idx->tune.test_visited_log2) slots = 1ull << idx->tune.test_visited_log2;  // tests force the overflow/retry path
 
-    if ((rc = idx->s_counters.reserve(16 + (size_t)nq * 4))) return rc;
-    uint32_t* d_counters = (uint32_t*)idx->s_counters.p;
-    uint32_t* d_overflow = d_counters + 4;
+    if ((rc = counters->reserve(16 + (size_t)nq * 4))) return rc;
+    d_counters = (uint32_t*)counters->p;
+    d_overflow = d_counters + 4;
     p.counters = d_counters;
     p.overflow_list = d_overflow;
     p.n_work = nq;
     p.query_list = nullptr;
     p2.counters = d_counters;
     p2.overflow_list = d_overflow;
-    Scratch retry_list;  // holds the overflow list of the previous pass
 
-    // ---- first pass with the visited sets in shared memory (search_kernel_v3); queries that
-    // outgrow their table are collected in the overflow list and re-run below on global tables
-    {
-        uint32_t need = 0;
-        if (idx->hint_visited > 0 && l_search <= idx->hint_l && beam <= idx->hint_beam)
-            need = (uint32_t)std::min<double>((double)idx->hint_visited * 1.15, 4.0e9);
-        if (idx->tune.test_visited_log2) need = (1u << idx->tune.test_visited_log2) / 2;
-        const bool skip = idx->v3_overflow_l == l_search && idx->v3_overflow_beam == beam && idx->v3_overflow_frac > 0.25f;
-        SearchParamsV3 p3;
-        memset(&p3, 0, sizeof(p3));
-        V3Launch v3;
-        int which = 0;
-        if (!skip && v3_prepare(idx, l_search, beam, need, p3, v3) == 0) which = 3;
-        if (which) {
-#define DAB_FILL_FIRST(q)                                                                            \
-    do {                                                                                             \
-        q.vectors = p.vectors, q.row_stride = p.row_stride, q.adj = p.adj, q.adj_stride = p.adj_stride; \
-        q.n_points = p.n_points, q.n_start = p.n_start, q.dim = p.dim, q.max_degree = p.max_degree;  \
-        q.queries = p.queries, q.query_rows = p.query_rows, q.query_list = nullptr, q.n_work = nq;   \
-        q.k = p.k, q.cap = p.cap, q.beam = p.beam;                                                   \
-        q.out_ids = p.out_ids, q.out_dists = p.out_dists, q.out_counts = p.out_counts;               \
-        q.out_cmps = p.out_cmps, q.out_hops = p.out_hops;                                            \
-        q.rec_ids = p.rec_ids, q.rec_dists = p.rec_dists, q.rec_counts = p.rec_counts, q.rec_cap = p.rec_cap; \
-        q.counters = d_counters, q.overflow_list = d_overflow;                                       \
-    } while (0)
-            DAB_CUDA(cudaMemsetAsync(d_counters, 0, 16, idx->stream));
-            // persistent workers: size the grid so every resident worker runs the same number of queries
-            {
-                DAB_FILL_FIRST(p3);
-                const uint64_t max_workers = (uint64_t)v3.grid * kV3Warps;
-                const uint64_t rounds = (nq + max_workers - 1) / max_workers;
-                const uint64_t need_warps = (nq + rounds - 1) / rounds;
-                const int launch_grid = (int)((need_warps + kV3Warps - 1) / kV3Warps);
-                v3.kern<<<launch_grid, kV3Warps * 32, v3.smem_block, idx->stream>>>(p3);
-            }
-#undef DAB_FILL_FIRST
-            DAB_LAUNCHED();
-            DAB_CUDA(cudaGetLastError());
-            uint32_t h_counters[4] = {0, 0, 0, 0};
-            DAB_CUDA(cudaMemcpyAsync(h_counters, d_counters, 16, cudaMemcpyDeviceToHost, idx->stream));
-            DAB_CUDA(cudaStreamSynchronize(idx->stream));
-            idx->rec_truncated += h_counters[3];
-            const uint32_t n_over = h_counters[1];
-            if (!rec_ids) {
-                if (l_search != idx->hint_l || beam != idx->hint_beam) {
-                    idx->hint_l = l_search;
-                    idx->hint_beam = beam;
-                    idx->hint_visited = 0;
-                }
-                idx->hint_visited = std::max(idx->hint_visited, h_counters[2]);
-                idx->v3_overflow_l = l_search;
-                idx->v3_overflow_beam = beam;
-                idx->v3_overflow_frac = (float)n_over / (float)nq;
-            }
-            if (n_over == 0) return DAB_OK;
-            if ((rc = retry_list.reserve((size_t)n_over * 4))) return rc;
-            DAB_CUDA(cudaMemcpyAsync(retry_list.p, d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToDevice, idx->stream));
-            DAB_CUDA(cudaStreamSynchronize(idx->stream));
-            p.query_list = (const uint32_t*)retry_list.p;
-            p.n_work = n_over;
-            // the overflowed queries are the largest: size the global tables from the estimate again
-            if (!idx->tune.test_visited_log2)
-                slots = std::max<uint64_t>(slots, std::min<uint64_t>((uint64_t)(1.1 * idx->max_degree * 1.3 * (double)l_search) + 1,
-                                                                        (uint64_t)((double)idx->n_total() * 1.34) + 1));
-        }
+    // first pass with the visited sets in shared memory (search_kernel_v3) where it is the faster
+    // kernel; queries that outgrow their table are re-run on global tables
+    stage = 1;
+    pass = 0;
+    uint32_t need = 0;
+    if (hinted) need = (uint32_t)std::min<double>((double)idx->hint_visited * 1.15, 4.0e9);
+    if (idx->tune.test_visited_log2) need = (1u << idx->tune.test_visited_log2) / 2;
+    const bool skip = idx->v3_overflow_l == l_search && idx->v3_overflow_beam == beam && idx->v3_overflow_frac > 0.25f;
+    memset(&p3, 0, sizeof(p3));
+    if (!skip && v3_prepare(idx, l_search, beam, need, p3, v3) == 0) {
+        stage = 0;
+        p3.vectors = p.vectors, p3.row_stride = p.row_stride, p3.adj = p.adj, p3.adj_stride = p.adj_stride;
+        p3.n_points = p.n_points, p3.n_start = p.n_start, p3.dim = p.dim, p3.max_degree = p.max_degree;
+        p3.queries = p.queries, p3.query_rows = p.query_rows, p3.query_list = nullptr, p3.n_work = nq;
+        p3.k = p.k, p3.cap = p.cap, p3.beam = p.beam;
+        p3.out_ids = p.out_ids, p3.out_dists = p.out_dists, p3.out_counts = p.out_counts;
+        p3.out_cmps = p.out_cmps, p3.out_hops = p.out_hops;
+        p3.rec_ids = p.rec_ids, p3.rec_dists = p.rec_dists, p3.rec_counts = p.rec_counts, p3.rec_cap = p.rec_cap;
+        p3.counters = d_counters, p3.overflow_list = d_overflow;
     }
+    return DAB_OK;
+}
 
-    for (int pass = 0; pass < 6; ++pass) {
+// launch the pass of the current stage and queue the read-back of its counters
+int SearchJob::launch() {
+    DAB_CUDA(cudaMemsetAsync(d_counters, 0, 16, stream));
+    if (stage == 0) {
+        // persistent workers: size the grid so every resident worker runs the same number of queries
+        const uint64_t max_workers = (uint64_t)v3.grid * kV3Warps;
+        const uint64_t rounds = (nq + max_workers - 1) / max_workers;
+        const uint64_t need_warps = (nq + rounds - 1) / rounds;
+        const int launch_grid = (int)((need_warps + kV3Warps - 1) / kV3Warps);
+        v3.kern<<<launch_grid, kV3Warps * 32, v3.smem_block, stream>>>(p3);
+    } else {
+        // slots per warp: a power of two for the generic kernel, any multiple of 8 (32-byte buckets) for v2
         const uint32_t warps = (uint32_t)grid * (use_v2 ? kV2WarpsHost : kSearchWarps);
         const uint32_t hlog = std::max<uint32_t>(use_v2 ? 8 : 10, next_pow2_log2(slots));
         const uint32_t n_buckets = (uint32_t)((slots + 7) / 8);
         const size_t words_per_warp = use_v2 ? (size_t)n_buckets * 8 : ((size_t)1 << hlog);
-        if ((rc = idx->s_tables.reserve((size_t)warps * words_per_warp * 4))) {
-            retry_list.release();
-            return rc;
-        }
-        p.tables = (uint32_t*)idx->s_tables.p;
+        int rc;
+        if ((rc = tables->reserve((size_t)warps * words_per_warp * 4))) return rc;
+        p.tables = (uint32_t*)tables->p;
         p.hcap_log2 = hlog;
-        pin_tables_in_l2(idx, use_v2 ? 0 : (size_t)warps * words_per_warp * 4);
-        DAB_CUDA(cudaMemsetAsync(d_counters, 0, 16, idx->stream));
-        int launch_grid = (int)std::min<uint64_t>((uint64_t)grid, ((uint64_t)p.n_work + kSearchWarps - 1) / kSearchWarps);
+        if (use_window) pin_tables_in_l2(idx, use_v2 ? 0 : (size_t)warps * words_per_warp * 4);
         if (use_v2) {
             // one warp per query, persistent: size the grid so every resident warp runs the same
             // number of queries (10K queries on 3108 slots would otherwise pay for 4 full rounds
@@ -639,68 +630,183 @@ int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_ro
             const uint64_t max_warps = (uint64_t)grid * kV2WarpsHost;
             const uint64_t rounds = (p.n_work + max_warps - 1) / max_warps;
             const uint64_t need = (p.n_work + rounds - 1) / rounds;
-            launch_grid = (int)((need + kV2WarpsHost - 1) / kV2WarpsHost);
+            const int launch_grid = (int)((need + kV2WarpsHost - 1) / kV2WarpsHost);
             p2.phase_cycles = nullptr;
-            if (getenv("DAB_PHASE_PROFILE")) {
-                static unsigned long long* d_phase = nullptr;
-                if (!d_phase) cudaMalloc(&d_phase, 64);
-                cudaMemsetAsync(d_phase, 0, 64, idx->stream);
-                p2.phase_cycles = d_phase;
+            if (idx->tune.phase_profile) {
+                if (!idx->d_phase_cycles) DAB_CUDA(cudaMalloc(&idx->d_phase_cycles, 64));
+                DAB_CUDA(cudaMemsetAsync(idx->d_phase_cycles, 0, 64, stream));
+                p2.phase_cycles = idx->d_phase_cycles;
             }
             p2.tables = p.tables;
             p2.n_buckets = n_buckets;
             p2.query_list = p.query_list;
             p2.n_work = p.n_work;
-            v2.kern<<<launch_grid, kV2WarpsHost * 32, v2.smem_block, idx->stream>>>(p2);
+            v2.kern<<<launch_grid, kV2WarpsHost * 32, v2.smem_block, stream>>>(p2);
         } else {
-            kern<<<launch_grid, kSearchWarps * 32, smem_block, idx->stream>>>(p);
+            const int launch_grid = (int)std::min<uint64_t>((uint64_t)grid, ((uint64_t)p.n_work + kSearchWarps - 1) / kSearchWarps);
+            kern<<<launch_grid, kSearchWarps * 32, smem_block, stream>>>(p);
         }
-        DAB_LAUNCHED();
-        DAB_CUDA(cudaGetLastError());
-        uint32_t h_counters[4] = {0, 0, 0, 0};
-        DAB_CUDA(cudaMemcpyAsync(h_counters, d_counters, 16, cudaMemcpyDeviceToHost, idx->stream));
-        DAB_CUDA(cudaStreamSynchronize(idx->stream));
+    }
+    DAB_LAUNCHED();
+    DAB_CUDA(cudaGetLastError());
+    DAB_CUDA(cudaMemcpyAsync(h_counters, d_counters, 16, cudaMemcpyDeviceToHost, stream));
+    return DAB_OK;
+}
+
+int SearchJob::finish() {
+    for (;;) {
+        DAB_CUDA(cudaStreamSynchronize(stream));
         idx->rec_truncated += h_counters[3];
         const uint32_t n_over = h_counters[1];
-        if (use_v2 && p2.phase_cycles) {
+        const uint32_t n_run = stage == 0 ? nq : p.n_work;
+        if (stage == 1 && use_v2 && p2.phase_cycles) {
             unsigned long long h_ph[8];
-            cudaMemcpy(h_ph, p2.phase_cycles, 64, cudaMemcpyDeviceToHost);
+            DAB_CUDA(cudaMemcpy(h_ph, p2.phase_cycles, 64, cudaMemcpyDeviceToHost));
             const char* names[8] = {"setup", "select", "adj+filter", "bulk-issue", "row-wait", "distance", "insert", "output"};
             unsigned long long tot = 0;
             for (int i = 0; i < 8; ++i) tot += h_ph[i];
-            fprintf(stderr, "[dab phase profile] nq=%u L=%u slots=%llu maxvisited=%u:", p.n_work, l_search, (unsigned long long)slots, h_counters[2]);
+            fprintf(stderr, "[dab phase profile] nq=%u L=%u slots=%llu maxvisited=%u:", n_run, l_search, (unsigned long long)slots, h_counters[2]);
             for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.1f%%", names[i], tot ? 100.0 * h_ph[i] / tot : 0.0);
-            fprintf(stderr, " | cycles/query=%.0f\n", (double)tot / p.n_work);
+            fprintf(stderr, " | cycles/query=%.0f\n", (double)tot / n_run);
         }
-        if (!rec_ids) {  // build-time searches run on a growing graph: do not learn from them
+        if (!recording) {  // build-time searches run on a growing graph: do not learn from them
             if (l_search != idx->hint_l || beam != idx->hint_beam) {
                 idx->hint_l = l_search;
                 idx->hint_beam = beam;
                 idx->hint_visited = 0;
             }
             idx->hint_visited = std::max(idx->hint_visited, h_counters[2]);
+            if (stage == 0) {
+                idx->v3_overflow_l = l_search;
+                idx->v3_overflow_beam = beam;
+                idx->v3_overflow_frac = (float)n_over / (float)nq;
+            }
         }
         if (n_over == 0) {
             retry_list.release();
             return DAB_OK;
         }
-        // re-run the overflowed queries with a 4x larger visited table
+        // re-run the overflowed queries on (larger) global tables
         Scratch next;
-        if ((rc = next.reserve((size_t)n_over * 4))) {
-            retry_list.release();
-            return rc;
-        }
-        DAB_CUDA(cudaMemcpyAsync(next.p, d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToDevice, idx->stream));
-        DAB_CUDA(cudaStreamSynchronize(idx->stream));
+        int rc;
+        if ((rc = next.reserve((size_t)n_over * 4))) return rc;
+        DAB_CUDA(cudaMemcpyAsync(next.p, d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToDevice, stream));
+        DAB_CUDA(cudaStreamSynchronize(stream));
         retry_list.release();
         retry_list = next;
         p.query_list = (const uint32_t*)retry_list.p;
         p.n_work = n_over;
-        slots *= 4;
-        if (slots > 4 * idx->n_total() + 4096) slots = 2 * idx->n_total() + 2048;
+        if (stage == 0) {
+            // the overflowed queries are the largest: size the global tables from the estimate again
+            stage = 1;
+            pass = 0;
+            if (!idx->tune.test_visited_log2)
+                slots = std::max<uint64_t>(slots, std::min<uint64_t>((uint64_t)(1.1 * idx->max_degree * 1.3 * (double)l_search) + 1,
+                                                                        (uint64_t)((double)idx->n_total() * 1.34) + 1));
+        } else {
+            if (++pass >= 6) {
+                retry_list.release();
+                return fail(DAB_ERR_VISITED_OVERFLOW, "search: visited set still overflowing after 6 passes");
+            }
+            slots *= 4;
+            if (slots > 4 * idx->n_total() + 4096) slots = 2 * idx->n_total() + 2048;
+        }
+        if ((rc = launch())) return rc;
     }
-    retry_list.release();
-    return fail(DAB_ERR_VISITED_OVERFLOW, "search: visited set still overflowing after 6 passes");
+}
+
+static int check_search_args(const dab_index* idx, uint32_t k, uint32_t l_search, uint32_t beam) {
+    if (!idx->vectors_ready || !idx->graph_ready) return fail(DAB_ERR_NOT_READY, "search: vectors and graph must be uploaded first");
+    if (k == 0 || l_search == 0 || beam == 0) return fail(DAB_ERR_INVALID_ARGUMENT, "search: k, l_search and beam_width must be > 0");
+    if (beam > 64) return fail(DAB_ERR_INVALID_ARGUMENT, "search: beam_width %u > 64", beam);
+    return DAB_OK;
+}
+
+// Runs the search over work items on the handle's stream and waits; device pointers only.  `rec_*` optional.
+int run_search(dab_index* idx, const void* d_queries, const uint32_t* d_query_rows, uint32_t nq, uint32_t k,
+               uint32_t l_search, uint32_t beam, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cmps,
+               uint32_t* d_hops, uint32_t* rec_ids, float* rec_dists, uint32_t* rec_counts, uint32_t rec_cap) {
+    int rc;
+    if ((rc = check_search_args(idx, k, l_search, beam))) return rc;
+    if (nq == 0) return DAB_OK;
+    if ((rc = idx->h_counters.reserve(16))) return rc;
+    SearchJob job;
+    job.idx = idx;
+    job.stream = idx->stream;
+    job.tables = &idx->s_tables;
+    job.counters = &idx->s_counters;
+    job.h_counters = (uint32_t*)idx->h_counters.p;
+    job.use_window = true;
+    if ((rc = job.prepare(d_queries, d_query_rows, nq, k, l_search, beam, d_ids, d_dists, d_counts, d_cmps, d_hops, rec_ids,
+                          rec_dists, rec_counts, rec_cap)))
+        return rc;
+    if ((rc = job.launch())) return rc;
+    return job.finish();
+}
+
+// ---- batches in flight (dab_search_batch_async / dab_search_batch_device_async / dab_wait) ----
+struct AsyncHostOut {  // host destinations of a pending host-buffer call
+    uint32_t* ids;
+    float* dists;
+    uint32_t *counts, *cmps, *hops;
+    uint32_t nq, k;
+};
+
+struct SearchSlot {
+    cudaStream_t stream = nullptr;
+    Scratch tables, counters, queries, out, stats, h_counters;
+    SearchJob* job = nullptr;
+    AsyncHostOut host_out{};
+    bool has_host_out = false;
+};
+
+void search_slots_release(dab_index* idx) {
+    for (int i = 0; i < DAB_MAX_SLOTS; ++i) {
+        SearchSlot* s = (SearchSlot*)idx->slots[i];
+        if (!s) continue;
+        if (s->stream) cudaStreamSynchronize(s->stream);
+        delete s->job;
+        s->tables.release(), s->counters.release(), s->queries.release(), s->out.release(), s->stats.release(), s->h_counters.release();
+        if (s->stream) cudaStreamDestroy(s->stream);
+        delete s;
+        idx->slots[i] = nullptr;
+    }
+}
+
+static int slot_of(dab_index* idx, uint32_t slot, SearchSlot** out) {
+    if (slot >= DAB_MAX_SLOTS) return fail(DAB_ERR_INVALID_ARGUMENT, "search: slot %u out of range (DAB_MAX_SLOTS = %d)", slot, DAB_MAX_SLOTS);
+    SearchSlot* s = (SearchSlot*)idx->slots[slot];
+    if (!s) {
+        s = new SearchSlot();
+        s->h_counters.pinned_host = true;
+        if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete s;
+            return fail(DAB_ERR_CUDA, "search: cannot create the stream of slot %u", slot);
+        }
+        idx->slots[slot] = s;
+    }
+    *out = s;
+    return DAB_OK;
+}
+
+static int slot_launch(dab_index* idx, SearchSlot* s, const void* d_queries, uint32_t nq, uint32_t k, uint32_t l_search, uint32_t beam,
+                       uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cmps, uint32_t* d_hops) {
+    int rc;
+    if ((rc = s->h_counters.reserve(16))) return rc;
+    SearchJob* job = new SearchJob();
+    job->idx = idx;
+    job->stream = s->stream;
+    job->tables = &s->tables;
+    job->counters = &s->counters;
+    job->h_counters = (uint32_t*)s->h_counters.p;
+    if ((rc = job->prepare(d_queries, nullptr, nq, k, l_search, beam, d_ids, d_dists, d_counts, d_cmps, d_hops, nullptr, nullptr,
+                           nullptr, 0)) ||
+        (rc = job->launch())) {
+        delete job;
+        return rc;
+    }
+    s->job = job;
+    return DAB_OK;
 }
 
 }  // namespace dab
@@ -748,6 +854,90 @@ int dab_search_batch(dab_index* idx, const void* queries, uint32_t nq, uint32_t 
     if (out_cmps) DAB_CUDA(cudaMemcpyAsync(out_cmps, d_cmps, (size_t)nq * 4, cudaMemcpyDeviceToHost, idx->stream));
     if (out_hops) DAB_CUDA(cudaMemcpyAsync(out_hops, d_hops, (size_t)nq * 4, cudaMemcpyDeviceToHost, idx->stream));
     DAB_CUDA(cudaStreamSynchronize(idx->stream));
+    return DAB_OK;
+}
+
+// ---- asynchronous batches: launch on a slot, collect with dab_wait ---------------------------
+// Host-buffer flavour: the queries are copied from `queries` on the slot's stream (pinned memory makes
+// the copy asynchronous), the kernel follows, and the results are copied into the host outputs; all of
+// it is queued by this call when no query can overflow its visited table on the way, i.e. nothing waits.
+// dab_wait(slot) blocks until the slot's batch is complete (and, in the rare overflow case, re-runs the
+// affected queries and repeats the result copies).  The buffers must stay valid until dab_wait returns.
+static int queue_result_copies(SearchSlot* s, const AsyncHostOut& o) {
+    const size_t rbytes = (size_t)o.nq * o.k * 4;
+    uint32_t* d_ids = (uint32_t*)s->out.p;
+    float* d_dists = (float*)((uint8_t*)s->out.p + rbytes);
+    uint32_t* d_counts = (uint32_t*)s->stats.p;
+    DAB_CUDA(cudaMemcpyAsync(o.ids, d_ids, rbytes, cudaMemcpyDeviceToHost, s->stream));
+    DAB_CUDA(cudaMemcpyAsync(o.dists, d_dists, rbytes, cudaMemcpyDeviceToHost, s->stream));
+    if (o.counts) DAB_CUDA(cudaMemcpyAsync(o.counts, d_counts, (size_t)o.nq * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (o.cmps) DAB_CUDA(cudaMemcpyAsync(o.cmps, d_counts + o.nq, (size_t)o.nq * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (o.hops) DAB_CUDA(cudaMemcpyAsync(o.hops, d_counts + 2 * (size_t)o.nq, (size_t)o.nq * 4, cudaMemcpyDeviceToHost, s->stream));
+    return DAB_OK;
+}
+
+int dab_search_batch_async(dab_index* idx, uint32_t slot, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search,
+                           uint32_t beam_width, uint32_t* out_ids, float* out_dists, uint32_t* out_counts, uint32_t* out_cmps,
+                           uint32_t* out_hops) {
+    if (!idx) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_async: idx is NULL");
+    if (nq && (!queries || !out_ids || !out_dists)) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_async: NULL argument");
+    int rc;
+    if ((rc = check_search_args(idx, k, l_search, beam_width))) return rc;
+    DAB_CUDA(cudaSetDevice(idx->device));
+    SearchSlot* s = nullptr;
+    if ((rc = slot_of(idx, slot, &s))) return rc;
+    if (s->job) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_async: slot %u still has a batch in flight (call dab_wait)", slot);
+    if (nq == 0) return DAB_OK;
+    const size_t qbytes = (size_t)nq * idx->dim * elem_size(idx->dtype);
+    const size_t rbytes = (size_t)nq * k * 4;
+    if ((rc = s->queries.reserve(qbytes))) return rc;
+    if ((rc = s->out.reserve(2 * rbytes))) return rc;
+    if ((rc = s->stats.reserve((size_t)nq * 12))) return rc;
+    uint32_t* d_ids = (uint32_t*)s->out.p;
+    float* d_dists = (float*)((uint8_t*)s->out.p + rbytes);
+    uint32_t* d_counts = (uint32_t*)s->stats.p;
+    DAB_CUDA(cudaMemcpyAsync(s->queries.p, queries, qbytes, cudaMemcpyHostToDevice, s->stream));
+    if ((rc = slot_launch(idx, s, s->queries.p, nq, k, l_search, beam_width, d_ids, d_dists, d_counts, d_counts + nq, d_counts + 2 * (size_t)nq)))
+        return rc;
+    s->host_out = AsyncHostOut{out_ids, out_dists, out_counts, out_cmps, out_hops, nq, k};
+    s->has_host_out = true;
+    // optimistic copies: valid as they are unless a query overflowed (then dab_wait repeats them)
+    return queue_result_copies(s, s->host_out);
+}
+
+int dab_search_batch_device_async(dab_index* idx, uint32_t slot, const void* d_queries, uint32_t nq, uint32_t k, uint32_t l_search,
+                                  uint32_t beam_width, uint32_t* d_out_ids, float* d_out_dists, uint32_t* d_out_counts,
+                                  uint32_t* d_out_cmps, uint32_t* d_out_hops) {
+    if (!idx) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_device_async: idx is NULL");
+    if (nq && (!d_queries || !d_out_ids || !d_out_dists)) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_device_async: NULL argument");
+    int rc;
+    if ((rc = check_search_args(idx, k, l_search, beam_width))) return rc;
+    DAB_CUDA(cudaSetDevice(idx->device));
+    SearchSlot* s = nullptr;
+    if ((rc = slot_of(idx, slot, &s))) return rc;
+    if (s->job) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_device_async: slot %u still has a batch in flight (call dab_wait)", slot);
+    if (nq == 0) return DAB_OK;
+    s->has_host_out = false;
+    return slot_launch(idx, s, d_queries, nq, k, l_search, beam_width, d_out_ids, d_out_dists, d_out_counts, d_out_cmps, d_out_hops);
+}
+
+int dab_wait(dab_index* idx, uint32_t slot) {
+    if (!idx) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_wait: idx is NULL");
+    if (slot >= DAB_MAX_SLOTS) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_wait: slot %u out of range (DAB_MAX_SLOTS = %d)", slot, DAB_MAX_SLOTS);
+    SearchSlot* s = (SearchSlot*)idx->slots[slot];
+    if (!s || !s->job) return DAB_OK;
+    DAB_CUDA(cudaSetDevice(idx->device));
+    SearchJob* job = s->job;
+    s->job = nullptr;
+    DAB_CUDA(cudaStreamSynchronize(s->stream));
+    const bool overflowed = job->h_counters[1] != 0;
+    int rc = job->finish();
+    delete job;
+    if (rc) return rc;
+    if (overflowed && s->has_host_out) {
+        if ((rc = queue_result_copies(s, s->host_out))) return rc;
+        DAB_CUDA(cudaStreamSynchronize(s->stream));
+    }
     return DAB_OK;
 }
 

@@ -84,6 +84,7 @@ class GpuIndex:
 
     def __init__(self, dtype, metric, dim, n_points, n_start=1, max_degree=83, device=0):
         self._h = C.c_void_p()
+        self._inflight = {}  # slot -> (queries, outputs) kept alive while a batch is in flight
         self.dtype, self.metric, self.dim = DType(dtype), Metric(metric), int(dim)
         self.n_points, self.n_start, self.max_degree, self.device = int(n_points), int(n_start), int(max_degree), device
         check(_lib.lib().dab_create(C.byref(self._h), int(dtype), int(metric), dim, n_points, n_start, max_degree, device))
@@ -238,6 +239,31 @@ class GpuIndex:
         check(_lib.lib().dab_search_batch_device(self._h, C.c_void_p(d_queries), nq, k, l_search, beam_width,
                                                  C.c_void_p(d_ids), C.c_void_p(d_dists), C.c_void_p(d_counts or None),
                                                  C.c_void_p(d_cmps or None), C.c_void_p(d_hops or None)))
+
+    def search_batch_async(self, slot, queries, k, l_search, beam_width=1, out=None):
+        """Queue a batch on `slot` (host buffers) and return its output arrays without waiting; they are
+        valid after wait(slot).  `queries` is used as passed (it must stay alive and unchanged until then);
+        `out` = (ids, dists, counts, cmps, hops) re-uses caller-owned (e.g. pinned) arrays."""
+        nq = queries.shape[0]
+        if out is None:
+            out = (np.empty((nq, k), np.uint32), np.empty((nq, k), np.float32), np.empty(nq, np.uint32),
+                   np.empty(nq, np.uint32), np.empty(nq, np.uint32))
+        ids, dists, counts, cmps, hops = out
+        check(_lib.lib().dab_search_batch_async(self._h, slot, _ptr(queries), nq, k, l_search, beam_width, _ptr(ids), _ptr(dists),
+                                                _ptr(counts), _ptr(cmps), _ptr(hops)))
+        self._inflight[slot] = (queries, out)
+        return out
+
+    def search_batch_device_async(self, slot, d_queries, nq, k, l_search, beam_width, d_ids, d_dists, d_counts=0, d_cmps=0, d_hops=0):
+        """Device-pointer flavour of search_batch_async; results stay in HBM."""
+        check(_lib.lib().dab_search_batch_device_async(self._h, slot, C.c_void_p(d_queries), nq, k, l_search, beam_width,
+                                                       C.c_void_p(d_ids), C.c_void_p(d_dists), C.c_void_p(d_counts or None),
+                                                       C.c_void_p(d_cmps or None), C.c_void_p(d_hops or None)))
+
+    def wait(self, slot):
+        """Join the batch in flight on `slot` (no-op when idle)."""
+        check(_lib.lib().dab_wait(self._h, slot))
+        return self._inflight.pop(slot, (None, None))[1]
 
     # -- PQ
     def pq_populate_lut(self, queries, metric=None):

@@ -96,6 +96,19 @@ impl<T: Element> GpuIndex<T> {
         Ok(b)
     }
 
+    /// Queue a batch on `slot` without waiting (`search_all`'s one task per partition, api.rs:410-419, mapped to
+    /// device slots).  The returned guard borrows the queries and owns the result buffers; `InFlight::wait` joins it.
+    pub fn search_batch_async<'a>(&'a self, slot: u32, queries: &'a [T], k: usize, l_search: u32, beam_width: u32) -> Result<InFlight<'a, T>> {
+        assert_eq!(queries.len() % self.dim, 0);
+        let nq = queries.len() / self.dim;
+        let mut b = Batch { k, ids: vec![0; nq * k], dists: vec![0.0; nq * k], counts: vec![0; nq], cmps: vec![0; nq], hops: vec![0; nq] };
+        check(unsafe {
+            sys::dab_search_batch_async(self.raw, slot, queries.as_ptr() as *const c_void, nq as u32, k as u32, l_search, beam_width,
+                                        b.ids.as_mut_ptr(), b.dists.as_mut_ptr(), b.counts.as_mut_ptr(), b.cmps.as_mut_ptr(), b.hops.as_mut_ptr())
+        })?;
+        Ok(InFlight { index: self, slot, batch: Some(b), _queries: queries })
+    }
+
     /// PQ traversal + the providers' full-precision `Rerank` (what `use_fp_for_search: false` runs).
     pub fn search_batch_pq_rerank(&self, queries: &[T], k: usize, l_search: u32, beam_width: u32) -> Result<Batch> {
         assert_eq!(queries.len() % self.dim, 0);
@@ -146,6 +159,30 @@ impl<T: Element> GpuIndex<T> {
     /// … and replicate the resident snapshot from `root` (one NCCL broadcast per buffer, at load).
     pub fn broadcast_index(&mut self, root: i32) -> Result<()> {
         check(unsafe { sys::dab_broadcast_index(self.raw, root) })
+    }
+}
+
+/// A batch in flight on one slot of the device.  Dropping it joins the slot (the library writes into the
+/// buffers it owns until then).
+pub struct InFlight<'a, T: Element> {
+    index: &'a GpuIndex<T>,
+    slot: u32,
+    batch: Option<Batch>,
+    _queries: &'a [T],
+}
+
+impl<'a, T: Element> InFlight<'a, T> {
+    pub fn wait(mut self) -> Result<Batch> {
+        check(unsafe { sys::dab_wait(self.index.raw, self.slot) })?;
+        Ok(self.batch.take().expect("joined once"))
+    }
+}
+
+impl<'a, T: Element> Drop for InFlight<'a, T> {
+    fn drop(&mut self) {
+        if self.batch.is_some() {
+            unsafe { sys::dab_wait(self.index.raw, self.slot) };
+        }
     }
 }
 

@@ -169,6 +169,27 @@ int dab_search_batch_device(dab_index* idx, const void* d_queries, uint32_t nq, 
                             float* d_out_dists, uint32_t* d_out_counts, uint32_t* d_out_cmps,
                             uint32_t* d_out_hops);
 
+/* Batches in flight.  The reference keeps every core busy by handing each query to a task of a
+ * thread pool (diskann-benchmark-core/src/search/api.rs:410-419: `search_all` spawns one task per
+ * query partition and joins them); the device equivalent is to keep more than one BATCH in flight:
+ * `dab_search_batch_async` queues the copy of the queries, the search and the copy of the results
+ * on a stream owned by `slot` (0 <= slot < DAB_MAX_SLOTS) and returns without waiting, `dab_wait`
+ * joins the slot.  Batches on different slots overlap: the host<->device copies of one run under
+ * the kernel of another, and the CTAs of the next batch fill the SMs that the draining tail of the
+ * previous one leaves idle.  Results, statistics and error behaviour are those of dab_search_batch;
+ * the host buffers (pinned memory makes the copies asynchronous) and the device buffers of the
+ * `_device_` flavour must stay valid and untouched until `dab_wait(slot)` returns.  A slot holds
+ * one batch at a time (DAB_ERR_INVALID_ARGUMENT otherwise); waiting on an idle slot is a no-op. */
+#define DAB_MAX_SLOTS 4
+int dab_search_batch_async(dab_index* idx, uint32_t slot, const void* queries, uint32_t nq, uint32_t k,
+                           uint32_t l_search, uint32_t beam_width, uint32_t* out_ids, float* out_dists,
+                           uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops);
+int dab_search_batch_device_async(dab_index* idx, uint32_t slot, const void* d_queries, uint32_t nq, uint32_t k,
+                                  uint32_t l_search, uint32_t beam_width, uint32_t* d_out_ids,
+                                  float* d_out_dists, uint32_t* d_out_counts, uint32_t* d_out_cmps,
+                                  uint32_t* d_out_hops);
+int dab_wait(dab_index* idx, uint32_t slot);
+
 /* ------------------------------------------------------------------ product quantization */
 
 /* FixedChunkPQTable::populate_chunk_distances / populate_chunk_inner_products

@@ -25,6 +25,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "diskann_b200.h"
@@ -189,9 +190,36 @@ class GpuKNN {
         return r;
     }
 
+    // Batches in flight (search_all's one task per query partition, api.rs:410-419, as slots of the device):
+    // `search_async` queues a batch on `slot` and returns at once, `wait` joins it and returns its results.
+    // `queries` must stay valid until then.
+    void search_async(uint32_t slot, const T* queries, uint32_t nq, uint32_t k) {
+        if (slot >= DAB_MAX_SLOTS) throw ANNError(DAB_ERR_INVALID_ARGUMENT, "slot out of range");
+        Pending& s = pending_[slot];
+        s.r.nq = nq;
+        s.r.k = k;
+        s.r.ids.resize((size_t)nq * k);
+        s.r.distances.resize((size_t)nq * k);
+        s.counts.resize(nq), s.cmps.resize(nq), s.hops.resize(nq);
+        check(dab_search_batch_async(p_.raw(), slot, queries, nq, k, l_, beam_, s.r.ids.data(), s.r.distances.data(), s.counts.data(),
+                                     s.cmps.data(), s.hops.data()));
+    }
+    KnnResults wait(uint32_t slot) {
+        check(dab_wait(p_.raw(), slot));
+        Pending& s = pending_[slot];
+        s.r.stats.resize(s.r.nq);
+        for (uint32_t i = 0; i < s.r.nq; ++i) s.r.stats[i] = SearchStats{s.cmps[i], s.hops[i], s.counts[i]};
+        return std::move(s.r);
+    }
+
    private:
+    struct Pending {
+        KnnResults r;
+        std::vector<uint32_t> counts, cmps, hops;
+    };
     Provider<T>& p_;
     uint32_t l_, beam_;
+    Pending pending_[DAB_MAX_SLOTS];
 };
 
 }  // namespace diskann_b200
