@@ -78,6 +78,9 @@ void Tuning::load() {
     frontier_narrow = flag("DAB_FRONTIER_NARROW");
     v2_stage_bytes = num("DAB_V2_STAGE_BYTES", 1024, 65536);
     v2_ctas_per_sm = num("DAB_V2_CTAS_PER_SM", 1, 64);
+    v2_slots = num("DAB_V2_SLOTS", 256, 1 << 24);
+    v2_full_grid = flag("DAB_V2_FULL_GRID");
+    v2_t1_bytes = getenv("DAB_V2_T1_BYTES") ? num("DAB_V2_T1_BYTES", 0, 64 * 1024) : -1;
     v3_table_bytes = num("DAB_V3_TABLE_BYTES", 512, 200 * 1024);
     v3_ctas_per_sm = num("DAB_V3_CTAS_PER_SM", 1, 32);
     test_visited_log2 = num("DAB_TEST_VISITED_LOG2", 8, 30);

@@ -64,6 +64,9 @@ struct Tuning {
     bool frontier_narrow = false;  // DAB_FRONTIER_NARROW: 4-byte-load frontier kernel
     int v2_stage_bytes = 0;        // DAB_V2_STAGE_BYTES
     int v2_ctas_per_sm = 0;        // DAB_V2_CTAS_PER_SM
+    int v2_t1_bytes = -1;          // DAB_V2_T1_BYTES: shared-memory level of search_kernel_v2's visited set, bytes per warp (0: off; default 4096)
+    bool v2_full_grid = false;     // DAB_V2_FULL_GRID: launch every resident worker instead of balancing the rounds per worker
+    int v2_slots = 0;              // DAB_V2_SLOTS: cap on the visited-table slots per warp (smaller tables, more overflow re-runs)
     int v3_table_bytes = 0;        // DAB_V3_TABLE_BYTES: visited-table bytes per warp
     bool tc_resident = false;      // DAB_TC_RESIDENT: tensor-core scan keeps the query tile in shared memory (measured equal to streaming it)
     int pq_ctas_per_sm = 0;        // DAB_PQ_CTAS_PER_SM: resident CTAs (4 warps) per SM of the PQ traversal kernel (default 6)

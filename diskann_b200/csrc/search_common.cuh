@@ -174,4 +174,46 @@ __device__ __forceinline__ void tag16_of(uint32_t id, const Tag16Map& m, uint32_
     bucket = h - tag * m.nbk;                              // h % nbk
 }
 
+
+// Probe of a shared-memory tag table (same layout and rules as smem16_insert, search_smem.cuh: 16 tags per
+// 32-byte bucket, slots fill upwards, an entry displaced to the d-th following bucket (d <= 2) carries d in
+// its top two bits, 0xFFFF = empty).  Returns 0: the id is in the table; 1: it was absent and has been
+// inserted; 2: it is absent and was not inserted (`allow_insert` false, or its three buckets are full).
+__device__ __forceinline__ int tag16_probe(uint32_t* table, uint32_t n_buckets, uint32_t b, uint32_t tag, bool allow_insert) {
+    uint32_t d = 0;
+    for (;;) {
+        uint32_t* bp = table + (size_t)b * 8;
+        const uint4 lo = reinterpret_cast<const uint4*>(bp)[0];
+        const uint4 hi = reinterpret_cast<const uint4*>(bp)[1];
+        const uint32_t s[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        const uint32_t want = (d << 14) | tag, want2 = want * 0x10001u;
+        // "some 16-bit half of x is zero" <=> ((x - 0x00010001) & ~x & 0x80008000) != 0
+        uint32_t hit = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t x = s[k] ^ want2;
+            hit |= (x - 0x00010001u) & ~x & 0x80008000u;
+        }
+        if (hit) return 0;
+        // first word with a free (upper) half: slots fill in order
+        int ew = -1;
+        uint32_t old = 0;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            if ((s[k] >> 16) == 0xFFFFu) {
+                ew = k;
+                old = s[k];
+            }
+        }
+        if (ew >= 0) {
+            if (!allow_insert) return 2;
+            const uint32_t neu = (old & 0xFFFFu) == 0xFFFFu ? (0xFFFF0000u | want) : ((old & 0xFFFFu) | (want << 16));
+            if (atomicCAS(bp + ew, old, neu) == old) return 1;
+            continue;  // another lane of this warp changed the word: look at the bucket again
+        }
+        if (++d > 2) return 2;
+        b = b + 1 == n_buckets ? 0 : b + 1;
+    }
+}
+
 }  // namespace dab

@@ -416,6 +416,7 @@ struct SearchJob {
     Scratch* counters = nullptr;
     uint32_t* h_counters = nullptr;  // pinned, 4 words
     bool use_window = false;         // persisting-L2 window for the generic kernel's tables (default stream only)
+    bool full_grid = false;          // batches in flight: launch every resident worker (the next batch fills what this one leaves)
 
     uint32_t nq = 0, l_search = 0, beam = 0;
     bool recording = false;
@@ -568,6 +569,7 @@ int SearchJob::prepare(const void* d_queries, const uint32_t* d_query_rows, uint
     if (est > (double)idx->n_total() * 1.34) est = (double)idx->n_total() * 1.34;
     slots = std::max<uint64_t>(256, (uint64_t)est + 1);
     if (idx->tune.test_visited_log2) slots = 1ull << idx->tune.test_visited_log2;  // tests force the overflow/retry path
+    if (idx->tune.v2_slots && use_v2 && slots > (uint64_t)idx->tune.v2_slots) slots = (uint64_t)idx->tune.v2_slots;
 
     if ((rc = counters->reserve(16 + (size_t)nq * 4))) return rc;
     d_counters = (uint32_t*)counters->p;
@@ -630,7 +632,8 @@ int SearchJob::launch() {
             const uint64_t max_warps = (uint64_t)grid * kV2WarpsHost;
             const uint64_t rounds = (p.n_work + max_warps - 1) / max_warps;
             const uint64_t need = (p.n_work + rounds - 1) / rounds;
-            const int launch_grid = (int)((need + kV2WarpsHost - 1) / kV2WarpsHost);
+            int launch_grid = (int)((need + kV2WarpsHost - 1) / kV2WarpsHost);
+            if (idx->tune.v2_full_grid || full_grid) launch_grid = (int)std::min<uint64_t>((uint64_t)grid, ((uint64_t)p.n_work + kV2WarpsHost - 1) / kV2WarpsHost);
             p2.phase_cycles = nullptr;
             if (idx->tune.phase_profile) {
                 if (!idx->d_phase_cycles) DAB_CUDA(cudaMalloc(&idx->d_phase_cycles, 64));
@@ -799,6 +802,7 @@ static int slot_launch(dab_index* idx, SearchSlot* s, const void* d_queries, uin
     job->tables = &s->tables;
     job->counters = &s->counters;
     job->h_counters = (uint32_t*)s->h_counters.p;
+    job->full_grid = true;
     if ((rc = job->prepare(d_queries, nullptr, nq, k, l_search, beam, d_ids, d_dists, d_counts, d_cmps, d_hops, nullptr, nullptr,
                            nullptr, 0)) ||
         (rc = job->launch())) {

@@ -44,7 +44,6 @@ constexpr int kGroup = 8;  // rows reduced together
 #ifndef DAB_V2_F32X2
 #define DAB_V2_F32X2 1     // packed FADD2 / FFMA2 distance arithmetic
 #endif
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -207,7 +206,28 @@ __device__ __forceinline__ void group_distance_int(const uint8_t* __restrict__ q
 }
 #endif
 
-template <typename TD, int KIND, int POST, int QT>
+// Rare paths of the two-level visited set: clearing the warp's global table when its first id arrives, and the
+// atomic insert.  (The kernel is sensitive to its code size — at ~100 KB of SASS every phase ran ~20 % slower than at
+// 60 KB — so the hot loop is kept compact: one rolled loop over a row's chunks, no unrolled copies of these.)
+__device__ __forceinline__ void clear_global_table(uint32_t* table, uint32_t nbk, int lane) {
+#pragma unroll 1
+    for (uint32_t i = lane; i < nbk; i += 32) store_empty_bucket(table + (size_t)i * 8);
+    __syncwarp();
+}
+__device__ __forceinline__ bool global_table_insert(uint32_t* table, uint32_t nbk, uint32_t id) {
+    uint32_t bs[8];
+    const uint32_t b = bucket_of(id, nbk);
+    load_bucket(table + (size_t)b * 8, bs);
+    return bucket_insert(table, nbk, b, bs, id);
+}
+
+// L1 = true: two-level visited set.  Level 1 is a table of 16-bit quotient tags in the warp's own shared memory
+// (tag16_probe, search_common.cuh); an id lives in exactly one level: level 1 while it has room for it (its three
+// buckets not full, table not closed at 87.5 % load), otherwise level 2, this warp's global table.  A probe asks level 1
+// first and only an id that is neither found nor placed there goes on to the global table — for most queries never,
+// so their visited set costs no global traffic at all; the global table is cleared when its first id arrives.
+// L1 = false: the global table alone (ids too wide for 14-bit tags at the table size, or level 1 disabled).
+template <typename TD, int KIND, int POST, int QT, bool L1>
 #ifndef DAB_V2_MIN_CTAS
 #define DAB_V2_MIN_CTAS 21
 #endif
@@ -225,6 +245,10 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
     const uint32_t rows_a = smem_u32(rows);
     uint32_t* adjbuf = reinterpret_cast<uint32_t*>(base + p.off_adj);
     const uint32_t adjbuf_a = smem_u32(adjbuf);
+
+    uint32_t* t1 = reinterpret_cast<uint32_t*>(base + p.off_t1);
+    const uint32_t nb1 = p.t1_buckets;
+    const Tag16Map tmap{p.tag_kmask, nb1, p.tag_magic, p.tag_shift};
 
     const uint32_t warp_slot = blockIdx.x * kV2Warps + wib;
     const uint32_t nbk = p.n_buckets;
@@ -275,7 +299,12 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
             {
                 for (int e = lane; e < dim; e += 32) qf[e] = to_f32(s[e]);
             }
-            for (uint32_t i = lane; i < nbk; i += 32) store_empty_bucket(table + (size_t)i * 8);
+            if constexpr (L1) {
+                const uint4 e4 = make_uint4(kEmptyV2, kEmptyV2, kEmptyV2, kEmptyV2);
+                for (uint32_t i = lane; i < nb1 * 2; i += 32) reinterpret_cast<uint4*>(t1)[i] = e4;
+            } else {
+                for (uint32_t i = lane; i < nbk; i += 32) store_empty_bucket(table + (size_t)i * 8);
+            }
         }
         __syncwarp();
 #if DAB_V2_INT_BUILD
@@ -287,8 +316,35 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
         DAB_PHASE(0);  // query staging + table clear
 
         uint32_t size = 0, cursor_lo = 0, cmps = 0, hops = 0, nvisited = 0, nrec = 0;
+        uint32_t n1 = 0;          // ids held by level 1 (nvisited counts those of the global table when L1 is on)
+        bool closed = false;      // level 1 takes no more ids
+        bool l2_used = false;     // the global table has been cleared for this query and may hold ids
         uint32_t pred = kEmptyV2;  // node whose adjacency row sits in adjbuf
         bool overflow = false;
+
+        // HashSet::insert of one id per lane through both levels (`ok`: this lane has an id); whole warp calls
+        auto visit_l1 = [&](uint32_t id, bool ok) -> bool {
+            bool ins = false, need = false;
+            if (ok) {
+                uint32_t b1, tg;
+                tag16_of(id, tmap, b1, tg);
+                const int r = tag16_probe(t1, nb1, b1, tg, !closed);
+                ins = r == 1;
+                need = r == 2;
+            }
+            n1 += __popc(__ballot_sync(kFull, ins));
+            if (__any_sync(kFull, need)) {  // rare
+                if (!l2_used) {
+                    clear_global_table(table, nbk, lane);
+                    l2_used = true;
+                }
+                bool ins2 = false;
+                if (need) ins2 = global_table_insert(table, nbk, id);
+                nvisited += __popc(__ballot_sync(kFull, ins2));
+                ins |= ins2;
+            }
+            return ins;
+        };
 
 
         // stage `n` candidate rows (ids cid[c0..)) with per-lane 16 B async copies and compute
@@ -355,7 +411,11 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
         // ---- start points (SearchAccessor::start_point_distances, provider.rs:406-433)
         for (uint32_t s0 = 0; s0 < p.n_start; s0 += 32) {
             const uint32_t n = min(32u, p.n_start - s0);
-            if ((uint32_t)lane < n) {
+            if constexpr (L1) {
+                const uint32_t id = (uint32_t)p.n_points + s0 + lane;
+                if ((uint32_t)lane < n) cid[lane] = id;
+                visit_l1(id, (uint32_t)lane < n);
+            } else if ((uint32_t)lane < n) {
                 const uint32_t id = (uint32_t)p.n_points + s0 + lane;
                 cid[lane] = id;
                 uint32_t bs[8];
@@ -366,7 +426,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
             __syncwarp();
             for (uint32_t c0 = 0; c0 < n; c0 += p.stage_rows) distances(c0, min(p.stage_rows, n - c0));
             merge_round<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, 0, n, lane);
-            nvisited += n;
+            if constexpr (!L1) nvisited += n;
             cmps += n;
         }
 
@@ -437,45 +497,61 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                     }
                 }
                 const uint32_t deg = min(__shfl_sync(kFull, wd[0], 0), p.max_degree);
-                // bucket probes of all three chunks in flight together
-                bool valid[3];
-                uint32_t bk[3];
-                uint32_t bs[3][8];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const uint32_t j = c * 32 + lane;
-                    valid[c] = j >= 1 && j <= deg;
-                    bk[c] = bucket_of(wd[c], nbk);
-                    if (valid[c]) load_bucket(table + (size_t)bk[c] * 8, bs[c]);
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    bool inserted = false;
-                    if (valid[c]) inserted = bucket_insert(table, nbk, bk[c], bs[c], wd[c]);
-                    const bool isnew = inserted && wd[c] < n_total;  // is_in_bounds
-                    const unsigned mi = __ballot_sync(kFull, inserted);
-                    const unsigned mn = __ballot_sync(kFull, isnew);
-                    if (isnew) cid[ncand + __popc(mn & ((1u << lane) - 1u))] = wd[c];
-                    ncand += __popc(mn);
-                    nvisited += __popc(mi);
-                }
-                // adjacency rows longer than 95 neighbours: remaining chunks
-                for (uint32_t c0 = 96; c0 < deg + 1; c0 += 32) {
-                    const uint32_t j = c0 + lane;
-                    const uint32_t word = j < p.adj_stride ? __ldg(row + j) : kEmptyV2;
-                    bool inserted = false;
-                    if (j <= deg) {
-                        const uint32_t b2 = bucket_of(word, nbk);
-                        uint32_t bs2[8];
-                        load_bucket(table + (size_t)b2 * 8, bs2);
-                        inserted = bucket_insert(table, nbk, b2, bs2, word);
+                if constexpr (L1) {
+                    // one compact loop over the row's chunks of 32 neighbours (the first three sit in registers)
+#pragma unroll 1
+                    for (uint32_t c0 = 0; c0 <= deg; c0 += 32) {
+                        const uint32_t j = c0 + lane;
+                        uint32_t word = c0 == 0 ? wd[0] : (c0 == 32 ? wd[1] : wd[2]);
+                        if (c0 >= 96) word = j < p.adj_stride ? __ldg(row + j) : kEmptyV2;
+                        const bool ins = visit_l1(word, j >= 1 && j <= deg);
+                        const bool isnew = ins && word < n_total;  // is_in_bounds
+                        const unsigned mn = __ballot_sync(kFull, isnew);
+                        if (isnew) cid[ncand + __popc(mn & ((1u << lane) - 1u))] = word;
+                        ncand += __popc(mn);
                     }
-                    const bool isnew = inserted && word < n_total;
-                    const unsigned mi = __ballot_sync(kFull, inserted);
-                    const unsigned mn = __ballot_sync(kFull, isnew);
-                    if (isnew) cid[ncand + __popc(mn & ((1u << lane) - 1u))] = word;
-                    ncand += __popc(mn);
-                    nvisited += __popc(mi);
+                    if (!closed && n1 + p.max_degree > p.t1_limit) closed = true;
+                } else {
+                // bucket probes of all three chunks in flight together
+                    bool valid[3];
+                    uint32_t bk[3];
+                    uint32_t bs[3][8];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const uint32_t j = c * 32 + lane;
+                        valid[c] = j >= 1 && j <= deg;
+                        bk[c] = bucket_of(wd[c], nbk);
+                        if (valid[c]) load_bucket(table + (size_t)bk[c] * 8, bs[c]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        bool inserted = false;
+                        if (valid[c]) inserted = bucket_insert(table, nbk, bk[c], bs[c], wd[c]);
+                        const bool isnew = inserted && wd[c] < n_total;  // is_in_bounds
+                        const unsigned mi = __ballot_sync(kFull, inserted);
+                        const unsigned mn = __ballot_sync(kFull, isnew);
+                        if (isnew) cid[ncand + __popc(mn & ((1u << lane) - 1u))] = wd[c];
+                        ncand += __popc(mn);
+                        nvisited += __popc(mi);
+                    }
+                    // adjacency rows longer than 95 neighbours: remaining chunks
+                    for (uint32_t c0 = 96; c0 < deg + 1; c0 += 32) {
+                        const uint32_t j = c0 + lane;
+                        const uint32_t word = j < p.adj_stride ? __ldg(row + j) : kEmptyV2;
+                        bool inserted = false;
+                        if (j <= deg) {
+                            const uint32_t b2 = bucket_of(word, nbk);
+                            uint32_t bs2[8];
+                            load_bucket(table + (size_t)b2 * 8, bs2);
+                            inserted = bucket_insert(table, nbk, b2, bs2, word);
+                        }
+                        const bool isnew = inserted && word < n_total;
+                        const unsigned mi = __ballot_sync(kFull, inserted);
+                        const unsigned mn = __ballot_sync(kFull, isnew);
+                        if (isnew) cid[ncand + __popc(mn & ((1u << lane) - 1u))] = word;
+                        ncand += __popc(mn);
+                        nvisited += __popc(mi);
+                    }
                 }
                 if (nvisited + p.max_degree > hlimit) {  // the next node could pass the load limit: stop expanding now
                     overflow = true;
@@ -527,7 +603,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
                 p.out_dists[(size_t)qidx * p.k + i] = __int_as_float(0x7F800000);
             }
             if (lane == 0) {
-                atomicMax(p.counters + 2, nvisited);
+                atomicMax(p.counters + 2, n1 + nvisited);
                 if (p.out_counts) p.out_counts[qidx] = count;
                 if (p.out_cmps) p.out_cmps[qidx] = cmps;
                 if (p.out_hops) p.out_hops[qidx] = hops;
@@ -599,11 +675,40 @@ int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchPar
     p.stage_rows = stage;
     p.row_bytes = row_bytes;
     p.row_slot = row_slot;
-    p.warp_smem = (uint32_t)round_up(fixed + (size_t)stage * row_slot, 128);
+    // level-1 visited table: 4 KB of 16-bit tags per warp (2048 slots; the mean visited set of the headline
+    // workload is ~1200 ids) when the ids fit 14-bit quotient tags, i.e. n_total <= 16384 * buckets
+    size_t t1_bytes = idx->tune.v2_t1_bytes >= 0 ? (size_t)idx->tune.v2_t1_bytes : (idx->tune.test_visited_log2 ? 512 : 4096);  // tests: a level 1 that fills at once
+    t1_bytes = t1_bytes / 32 * 32;
+    p.t1_buckets = 0;
+    if (t1_bytes >= 512) {
+        uint32_t K = 8;
+        while (((uint64_t)1 << K) < idx->n_total()) ++K;
+        const uint64_t nb1 = t1_bytes / 32;
+        uint32_t sbits = 0;
+        while (((uint64_t)1 << sbits) < nb1) ++sbits;
+        if ((((uint64_t)1 << K) + 16383) >> 14 <= nb1 && K + sbits <= 32) {
+            p.t1_buckets = (uint32_t)nb1;
+            p.t1_limit = (uint32_t)(nb1 * 14);
+            p.tag_kmask = (uint32_t)(((uint64_t)1 << K) - 1);
+            p.tag_shift = K + sbits;
+            p.tag_magic = (uint32_t)((((uint64_t)1 << (K + sbits)) + nb1 - 1) / nb1);
+        }
+    }
+    p.off_t1 = (uint32_t)round_up(fixed + (size_t)stage * row_slot, 32);
+    // level 1 pays for itself only while enough warps stay resident: at C2 (24 -> 20 one-warp CTAs per SM) it removes
+    // the table traffic (8.8 -> 5.3 GB of DRAM traffic per 10K queries) and is 2 % faster, at C3 (12 -> 10) it is 11 % slower
+    if (p.t1_buckets && idx->tune.v2_t1_bytes < 0 && (227 * 1024) / (round_up((size_t)p.off_t1 + t1_bytes, 128) * kV2Warps + 1024) * kV2Warps < 16)
+        p.t1_buckets = 0;
+    if (!p.t1_buckets) t1_bytes = 0;
+    p.warp_smem = (uint32_t)round_up((size_t)p.off_t1 + t1_bytes, 128);
     out.smem_block = (size_t)p.warp_smem * kV2Warps;
     if (out.smem_block > 200 * 1024) return 1;
 
-#define PICK2(TD, K, P, Q) out.kern = search_kernel_v2<TD, K, P, Q>
+#define PICK2(TD, K, P, Q)                                              \
+    do {                                                                \
+        if (p.t1_buckets) out.kern = search_kernel_v2<TD, K, P, Q, true>; \
+        else out.kern = search_kernel_v2<TD, K, P, Q, false>;           \
+    } while (0)
 #define PICK_Q(TD, K, P)                 \
     do {                                 \
         if (cap <= 128) PICK2(TD, K, P, 4); \

@@ -32,6 +32,10 @@ struct SearchParamsV2 {
     uint32_t* out_hops;
     uint32_t* tables;
     uint32_t n_buckets;   // visited table: buckets of 8 ids (32 B) per warp, any count >= 16
+    // level 1 of the visited set: per-warp table of 16-bit quotient tags in shared memory (search_common.cuh)
+    uint32_t t1_buckets;  // buckets of 16 tags (0: off — ids too wide for 14-bit tags, or disabled)
+    uint32_t t1_limit;    // ids after which level 1 takes no more (87.5 % of its slots)
+    uint32_t tag_kmask, tag_magic, tag_shift, off_t1;
     uint32_t* counters;
     uint32_t* overflow_list;
     uint32_t* rec_ids;

@@ -275,6 +275,44 @@ def test_visited_table_overflow_is_retried_exactly(dab, monkeypatch):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+@pytest.mark.parametrize("force_overflow", [False, True])
+def test_batches_in_flight_match_the_oracle(dab, monkeypatch, force_overflow):
+    """dab_search_batch_async / dab_wait: several batches queued on different slots before any is joined
+    return what the synchronous call (and the oracle) returns — also when every query of a batch outgrows
+    its visited table and is re-run inside dab_wait — and the slot rules hold (one batch per slot, idle wait)."""
+    rng = np.random.default_rng(15)
+    n, d = 5000, 32
+    vecs, adj, maxdeg = make_index(rng, np.float32, O.L2, n, d, 24, 40)
+    oidx = O.Index(vecs, adj, n, 1, O.L2)
+    batches = [clustered(rng, m, d) for m in (200, 64, 333, 1)]
+    want = [oidx.search_batch(q, 10, 60, threads=4) for q in batches]
+    if force_overflow:
+        monkeypatch.setenv("DAB_TEST_VISITED_LOG2", "8")
+    with dab.GpuIndex(dab.DType.f32, dab.Metric.L2, d, n, 1, maxdeg) as g:
+        g.upload_vectors(vecs)
+        g.upload_graph(adj)
+        g.wait(2)  # idle slot: no-op
+        for rounds in range(2):  # slots are reusable
+            outs = [g.search_batch_async(s, q, 10, 60) for s, q in enumerate(batches)]
+            with pytest.raises(dab.DabError):
+                g.search_batch_async(1, batches[1], 10, 60)  # slot 1 still has a batch in flight
+            for s in (2, 0, 3, 1):
+                g.wait(s)
+            for got, w in zip(outs, want):
+                for a, b in zip(got, w):
+                    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        with pytest.raises(dab.DabError):
+            g.search_batch_async(dab.MAX_SLOTS, batches[0], 10, 60)
+        # interleaved with the synchronous call on the handle's own stream
+        out = g.search_batch_async(0, batches[0], 10, 60)
+        sync = g.search_batch(batches[2], 10, 60)
+        g.wait(0)
+        for a, b in zip(out, want[0]):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        for a, b in zip(sync, want[2]):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 # ---------------------------------------------------------------- product quantization
 
 def trained_pq(rng, base, chunks, centers=256):
