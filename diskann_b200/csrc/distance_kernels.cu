@@ -260,6 +260,84 @@ frontier_int_kernel(const uint8_t* __restrict__ queries, uint32_t nq, const uint
     }
 }
 
+// Integer rows, wide loads: eight lanes own one row (16 B each per 128-byte step), so one warp instruction
+// requests four rows and eight rows are in flight per pass (a 128-byte i8 row is ONE request of the warp instead of
+// a quarter of four).  Integer sums are exact in any order (wrapping i32, as warp_int_multi), so the lane split
+// is free; the three xor-shuffles reduce within the team.  Needs dim % 16 == 0 (rows are 32-byte aligned).
+template <bool SIGNED, int KIND, int POST>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+frontier_int_wide_kernel(const uint8_t* __restrict__ queries, uint32_t nq, const uint32_t* __restrict__ ids, uint32_t c,
+                         const uint8_t* __restrict__ vectors, size_t row_stride, uint64_t n_total, int dim,
+                         float* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int TILE = 32, ROWS = 4, PASS = 2;  // rows per load instruction, load instructions in flight
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int team = lane >> 3, tl = lane & 7;
+    uint8_t* q = smem + (size_t)wib * dim;
+    const uint32_t tiles_per_q = (c + TILE - 1) / TILE;
+    const uint64_t total_tiles = (uint64_t)nq * tiles_per_q;
+    const uint64_t nwarps = (uint64_t)gridDim.x * kWarpsPerBlock;
+    for (uint64_t t = (uint64_t)blockIdx.x * kWarpsPerBlock + wib; t < total_tiles; t += nwarps) {
+        const uint32_t qi = (uint32_t)(t / tiles_per_q);
+        const uint32_t j0 = (uint32_t)(t % tiles_per_q) * TILE;
+        __syncwarp();
+        for (int e = lane * 16; e < dim; e += 512)
+            *reinterpret_cast<uint4*>(q + e) = __ldg(reinterpret_cast<const uint4*>(queries + (size_t)qi * dim + e));
+        __syncwarp();
+        const int qq = KIND == KIND_IP ? 0 : warp_int_self<SIGNED>(q, dim, lane);
+        const uint32_t jend = min(j0 + TILE, c);
+        for (uint32_t j = j0; j < jend; j += ROWS * PASS) {
+            uint32_t id[PASS];
+            bool ok[PASS];
+            const uint8_t* row[PASS];
+            int xy[PASS], yy[PASS];
+#pragma unroll
+            for (int u = 0; u < PASS; ++u) {
+                const uint32_t jj = j + u * ROWS + team;
+                id[u] = jj < jend ? ids[(size_t)qi * c + jj] : kNoId;
+                ok[u] = id[u] != kNoId && id[u] < n_total;
+                row[u] = vectors + (size_t)(ok[u] ? id[u] : 0) * row_stride;
+                xy[u] = yy[u] = 0;
+            }
+            for (int e = tl * 16; e < dim; e += 128) {
+                const uint4 x = *reinterpret_cast<const uint4*>(q + e);
+                uint4 y[PASS];
+#pragma unroll
+                for (int u = 0; u < PASS; ++u) y[u] = __ldg(reinterpret_cast<const uint4*>(row[u] + e));
+#pragma unroll
+                for (int u = 0; u < PASS; ++u) {
+                    xy[u] = dp4<SIGNED>((int)x.x, (int)y[u].x, xy[u]);
+                    xy[u] = dp4<SIGNED>((int)x.y, (int)y[u].y, xy[u]);
+                    xy[u] = dp4<SIGNED>((int)x.z, (int)y[u].z, xy[u]);
+                    xy[u] = dp4<SIGNED>((int)x.w, (int)y[u].w, xy[u]);
+                    if (KIND != KIND_IP) {
+                        yy[u] = dp4<SIGNED>((int)y[u].x, (int)y[u].x, yy[u]);
+                        yy[u] = dp4<SIGNED>((int)y[u].y, (int)y[u].y, yy[u]);
+                        yy[u] = dp4<SIGNED>((int)y[u].z, (int)y[u].z, yy[u]);
+                        yy[u] = dp4<SIGNED>((int)y[u].w, (int)y[u].w, yy[u]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PASS; ++u) {
+#pragma unroll
+                for (int m = 1; m < 8; m <<= 1) {
+                    xy[u] += __shfl_xor_sync(kFull, xy[u], m);
+                    if (KIND != KIND_IP) yy[u] += __shfl_xor_sync(kFull, yy[u], m);
+                }
+                const uint32_t jj = j + u * ROWS + team;
+                if (tl == 0 && jj < jend) {
+                    float r;
+                    if (KIND == KIND_IP) r = (float)xy[u];
+                    else if (KIND == KIND_L2) r = (float)(int)((unsigned)qq + (unsigned)yy[u] - 2u * (unsigned)xy[u]);
+                    else r = cosine_finish((float)qq, (float)yy[u], (float)xy[u]);
+                    out[(size_t)qi * c + jj] = ok[u] ? post_op<POST>(r) : __int_as_float(0x7FC00000);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ data x data pairs by id
 template <typename T, int NA, int KIND, int POST>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -441,6 +519,22 @@ int launch_frontier(const dab_index* idx, const void* d_queries, uint32_t nq, co
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                   \
             kern<<<grid, block, smem, st>>>((const __half*)d_queries, ARGS);                                      \
         }                                                                                                         \
+    } while (0)
+        DAB_KIND_POST_SWITCH(plan, L);
+#undef L
+    } else if (is_int && dim % 16 == 0 && ((uintptr_t)d_queries & 15) == 0 && !idx->tune.frontier_narrow) {
+        const size_t ismem = (size_t)kWarpsPerBlock * dim;
+#define L(K, P)                                                                                   \
+    do {                                                                                          \
+        if (idx->dtype == DAB_I8) {                                                               \
+            auto kern = frontier_int_wide_kernel<true, K, P>;                                     \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem);  \
+            kern<<<grid, block, ismem, st>>>((const uint8_t*)d_queries, ARGS);                    \
+        } else {                                                                                  \
+            auto kern = frontier_int_wide_kernel<false, K, P>;                                    \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem);  \
+            kern<<<grid, block, ismem, st>>>((const uint8_t*)d_queries, ARGS);                    \
+        }                                                                                         \
     } while (0)
         DAB_KIND_POST_SWITCH(plan, L);
 #undef L

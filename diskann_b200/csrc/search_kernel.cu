@@ -529,7 +529,7 @@ int SearchJob::prepare(const void* d_queries, const uint32_t* d_query_rows, uint
 
     // the latency-restructured kernel covers the NA = 4 schemas up to L + S = 256
     memset(&p2, 0, sizeof(p2));
-    use_v2 = v2_prepare(idx, l_search, beam, p2, v2) == 0;
+    use_v2 = v2_prepare(idx, l_search, beam, full_grid, p2, v2) == 0;
     if (use_v2) {
         p2.vectors = p.vectors;
         p2.row_stride = p.row_stride;

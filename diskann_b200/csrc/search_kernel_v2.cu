@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, DAB_V2_MIN_CTAS) search_kernel_
 // ------------------------------------------------------------------ host side
 // Returns 1 when this configuration is not covered by v2 (caller falls back to v1), 0 on
 // success with `out` filled, or a negative DAB error code.
-int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchParamsV2& p, V2Launch& out) {
+int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, bool level1, SearchParamsV2& p, V2Launch& out) {
     if (idx->tune.disable_v2) return 1;
 #if DAB_V2_INT_BUILD
     const bool v2_int = idx->dtype == DAB_I8 || idx->dtype == DAB_U8;
@@ -697,6 +697,9 @@ int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchPar
     p.off_t1 = (uint32_t)round_up(fixed + (size_t)stage * row_slot, 32);
     // level 1 pays for itself only while enough warps stay resident: at C2 (24 -> 20 one-warp CTAs per SM) it removes
     // the table traffic (8.8 -> 5.3 GB of DRAM traffic per 10K queries) and is 2 % faster, at C3 (12 -> 10) it is 11 % slower
+    // ... and while batches overlap: one batch at a time is dominated by its tail, where the 4 resident warps fewer
+    // cost more (2.96 vs 2.67 ms) than the traffic saves
+    if (p.t1_buckets && idx->tune.v2_t1_bytes < 0 && !level1) p.t1_buckets = 0;
     if (p.t1_buckets && idx->tune.v2_t1_bytes < 0 && (227 * 1024) / (round_up((size_t)p.off_t1 + t1_bytes, 128) * kV2Warps + 1024) * kV2Warps < 16)
         p.t1_buckets = 0;
     if (!p.t1_buckets) t1_bytes = 0;

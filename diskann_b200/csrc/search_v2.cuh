@@ -59,6 +59,7 @@ struct V2Launch {
 
 // Returns 1 when this configuration is not covered by v2 (caller falls back to the generic
 // kernel), 0 on success with `out` filled, or a negative DAB error code.
-int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, SearchParamsV2& p, V2Launch& out);
+// `level1`: give the visited set its shared-memory level (see search_kernel_v2.cu) when the configuration allows it.
+int v2_prepare(const dab_index* idx, uint32_t l_search, uint32_t beam, bool level1, SearchParamsV2& p, V2Launch& out);
 
 }  // namespace dab

@@ -226,6 +226,11 @@ def test_search_batch_identical_to_oracle(dab, dt, metric, d, n, R, Lb):
             want = oidx.search_batch(queries, k, L, beam=beam, threads=4)
             for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
                 assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, k, L, beam)
+            # batches in flight run the two-level visited set (shared-memory tags first): same answer
+            out = g.search_batch_async(1, queries, k, L, beam)
+            g.wait(1)
+            for a, b, name in zip(out, want, ("ids", "dists", "counts", "cmps", "hops")):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), ("in flight", name, k, L, beam)
 
 
 def test_search_edge_cases(dab):
