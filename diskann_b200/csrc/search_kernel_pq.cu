@@ -54,6 +54,7 @@ struct SearchParamsPq {
     const uint8_t* codes;
     uint32_t n_chunks, n_centers;
     int ip_table;  // 1: TableIP (entries -dot), 0: TableL2
+    int direct_cosine;  // 1: Metric::Cosine -> QueryComputer::DirectCosine (no table): resumable cosine over the gathered pivot chunks
     float* luts;   // [warps][n_chunks * n_centers]
     uint32_t* out_ids;
     float* out_dists;
@@ -169,6 +170,31 @@ __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchPa
                     }
                     cd[c] = r;
                 }
+            } else if (p.direct_cosine) {
+                // DirectCosine (pq/distance/cosine.rs:16-70; direct_distance_impl, fixed_chunk_pq_table.rs:35-59): the
+                // Resumable V3 cosine (Strategy2x4) accumulated chunk by chunk over the pivots the code selects, 1 - cos
+                if (c < n) {
+                    const uint8_t* code = p.codes + (size_t)cid[c] * p.n_chunks;
+                    float nx[8], ny[8], xy[8];
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) nx[l] = ny[l] = xy[l] = 0.0f;
+                    for (uint32_t ch = 0; ch < p.n_chunks; ++ch) {
+                        const uint32_t start = p.offsets[ch], stop = p.offsets[ch + 1];
+                        const float* xc = qf + start;
+                        const float* yc = p.pivots + (size_t)__ldg(code + ch) * dim + start;
+                        float a[8], b[8], d[8];
+                        thread_simd_combined<2, KIND_IP>(xc, xc, (int)(stop - start), a);
+                        thread_simd_combined<2, KIND_IP>(yc, yc, (int)(stop - start), b);
+                        thread_simd_combined<2, KIND_IP>(xc, yc, (int)(stop - start), d);
+#pragma unroll
+                        for (int l = 0; l < 8; ++l) {
+                            nx[l] = __fadd_rn(nx[l], a[l]);
+                            ny[l] = __fadd_rn(ny[l], b[l]);
+                            xy[l] = __fadd_rn(xy[l], d[l]);
+                        }
+                    }
+                    cd[c] = __fsub_rn(1.0f, cosine_finish(thread_tree8(nx), thread_tree8(ny), thread_tree8(xy)));
+                }
             } else if (c < n) {
                 const uint8_t* code = p.codes + (size_t)cid[c] * p.n_chunks;
                 float accum = 0.0f;
@@ -257,7 +283,7 @@ __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchPa
             }
             __syncwarp();
         }
-        for (uint32_t t = lane; MODE == 0 && t < entries; t += 32) {
+        for (uint32_t t = lane; MODE == 0 && !p.direct_cosine && t < entries; t += 32) {
             const uint32_t chunk = t / p.n_centers, center = t % p.n_centers;
             const uint32_t start = p.offsets[chunk], stop = p.offsets[chunk + 1];
             const float* piv = p.pivots + (size_t)center * dim + start;
@@ -532,8 +558,10 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     if (mode == 1 && (!idx->d_sq_codes || !idx->sq_codes_ready))
         return fail(DAB_ERR_NOT_READY, "dab_search_batch_sq: no scalar-quantized rows (dab_upload_sq with rows, or dab_sq_encode_all)");
     if (k == 0 || l_search == 0 || beam == 0 || beam > 64) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: bad k / l_search / beam_width");
-    if (mode == 0 && idx->metric == DAB_COSINE)
-        return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: Metric::Cosine traverses with DirectCosine (no table); use dab_pq_distances");
+    // Metric::Cosine traverses with DirectCosine (no table); the full-precision rerank of float rows would need the
+    // NA = 2 float cosine schema, which the rerank kernel does not carry
+    if (mode == 0 && idx->metric == DAB_COSINE && rerank && (idx->dtype == DAB_F32 || idx->dtype == DAB_F16))
+        return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq_rerank: Metric::Cosine over float rows is not supported by the rerank stage (use dab_search_batch_pq)");
     // SQStore::distance_computer (providers inmem/scalar.rs:214-226): UnsupportedDistanceMetric
     if (mode == 1 && idx->metric == DAB_COSINE)
         return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_sq: the scalar-quantized store supports L2, InnerProduct and CosineNormalized");
@@ -558,6 +586,7 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     p.n_chunks = idx->pq_chunks;
     p.n_centers = idx->pq_centers;
     p.ip_table = idx->metric == DAB_INNER_PRODUCT ? 1 : 0;  // L2 and CosineNormalized use TableL2 (dynamic.rs:80-85)
+    p.direct_cosine = mode == 0 && idx->metric == DAB_COSINE ? 1 : 0;
     if (mode == 1) {
         p.sq_codes = idx->d_sq_codes;
         p.sq_comp = idx->d_sq_comp;

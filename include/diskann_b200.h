@@ -214,8 +214,10 @@ int dab_pq_self_distances(dab_index* idx, const uint32_t* ids_a, const uint32_t*
  * search_internal — dab_search_batch with every traversal distance an ADC lookup over the
  * uploaded codes (start points included).  Queries have the index dtype and are converted to
  * f32 (T: Into<f32>); L2 / CosineNormalized use TableL2, InnerProduct TableIP; Metric::Cosine
- * (DirectCosine, no table) is rejected here — use dab_pq_distances.  No rerank: distances
- * returned are the ADC values. */
+ * runs QueryComputer::DirectCosine (pq/distance/cosine.rs:16-70: no table, the resumable cosine
+ * over the pivot chunks a code selects).  No rerank: distances returned are the traversal values.
+ * (dab_search_batch_pq_rerank rejects Metric::Cosine over f32 / f16 rows: the rerank stage has no
+ * float cosine schema.) */
 int dab_search_batch_pq(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search,
                         uint32_t beam_width, uint32_t* out_ids, float* out_dists,
                         uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops);

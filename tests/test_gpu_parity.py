@@ -608,8 +608,16 @@ def test_pq_traversal_search_identical_to_oracle(dab, dt, metric, d, chunks):
         g.upload_vectors(f32)
         g.upload_graph(adj)
         g.upload_pq(piv, off, codes)
+        # Metric::Cosine traverses with QueryComputer::DirectCosine (no table): resumable cosine over the gathered pivots
+        ocos = O.Index(np.ascontiguousarray(f32), adj, n, 1, O.COSINE, pq=(piv, off, codes))
+        qf = np.ascontiguousarray(f32[rng.integers(0, n, 100)])
+        for (k, Ls, beam) in [(10, 30, 1), (5, 64, 2)]:
+            got = g.search_batch_pq(qf, k, Ls, beam)
+            want = ocos.search_batch(qf, k, Ls, beam=beam, threads=4)
+            for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), ("direct cosine", name, k, Ls, beam)
         with pytest.raises(dab.DabError):
-            g.search_batch_pq(f32[:2], 5, 10)  # DirectCosine has no table: rejected loudly
+            g.search_batch_pq(qf[:2], 5, 10, 1, rerank=True)  # float cosine rerank: not carried by the rerank stage
 
 
 def sq_quantizer(f32, metric):
