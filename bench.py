@@ -199,15 +199,17 @@ def measured_peak_gbs():
 
 
 def ncu_traffic(workload):
+    """DRAM bytes (read + write) of one launch of the workload's search kernel from the committed `ncu --set full`
+    capture (profiles/traffic.json: {workload: {search_kernel_dram_bytes_per_launch, source, kernel}}), else None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        try:
-            t = json.load(open(p))
-            if t.get("workload", "c2_1Mx128_f32_l2") == workload:
-                return t.get("search_kernel_dram_bytes_per_launch")
-        except Exception:
-            return None
-    return None
+    try:
+        t = json.load(open(p))
+    except Exception:
+        return None
+    if "search_kernel_dram_bytes_per_launch" in t:  # round-1 layout: one entry, the C2 kernel
+        t = {t.get("workload", "c2_1Mx128_f32_l2"): t}
+    e = t.get(workload)
+    return e.get("search_kernel_dram_bytes_per_launch") if isinstance(e, dict) else None
 
 
 def metric_name(cfg):
@@ -553,7 +555,7 @@ def run_gpu(args):
                        "note": "one batch at a time (dab_search_batch_device / dab_search_batch): launch, wait, next"},
             "setup_s": dict(t_prep, data=round(t_data, 1), ground_truth=round(t_gt, 2)),
             "l_sweep": sweep, "at_min_l": at_min_l, "parity_gate": parity})
-        kernel = ("search_kernel_pq + rerank_kernel" if is_pq else "search_kernel_v3 / v2") + f"<{cfg['dtype']},{cfg['metric'].upper()}>"
+        kernel = ("search_kernel_pqs + rerank_kernel" if is_pq else "search_kernel_v3 / v2") + f"<{cfg['dtype']},{cfg['metric'].upper()}>"
         result = {
             "metric": metric_name(cfg), "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,

@@ -75,6 +75,8 @@ void Tuning::load() {
     tc_resident = flag("DAB_TC_RESIDENT");
     v3_max_cap = num("DAB_V3_MAX_CAP", 1, 512);
     pq_ctas_per_sm = num("DAB_PQ_CTAS_PER_SM", 1, 16);
+    pq_global_lut = flag("DAB_PQ_GLOBAL_LUT");
+    pq_warps = num("DAB_PQ_WARPS", 1, 16);
     frontier_narrow = flag("DAB_FRONTIER_NARROW");
     v2_stage_bytes = num("DAB_V2_STAGE_BYTES", 1024, 65536);
     v2_ctas_per_sm = num("DAB_V2_CTAS_PER_SM", 1, 64);
@@ -292,6 +294,9 @@ int dab_upload_pq(dab_index* idx, const float* pivots, uint32_t n_centers, const
         DAB_CUDA(cudaMemset(idx->d_codes, 0, idx->n_total() * (size_t)n_chunks));
     idx->pq_chunks = n_chunks;
     idx->pq_centers = n_centers;
+    idx->pq_uniform_len = off32[1] - off32[0];
+    for (uint32_t c = 1; c < n_chunks; ++c)
+        if (off32[c + 1] - off32[c] != idx->pq_uniform_len) idx->pq_uniform_len = 0;
     idx->pq_codes_ready = codes != nullptr;
     return DAB_OK;
 }

@@ -70,6 +70,8 @@ struct Tuning {
     int v3_table_bytes = 0;        // DAB_V3_TABLE_BYTES: visited-table bytes per warp
     bool tc_resident = false;      // DAB_TC_RESIDENT: tensor-core scan keeps the query tile in shared memory (measured equal to streaming it)
     int pq_ctas_per_sm = 0;        // DAB_PQ_CTAS_PER_SM: resident CTAs (4 warps) per SM of the PQ traversal kernel (default 6)
+    bool pq_global_lut = false;    // DAB_PQ_GLOBAL_LUT: PQ traversal with the per-warp table in global memory (search_kernel_pq) also where search_kernel_pqs fits
+    int pq_warps = 0;              // DAB_PQ_WARPS: cap on the warps (queries in flight) per CTA of search_kernel_pqs (default: what shared memory holds, <= 16)
     int v3_max_cap = 0;            // DAB_V3_MAX_CAP: largest L + #start that still runs search_kernel_v3 (default 24)
     bool v3_generic = false;       // DAB_V3_GENERIC: generic distance loop also for 32 / 64 / 96 / 128-d f32 rows
     int v3_ctas_per_sm = 0;        // DAB_V3_CTAS_PER_SM: cap on resident CTAs
@@ -104,6 +106,7 @@ struct dab_index {
     uint32_t* d_offsets = nullptr; // [n_chunks + 1]
     uint8_t* d_codes = nullptr;    // [n_total][n_chunks]
     uint32_t pq_chunks = 0, pq_centers = 0;
+    uint32_t pq_uniform_len = 0;   // every chunk has this many dimensions (0: lengths differ)
     bool pq_codes_ready = false;   // codes uploaded (dab_upload_pq) or produced (dab_pq_encode_all)
     // scalar-quantized store (providers inmem/scalar.rs SQStore<NBITS>): dense N-bit codes, one 16 B-aligned
     // row per point, compensations apart (only the inner-product epilogue reads them)

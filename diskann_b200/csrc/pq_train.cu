@@ -416,6 +416,7 @@ int dab_pq_train(dab_index* idx, const float* train, uint64_t n, uint32_t n_chun
     DAB_CUDA(cudaStreamSynchronize(st));
     idx->pq_chunks = n_chunks;
     idx->pq_centers = n_centers;
+    idx->pq_uniform_len = dim % n_chunks == 0 ? dim / n_chunks : 0;
     idx->pq_codes_ready = false;
     for (uint32_t c = 0; c < n_chunks; ++c)
         if (h_sel[c] != n_centers)

@@ -88,4 +88,34 @@ __device__ __forceinline__ float thread_simd_l2ip(const float* x, const float* y
     return thread_tree8(c);
 }
 
+// ------------------------------------------------------------------ PQ table entries from shared-memory pivots
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+// Table entry of (chunk, centre) computed from a query (qf) and a pivot table (spiv, rows pstride floats apart)
+// in shared memory; CL = 4 / 8: every chunk has that length and starts 16-byte aligned, 0: lengths from `offsets`.
+// The arithmetic is thread_simd_l2ip either way — the same bits whether the entry is stored in a table first or not
+// (fixed_chunk_pq_table.rs:152-187; TableIP entries are -dot, implementations.rs:309-314).
+template <int CL>
+__device__ __forceinline__ float pqs_term(const float* qf, const float* spiv, uint32_t pstride, const uint32_t* __restrict__ offsets,
+                                          uint32_t ch, uint32_t center, bool ip) {
+    if constexpr (CL == 4 || CL == 8) {
+        constexpr int N = CL;
+        float x[N], y[N];
+        const float4* xp = reinterpret_cast<const float4*>(qf + ch * N);
+        const float4* yp = reinterpret_cast<const float4*>(spiv + (size_t)center * pstride + ch * N);
+#pragma unroll
+        for (int v = 0; v < N / 4; ++v) {
+            const float4 a = xp[v], b = yp[v];
+            x[4 * v] = a.x, x[4 * v + 1] = a.y, x[4 * v + 2] = a.z, x[4 * v + 3] = a.w;
+            y[4 * v] = b.x, y[4 * v + 1] = b.y, y[4 * v + 2] = b.z, y[4 * v + 3] = b.w;
+        }
+        return ip ? -thread_simd_l2ip<KIND_IP>(x, y, N) : thread_simd_l2ip<KIND_L2>(x, y, N);
+    } else {
+        const uint32_t start = __ldg(offsets + ch), stop = __ldg(offsets + ch + 1);
+        const float* xp = qf + start;
+        const float* yp = spiv + (size_t)center * pstride + start;
+        return ip ? -thread_simd_l2ip<KIND_IP>(xp, yp, (int)(stop - start)) : thread_simd_l2ip<KIND_L2>(xp, yp, (int)(stop - start));
+    }
+}
+
 }  // namespace dab

@@ -75,6 +75,91 @@ pq_adc_kernel(const float* __restrict__ lut, uint32_t nq, const uint32_t* __rest
     }
 }
 
+// ------------------------------------------------------------------ fused LUT build + ADC (K6 + K7)
+// pq_lut_kernel + pq_adc_kernel spend their time moving tables: every query re-reads the 128 KB pivot table from L2
+// to build its LUT, writes the 32 KB LUT to global memory and reads it back.  Here a persistent CTA per SM stages the
+// pivots in shared memory ONCE (rows padded to an odd multiple of four floats), then per query: stage the query,
+// build the LUT shared-to-shared (same entry arithmetic, quant_device.cuh pqs_term), optionally write it out
+// (dab_pq_populate_lut), and sum one entry per chunk for every candidate in chunk order from 0.0.  While the LUT is
+// being built the code rows of the query's candidates and the ids of the CTA's next query are on their way to L2.
+struct PqFusedParams {
+    const float* queries;
+    uint32_t nq;
+    const float* pivots;
+    const uint32_t* offsets;
+    uint32_t n_centers, n_chunks, dim;
+    uint32_t piv_stride, piv_bytes;
+    int ip;
+    float* lut_out;        // [nq][n_chunks][n_centers] or NULL
+    const uint32_t* ids;   // [nq][c] or NULL (LUT only)
+    uint32_t c;
+    const uint8_t* codes;
+    uint64_t n_total;
+    float* out;            // [nq][c]
+};
+
+template <int CL>
+__global__ void __launch_bounds__(512, 1) pq_fused_kernel(const PqFusedParams p) {
+    extern __shared__ __align__(16) uint8_t fsm[];
+    float* spiv = reinterpret_cast<float*>(fsm);
+    float* slut = reinterpret_cast<float*>(fsm + p.piv_bytes);
+    const uint32_t entries = p.n_chunks * p.n_centers;
+    float* sq = slut + ((entries + 3u) & ~3u);
+    {
+        const uint32_t total = p.n_centers * p.dim;
+        for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
+            const uint32_t c = e / p.dim, d = e - c * p.dim;
+            spiv[(size_t)c * p.piv_stride + d] = __ldg(p.pivots + e);
+        }
+    }
+    const bool ip = p.ip != 0;
+    for (uint32_t q = blockIdx.x; q < p.nq; q += gridDim.x) {
+        __syncthreads();  // pivots staged (first query) / the previous query's LUT no longer read
+        for (uint32_t e = threadIdx.x; e < p.dim; e += blockDim.x) sq[e] = __ldg(p.queries + (size_t)q * p.dim + e);
+        if (p.ids) {
+            for (uint32_t j = threadIdx.x; j < p.c; j += blockDim.x) {
+                const uint32_t id = __ldg(p.ids + (size_t)q * p.c + j);
+                if (id != kNoId && id < p.n_total) prefetch_l2(p.codes + (size_t)id * p.n_chunks);
+            }
+            const uint32_t qn = q + gridDim.x;  // the ids of this CTA's next query: one 128-byte line per thread
+            if (qn < p.nq && threadIdx.x * 32u < p.c) prefetch_l2(p.ids + (size_t)qn * p.c + threadIdx.x * 32u);
+        }
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < entries; t += blockDim.x) {
+            const uint32_t chunk = t / p.n_centers, center = t - chunk * p.n_centers;
+            const float v = pqs_term<CL>(sq, spiv, p.piv_stride, p.offsets, chunk, center, ip);
+            slut[t] = v;
+            if (p.lut_out) p.lut_out[(size_t)q * entries + t] = v;
+        }
+        __syncthreads();
+        if (!p.ids) continue;
+        for (uint32_t j = threadIdx.x; j < p.c; j += blockDim.x) {
+            const uint32_t id = __ldg(p.ids + (size_t)q * p.c + j);
+            if (id == kNoId || id >= p.n_total) {
+                p.out[(size_t)q * p.c + j] = __int_as_float(0x7FC00000);
+                continue;
+            }
+            const uint8_t* code = p.codes + (size_t)id * p.n_chunks;
+            float accum = 0.0f;
+            uint32_t ch = 0;
+            if ((p.n_chunks & 15u) == 0) {
+                for (; ch < p.n_chunks; ch += 16) {
+                    const uint4 w = __ldg(reinterpret_cast<const uint4*>(code + ch));
+                    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const uint32_t b = (ws[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
+                        accum = __fadd_rn(accum, slut[(ch + k) * p.n_centers + b]);
+                    }
+                }
+            } else {
+                for (; ch < p.n_chunks; ++ch) accum = __fadd_rn(accum, slut[ch * p.n_centers + __ldg(code + ch)]);
+            }
+            p.out[(size_t)q * p.c + j] = accum;
+        }
+    }
+}
+
 // DirectCosine (pq/distance/cosine.rs:16-70; direct_distance_impl,
 // fixed_chunk_pq_table.rs:35-59): resumable V3 cosine (Strategy2x4) over gathered pivot
 // chunks, 1 - cos.  One thread per candidate (rare path).
@@ -284,7 +369,58 @@ static int require_pq(const dab_index* idx, const char* who) {
     return DAB_OK;
 }
 
+// true when the pivot table + one LUT + one query fit the shared memory of a CTA: launches pq_fused_kernel.
+// d_lut / d_ids may be NULL (ADC only / LUT only).
+static bool fused_fits(const dab_index* idx, uint32_t* stride_out, size_t* piv_bytes_out, size_t* smem_out) {
+    uint32_t stride = (uint32_t)round_up(idx->dim, 4);
+    if ((stride & 7u) == 0) stride += 4;
+    const size_t piv_bytes = (size_t)idx->pq_centers * stride * 4;
+    const size_t entries = (size_t)idx->pq_chunks * idx->pq_centers;
+    const size_t smem = piv_bytes + round_up(entries, 4) * 4 + round_up(idx->dim, 4) * 4;
+    *stride_out = stride;
+    *piv_bytes_out = piv_bytes;
+    *smem_out = smem;
+    return smem <= 227 * 1024 && !idx->tune.pq_global_lut;
+}
+
+static int launch_fused(const dab_index* idx, const float* d_queries, uint32_t nq, int lut_metric, float* d_lut, const uint32_t* d_ids,
+                        uint32_t c, float* d_out) {
+    PqFusedParams p;
+    memset(&p, 0, sizeof(p));
+    uint32_t stride;
+    size_t piv_bytes, smem;
+    fused_fits(idx, &stride, &piv_bytes, &smem);
+    p.queries = d_queries;
+    p.nq = nq;
+    p.pivots = idx->d_pivots;
+    p.offsets = idx->d_offsets;
+    p.n_centers = idx->pq_centers;
+    p.n_chunks = idx->pq_chunks;
+    p.dim = idx->dim;
+    p.piv_stride = stride;
+    p.piv_bytes = (uint32_t)piv_bytes;
+    p.ip = lut_metric == DAB_INNER_PRODUCT ? 1 : 0;
+    p.lut_out = d_lut;
+    p.ids = d_ids;
+    p.c = c;
+    p.codes = idx->d_codes;
+    p.n_total = idx->n_total();
+    p.out = d_out;
+    void (*kern)(const PqFusedParams) = idx->pq_uniform_len == 4 ? pq_fused_kernel<4> : idx->pq_uniform_len == 8 ? pq_fused_kernel<8> : pq_fused_kernel<0>;
+    DAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<uint32_t>(nq, (uint32_t)idx->sm_count);
+    kern<<<grid, 512, smem, idx->stream>>>(p);
+    DAB_LAUNCHED();
+    DAB_CUDA(cudaGetLastError());
+    return DAB_OK;
+}
+
 static int launch_lut(const dab_index* idx, const float* d_queries, uint32_t nq, int metric, float* d_lut) {
+    {
+        uint32_t stride;
+        size_t piv_bytes, smem;
+        if (fused_fits(idx, &stride, &piv_bytes, &smem)) return launch_fused(idx, d_queries, nq, metric, d_lut, nullptr, 0, nullptr);
+    }
     const size_t smem = (size_t)idx->dim * 4;
     if (metric == DAB_INNER_PRODUCT)
         pq_lut_kernel<KIND_IP><<<nq, 256, smem, idx->stream>>>(d_queries, nq, idx->d_pivots, idx->pq_centers, idx->d_offsets,
@@ -372,8 +508,19 @@ int dab_pq_distances(dab_index* idx, const float* queries, uint32_t nq, const ui
         DAB_CUDA(cudaGetLastError());
     } else {
         // L2 and CosineNormalized -> TableL2, InnerProduct -> TableIP (dynamic.rs:80-85)
-        if ((rc = idx->s_out2.reserve((size_t)nq * entries * 4))) return rc;
         const int lut_metric = idx->metric == DAB_INNER_PRODUCT ? DAB_INNER_PRODUCT : DAB_L2;
+        uint32_t stride;
+        size_t piv_bytes, fsmem;
+        if (fused_fits(idx, &stride, &piv_bytes, &fsmem)) {
+            // pivots resident in shared memory, LUT built and consumed there: no table ever leaves the SM
+            if ((rc = launch_fused(idx, (const float*)idx->s_queries.p, nq, lut_metric, nullptr, (const uint32_t*)idx->s_ids.p, c,
+                                   (float*)idx->s_out.p)))
+                return rc;
+            DAB_CUDA(cudaMemcpyAsync(out, idx->s_out.p, ibytes, cudaMemcpyDeviceToHost, idx->stream));
+            DAB_CUDA(cudaStreamSynchronize(idx->stream));
+            return DAB_OK;
+        }
+        if ((rc = idx->s_out2.reserve((size_t)nq * entries * 4))) return rc;
         if ((rc = launch_lut(idx, (const float*)idx->s_queries.p, nq, lut_metric, (float*)idx->s_out2.p))) return rc;
         const size_t smem = entries * 4;
         if (smem > 200 * 1024) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_pq_distances: LUT of %zu B does not fit shared memory", smem);

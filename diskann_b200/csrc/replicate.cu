@@ -78,7 +78,7 @@ int need_nccl(const char* who) {
 // what a replica must agree on with the root before any buffer is overwritten
 struct IndexMeta {
     uint64_t n_points, row_stride;
-    uint32_t dtype, metric, dim, n_start, max_degree, adj_stride, vectors_ready, graph_ready, pq_chunks, pq_centers, pq_codes_ready, pad;
+    uint32_t dtype, metric, dim, n_start, max_degree, adj_stride, vectors_ready, graph_ready, pq_chunks, pq_centers, pq_codes_ready, pq_uniform_len;
 };
 
 IndexMeta meta_of(const dab_index* idx) {
@@ -97,6 +97,7 @@ IndexMeta meta_of(const dab_index* idx) {
     m.pq_chunks = idx->pq_chunks;
     m.pq_centers = idx->pq_centers;
     m.pq_codes_ready = idx->pq_codes_ready;
+    m.pq_uniform_len = idx->pq_uniform_len;
     return m;
 }
 
@@ -140,6 +141,7 @@ int broadcast_buffers(dab_index* idx, ncclComm_t comm, int root, bool is_root, I
     idx->graph_ready = got.graph_ready != 0;
     idx->pq_chunks = got.pq_chunks;
     idx->pq_centers = got.pq_centers;
+    idx->pq_uniform_len = got.pq_uniform_len;
     idx->pq_codes_ready = got.pq_codes_ready != 0;
     return DAB_OK;
 }
@@ -268,6 +270,7 @@ int dab_broadcast(dab_index* const* per_gpu, int n_gpus) {
             per_gpu[i]->graph_ready = want.graph_ready != 0;
             per_gpu[i]->pq_chunks = want.pq_chunks;
             per_gpu[i]->pq_centers = want.pq_centers;
+            per_gpu[i]->pq_uniform_len = want.pq_uniform_len;
             per_gpu[i]->pq_codes_ready = want.pq_codes_ready != 0;
         }
         n.CommDestroy(comms[i]);

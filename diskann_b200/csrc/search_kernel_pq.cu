@@ -27,57 +27,13 @@
 #include "dab_common.cuh"
 #include "quant_device.cuh"
 #include "search_common.cuh"
+#include "search_pq.cuh"
 #include "search_smem.cuh"
 
 #include <algorithm>
 #include <type_traits>
 
 namespace dab {
-
-constexpr int kPqWarps = 4;
-
-struct SearchParamsPq {
-    const uint8_t* vectors;  // only for the f32 view of the query rows in build-free search: unused
-    const uint32_t* adj;
-    uint32_t adj_stride;
-    uint64_t n_points;
-    uint32_t n_start;
-    uint32_t dim;
-    uint32_t max_degree;
-    int dtype;
-    const void* queries;
-    const uint32_t* query_list;
-    uint32_t n_work;
-    uint32_t k, cap, beam;
-    const float* pivots;
-    const uint32_t* offsets;
-    const uint8_t* codes;
-    uint32_t n_chunks, n_centers;
-    int ip_table;  // 1: TableIP (entries -dot), 0: TableL2
-    int direct_cosine;  // 1: Metric::Cosine -> QueryComputer::DirectCosine (no table): resumable cosine over the gathered pivot chunks
-    float* luts;   // [warps][n_chunks * n_centers]
-    uint32_t* out_ids;
-    float* out_dists;
-    uint32_t* out_counts;
-    uint32_t* out_cmps;
-    uint32_t* out_hops;
-    uint32_t* tables;
-    uint32_t n_buckets;
-    uint32_t* counters;
-    uint32_t* overflow_list;
-    // optional: the whole candidate list (best.iter()) for the rerank stage
-    uint32_t* list_ids;     // [nq][list_cap]
-    uint32_t* list_counts;  // [nq]
-    uint32_t list_cap;
-    // MODE 1: scalar-quantized store
-    const uint8_t* sq_codes;  // [n_total][sq_stride], dense N-bit codes, zero padded to 16 B
-    const float* sq_comp;     // [n_total]
-    const float* sq_shift;    // [dim]
-    uint32_t sq_stride;
-    int sq_nbits, sq_metric;
-    float sq_scale, sq_scale_squared, sq_shift_square_norm, sq_mean_norm;
-    uint32_t warp_smem, off_q, off_qd, off_qi, off_cid, off_cd, off_beam, off_qc;
-};
 
 // integer cores over one 32-bit word of dense NBITS codes (fields never straddle bytes for 1/2/4/8 bits)
 template <int NBITS>
@@ -624,21 +580,35 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     p.off_qc = (uint32_t)off;
     if (mode == 1) off += idx->sq_stride;
     p.warp_smem = (uint32_t)round_up(off, 16);
+    // table metrics with a pivot table that fits shared memory: search_kernel_pqs (pivots resident per SM, entries
+    // computed on the fly); everything else — SQ, DirectCosine, wide pivots, > 32 chunks — the per-warp kernel below
+    PqsPlan plan;
+    memset(&plan, 0, sizeof(plan));
+    const bool use_pqs = mode == 0 && !p.direct_cosine && pqs_plan(idx, p.warp_smem, nq, &plan);
     const size_t smem_block = (size_t)p.warp_smem * kPqWarps;
-    if (smem_block > 200 * 1024) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: configuration needs %zu B shared memory per CTA", smem_block);
-    void (*kern)(const SearchParamsPq);
-    if (mode == 1) kern = cap <= 128 ? search_kernel_pq<4, 1> : cap <= 256 ? search_kernel_pq<8, 1> : search_kernel_pq<16, 1>;
-    else kern = cap <= 128 ? search_kernel_pq<4, 0> : cap <= 256 ? search_kernel_pq<8, 0> : search_kernel_pq<16, 0>;
-    DAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block));
-    int per_sm = 0;
-    DAB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPqWarps * 32, smem_block));
-    if (per_sm < 1) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: kernel does not fit");
-    // every resident warp owns a LUT (n_chunks x n_centers f32: 32 KB at 32 x 256) and a visited table in
-    // global memory; ADC terms and probes are L2 hits only while all of them stay L2-resident
-    // (the SQ kernel has no LUT: it keeps the occupancy the shared memory allows unless the knob is set)
-    if (mode == 0 || idx->tune.pq_ctas_per_sm) per_sm = std::min(per_sm, idx->tune.pq_ctas_per_sm ? idx->tune.pq_ctas_per_sm : 6);
-    const int grid = (int)std::min<uint64_t>((uint64_t)per_sm * idx->sm_count, ((uint64_t)nq + kPqWarps - 1) / kPqWarps);
-    const uint32_t warps = (uint32_t)grid * kPqWarps;
+    void (*kern)(const SearchParamsPq) = nullptr;
+    int grid;
+    uint32_t warps;
+    if (use_pqs) {
+        p.piv_stride = plan.piv_stride;
+        p.piv_bytes = plan.piv_bytes;
+        grid = plan.grid;
+        warps = (uint32_t)plan.grid * (uint32_t)plan.warps;
+    } else {
+        if (smem_block > 200 * 1024) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: configuration needs %zu B shared memory per CTA", smem_block);
+        if (mode == 1) kern = cap <= 128 ? search_kernel_pq<4, 1> : cap <= 256 ? search_kernel_pq<8, 1> : search_kernel_pq<16, 1>;
+        else kern = cap <= 128 ? search_kernel_pq<4, 0> : cap <= 256 ? search_kernel_pq<8, 0> : search_kernel_pq<16, 0>;
+        DAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block));
+        int per_sm = 0;
+        DAB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPqWarps * 32, smem_block));
+        if (per_sm < 1) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: kernel does not fit");
+        // every resident warp owns a LUT (n_chunks x n_centers f32: 32 KB at 32 x 256) and a visited table in
+        // global memory; ADC terms and probes are L2 hits only while all of them stay L2-resident
+        // (the SQ kernel has no LUT: it keeps the occupancy the shared memory allows unless the knob is set)
+        if (mode == 0 || idx->tune.pq_ctas_per_sm) per_sm = std::min(per_sm, idx->tune.pq_ctas_per_sm ? idx->tune.pq_ctas_per_sm : 6);
+        grid = (int)std::min<uint64_t>((uint64_t)per_sm * idx->sm_count, ((uint64_t)nq + kPqWarps - 1) / kPqWarps);
+        warps = (uint32_t)grid * kPqWarps;
+    }
 
     // visited-table capacity: the reference's estimate (scratch.rs:186-192) on the first call, then 1.15x the
     // largest visited set seen at this (or a larger) L at 87.5 % load — the estimate is ~10x what a search
@@ -650,12 +620,13 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
         slots = std::min(slots, std::max<uint64_t>(256, seen));
     }
     if (slots > 2 * idx->n_total() + 2048) slots = 2 * idx->n_total() + 2048;
+    if (idx->tune.test_visited_log2) slots = 1ull << idx->tune.test_visited_log2;  // tests force the overflow re-runs
     int rc;
     if ((rc = idx->s_counters.reserve(16 + (size_t)nq * 4))) return rc;
     uint32_t* d_counters = (uint32_t*)idx->s_counters.p;
     p.counters = d_counters;
     p.overflow_list = d_counters + 4;
-    const size_t lut_bytes = mode == 0 ? (size_t)warps * idx->pq_chunks * idx->pq_centers * 4 : 16;
+    const size_t lut_bytes = mode == 0 && !use_pqs ? (size_t)warps * idx->pq_chunks * idx->pq_centers * 4 : 16;
     if ((rc = idx->s_out2.reserve(lut_bytes))) return rc;
     p.luts = (float*)idx->s_out2.p;
     p.n_work = nq;
@@ -675,9 +646,16 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
         }
         p.tables = (uint32_t*)idx->s_tables.p;
         DAB_CUDA(cudaMemsetAsync(d_counters, 0, 16, idx->stream));
-        kern<<<grid, kPqWarps * 32, smem_block, idx->stream>>>(p);
-        DAB_LAUNCHED();
-        DAB_CUDA(cudaGetLastError());
+        if (use_pqs) {
+            if ((rc = pqs_launch(idx, p, plan, cap))) {
+                retry.release();
+                return rc;
+            }
+        } else {
+            kern<<<grid, kPqWarps * 32, smem_block, idx->stream>>>(p);
+            DAB_LAUNCHED();
+            DAB_CUDA(cudaGetLastError());
+        }
         uint32_t h[3] = {0, 0, 0};
         DAB_CUDA(cudaMemcpyAsync(h, d_counters, 12, cudaMemcpyDeviceToHost, idx->stream));
         DAB_CUDA(cudaStreamSynchronize(idx->stream));

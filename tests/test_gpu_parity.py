@@ -330,9 +330,14 @@ def trained_pq(rng, base, chunks, centers=256):
 
 @pytest.mark.parametrize("metric,dim,chunks", [(O.L2, 128, 32), (O.INNER_PRODUCT, 128, 32), (O.COSINE_NORMALIZED, 96, 12),
                                                (O.COSINE, 64, 8), (O.L2, 100, 7), (O.L2, 17, 17)])
-def test_pq_lut_adc_encode_bit_exact(dab, metric, dim, chunks):
+@pytest.mark.parametrize("path", ["fused", "separate_kernels"])
+def test_pq_lut_adc_encode_bit_exact(dab, monkeypatch, metric, dim, chunks, path):
+    """K6 / K7 through dab_pq_populate_lut / dab_pq_distances: pq_fused_kernel (pivots and the query's table in shared
+    memory, the default where they fit) and the pq_lut_kernel + pq_adc_kernel pair (DAB_PQ_GLOBAL_LUT)."""
+    if path == "separate_kernels":
+        monkeypatch.setenv("DAB_PQ_GLOBAL_LUT", "1")
     rng = np.random.default_rng(dim + chunks)
-    n, nq, c = 2000, 16, 200
+    n, nq, c = 2000, (300 if chunks == 32 else 16), (700 if chunks == 32 else 200)  # > one CTA per SM, > one pass of candidates
     base = clustered(rng, n + 1, dim)
     piv, off = trained_pq(rng, base, chunks)
     L = O.lib()
@@ -568,11 +573,19 @@ def test_device_batched_build_is_the_reference_multi_insert(dab, dt, metric, d, 
 
 # ---------------------------------------------------------------- PQ traversal (C4 shape) and C3 shape
 
+@pytest.mark.parametrize("path", ["smem_pivots", "global_lut", "smem_pivots_overflow"])
 @pytest.mark.parametrize("dt,metric,d,chunks", [(np.int8, O.L2, 128, 32), (np.float32, O.L2, 96, 12), (np.float32, O.INNER_PRODUCT, 64, 16),
-                                                (np.uint8, O.COSINE_NORMALIZED, 40, 7)])
-def test_pq_traversal_search_identical_to_oracle(dab, dt, metric, d, chunks):
+                                                (np.uint8, O.COSINE_NORMALIZED, 40, 7), (np.float32, O.INNER_PRODUCT, 100, 25)])
+def test_pq_traversal_search_identical_to_oracle(dab, monkeypatch, dt, metric, d, chunks, path):
     """dab_search_batch_pq: greedy search whose traversal distances are ADC lookups over the codes
-    (providers' QuantAccessor, product.rs:311-340) == the oracle's search with pq_codes set."""
+    (providers' QuantAccessor, product.rs:311-340) == the oracle's search with pq_codes set.
+    Both kernels are covered: search_kernel_pqs (pivots in shared memory, the default where they fit: chunk
+    lengths 4 / 8 / mixed, 32 / 25 / 16 / 12 / 7 chunks) and search_kernel_pq (per-warp table in global memory),
+    and the overflow re-run of the former (a 256-slot visited table)."""
+    if path == "global_lut":
+        monkeypatch.setenv("DAB_PQ_GLOBAL_LUT", "1")
+    if path == "smem_pivots_overflow":
+        monkeypatch.setenv("DAB_TEST_VISITED_LOG2", "8")
     rng = np.random.default_rng(d + chunks)
     n = 4000
     vecs, adj, maxdeg = make_index(rng, dt, O.L2 if metric == O.COSINE_NORMALIZED else metric, n, d, 24, 40)

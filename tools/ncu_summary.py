@@ -1,9 +1,11 @@
 """Summarise one kernel of an .ncu-rep (ncu --set full) as markdown + profiles/traffic.json.
-usage: python tools/ncu_summary.py report.ncu-rep "<command line used>" out.md [traffic.json]"""
+usage: python tools/ncu_summary.py report.ncu-rep "<command line used>" out.md [traffic.json [workload]]
+(traffic.json maps a bench workload to the DRAM bytes of one launch of its search kernel; entries of other workloads are kept)"""
 import csv, io, json, subprocess, sys
 
 rep, cmd, out = sys.argv[1], sys.argv[2], sys.argv[3]
 traffic = sys.argv[4] if len(sys.argv) > 4 else None
+workload = sys.argv[5] if len(sys.argv) > 5 else "c2_1Mx128_f32_l2"
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -44,5 +46,12 @@ for v, n in sorted(st, reverse=True)[:10]:
 lines += ["", "Tensor pipe: not used by design (HBM-gather / integer path; see DESIGN.md §5)."]
 open(out, "w").write("\n".join(lines) + "\n")
 if traffic:
-    json.dump({"search_kernel_dram_bytes_per_launch": total, "source": f"ncu --set full, {out}", "kernel": kernel}, open(traffic, "w"))
+    try:
+        t = json.load(open(traffic))
+    except Exception:
+        t = {}
+    if "search_kernel_dram_bytes_per_launch" in t:  # round-1 layout: a single (C2) entry
+        t = {t.get("workload", "c2_1Mx128_f32_l2"): t}
+    t[workload] = {"search_kernel_dram_bytes_per_launch": total, "source": f"ncu --set full, {out}", "kernel": kernel}
+    json.dump(t, open(traffic, "w"), indent=1)
 print(out, "dram GB", total / 1e9)
