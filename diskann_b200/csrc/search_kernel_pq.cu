@@ -388,7 +388,10 @@ struct RerankParams {
     uint32_t warp_smem, off_ids, off_d;
 };
 
-template <typename TD, int KIND, int POST>
+// NA = 4: the wide-load loops (f32 rows, L2 / InnerProduct / CosineNormalized; integers).  NA = 2: the schemas with two
+// accumulators — f16 x f16 (Strategy2x4, simd.rs:424-483: both sides widened to f32 lanes, so the f32 copy of the query
+// in shared memory is the same operand) and Metric::Cosine over float rows — one team of 16 lanes per row.
+template <typename TD, int KIND, int POST, int NA = 4>
 __global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const RerankParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr bool kInt = std::is_same<TD, int8_t>::value || std::is_same<TD, uint8_t>::value;
@@ -424,6 +427,20 @@ __global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const RerankP
             if (KIND != KIND_IP) qq = warp_int_self<std::is_same<TD, int8_t>::value>(reinterpret_cast<const uint8_t*>(qf), dim, lane);
             wide_distances_int<std::is_same<TD, int8_t>::value, KIND, POST, 4>(reinterpret_cast<const uint8_t*>(qf), qq, p.vectors, p.row_stride,
                                                                              cid, m, cd, dim, lane);
+        } else if constexpr (NA == 2) {
+            constexpr int S = 16, U = 2;
+            const int team = lane / S, slot = lane % S;
+            for (uint32_t c0 = 0; c0 < m; c0 += 2 * U) {  // every lane takes part in the team shuffles: uniform trip count
+                const TD* rows[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    rows[u] = reinterpret_cast<const TD*>(p.vectors + (size_t)cid[min(c0 + team * U + u, m - 1)] * p.row_stride);
+                float r[U];
+                team_float_multi<2, KIND, U>(qf, rows, dim, slot, r);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (slot == 0 && c0 + team * U + u < m) cd[c0 + team * U + u] = post_op<POST>(r[u]);
+            }
         } else {
             wide_distances<TD, KIND, POST, 2, 4>(qf, p.vectors, p.row_stride, cid, m, cd, dim, lane);
         }
@@ -452,10 +469,7 @@ __global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const RerankP
 static int launch_rerank(dab_index* idx, const void* d_queries, uint32_t nq, uint32_t k, uint32_t list_cap, const uint32_t* d_list,
                          const uint32_t* d_list_n, uint32_t* d_ids, float* d_dists, uint32_t* d_counts) {
     const bool is_int = idx->dtype == DAB_I8 || idx->dtype == DAB_U8;
-    if (idx->dtype == DAB_F16)
-        return fail(DAB_ERR_INVALID_ARGUMENT, "rerank: f16 x f16 full-precision distances (Strategy2x4) are not built on this path");
     const MetricPlan plan = plan_for(idx->metric, is_int);
-    if (plan.kind == KIND_COS && !is_int) return fail(DAB_ERR_INVALID_ARGUMENT, "rerank: Metric::Cosine over float rows is not built on this path");
     RerankParams p;
     memset(&p, 0, sizeof(p));
     p.vectors = idx->d_vectors;
@@ -480,16 +494,22 @@ static int launch_rerank(dab_index* idx, const void* d_queries, uint32_t nq, uin
     const size_t smem = off * kRerankWarps;
     if (smem > 200 * 1024) return fail(DAB_ERR_INVALID_ARGUMENT, "rerank: configuration needs %zu B shared memory per CTA", smem);
     const int grid = (int)std::min<uint64_t>(((uint64_t)nq + kRerankWarps - 1) / kRerankWarps, (uint64_t)idx->sm_count * 8);
-#define DAB_RERANK(TD, K_, P_)                                                                               \
+#define DAB_RERANK(TD, K_, P_, ...)                                                                          \
     do {                                                                                                     \
-        auto kern = rerank_kernel<TD, K_, P_>;                                                               \
+        auto kern = rerank_kernel<TD, K_, P_, ##__VA_ARGS__>;                                                \
         DAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
         kern<<<grid, kRerankWarps * 32, smem, idx->stream>>>(p);                                             \
     } while (0)
     if (idx->dtype == DAB_F32) {
         if (plan.kind == KIND_L2) DAB_RERANK(float, KIND_L2, POST_ID);
+        else if (plan.kind == KIND_COS) DAB_RERANK(float, KIND_COS, POST_ONE_MINUS, 2);
         else if (plan.post == POST_NEG) DAB_RERANK(float, KIND_IP, POST_NEG);
         else DAB_RERANK(float, KIND_IP, POST_ONE_MINUS);
+    } else if (idx->dtype == DAB_F16) {
+        if (plan.kind == KIND_L2) DAB_RERANK(__half, KIND_L2, POST_ID, 2);
+        else if (plan.kind == KIND_COS) DAB_RERANK(__half, KIND_COS, POST_ONE_MINUS, 2);
+        else if (plan.post == POST_NEG) DAB_RERANK(__half, KIND_IP, POST_NEG, 2);
+        else DAB_RERANK(__half, KIND_IP, POST_ONE_MINUS, 2);
     } else if (idx->dtype == DAB_I8) {
         if (plan.kind == KIND_L2) DAB_RERANK(int8_t, KIND_L2, POST_ID);
         else if (plan.kind == KIND_IP) DAB_RERANK(int8_t, KIND_IP, POST_NEG);
@@ -514,10 +534,6 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     if (mode == 1 && (!idx->d_sq_codes || !idx->sq_codes_ready))
         return fail(DAB_ERR_NOT_READY, "dab_search_batch_sq: no scalar-quantized rows (dab_upload_sq with rows, or dab_sq_encode_all)");
     if (k == 0 || l_search == 0 || beam == 0 || beam > 64) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: bad k / l_search / beam_width");
-    // Metric::Cosine traverses with DirectCosine (no table); the full-precision rerank of float rows would need the
-    // NA = 2 float cosine schema, which the rerank kernel does not carry
-    if (mode == 0 && idx->metric == DAB_COSINE && rerank && (idx->dtype == DAB_F32 || idx->dtype == DAB_F16))
-        return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq_rerank: Metric::Cosine over float rows is not supported by the rerank stage (use dab_search_batch_pq)");
     // SQStore::distance_computer (providers inmem/scalar.rs:214-226): UnsupportedDistanceMetric
     if (mode == 1 && idx->metric == DAB_COSINE)
         return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_sq: the scalar-quantized store supports L2, InnerProduct and CosineNormalized");

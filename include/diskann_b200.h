@@ -215,9 +215,7 @@ int dab_pq_self_distances(dab_index* idx, const uint32_t* ids_a, const uint32_t*
  * uploaded codes (start points included).  Queries have the index dtype and are converted to
  * f32 (T: Into<f32>); L2 / CosineNormalized use TableL2, InnerProduct TableIP; Metric::Cosine
  * runs QueryComputer::DirectCosine (pq/distance/cosine.rs:16-70: no table, the resumable cosine
- * over the pivot chunks a code selects).  No rerank: distances returned are the traversal values.
- * (dab_search_batch_pq_rerank rejects Metric::Cosine over f32 / f16 rows: the rerank stage has no
- * float cosine schema.) */
+ * over the pivot chunks a code selects).  No rerank: distances returned are the traversal values. */
 int dab_search_batch_pq(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search,
                         uint32_t beam_width, uint32_t* out_ids, float* out_dists,
                         uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops);
@@ -228,7 +226,8 @@ int dab_search_batch_pq(dab_index* idx, const void* queries, uint32_t nq, uint32
  * Distance<T, T> over the uploaded rows, the list is ordered by that distance (ties keep their
  * traversal order; the reference leaves them unspecified) and the first k are returned — what
  * `use_fp_for_search: false` runs in diskann-benchmark (src/index/inmem/product.rs:233-239).
- * f32, i8 and u8 rows. */
+ * Every row type and metric of the index: f32 / f16 / i8 / u8 (f16 x f16 and Metric::Cosine over float rows use the
+ * schemas with two accumulators, simd.rs:424-483). */
 int dab_search_batch_pq_rerank(dab_index* idx, const void* queries, uint32_t nq, uint32_t k, uint32_t l_search,
                                uint32_t beam_width, uint32_t* out_ids, float* out_dists,
                                uint32_t* out_counts, uint32_t* out_cmps, uint32_t* out_hops);

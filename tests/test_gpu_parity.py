@@ -575,7 +575,8 @@ def test_device_batched_build_is_the_reference_multi_insert(dab, dt, metric, d, 
 
 @pytest.mark.parametrize("path", ["smem_pivots", "global_lut", "smem_pivots_overflow"])
 @pytest.mark.parametrize("dt,metric,d,chunks", [(np.int8, O.L2, 128, 32), (np.float32, O.L2, 96, 12), (np.float32, O.INNER_PRODUCT, 64, 16),
-                                                (np.uint8, O.COSINE_NORMALIZED, 40, 7), (np.float32, O.INNER_PRODUCT, 100, 25)])
+                                                (np.uint8, O.COSINE_NORMALIZED, 40, 7), (np.float32, O.INNER_PRODUCT, 100, 25),
+                                                (np.float16, O.L2, 64, 16)])
 def test_pq_traversal_search_identical_to_oracle(dab, monkeypatch, dt, metric, d, chunks, path):
     """dab_search_batch_pq: greedy search whose traversal distances are ADC lookups over the codes
     (providers' QuantAccessor, product.rs:311-340) == the oracle's search with pq_codes set.
@@ -609,14 +610,11 @@ def test_pq_traversal_search_identical_to_oracle(dab, monkeypatch, dt, metric, d
             for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
                 assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, k, Ls, beam)
             # + Pipeline<FilterStartPoints, Rerank>: the candidate list re-scored with Distance<T, T>
-            if vecs.dtype != np.float16:
-                got = g.search_batch_pq(queries, k, Ls, beam, rerank=True)
-                want = oidx.search_batch_rerank(queries, k, Ls, beam=beam, threads=4)
-                for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
-                    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), ("rerank", name, k, Ls, beam)
-            else:
-                with pytest.raises(dab.DabError):
-                    g.search_batch_pq(queries[:2], k, Ls, beam, rerank=True)
+            # (f16 rows: the f16 x f16 schema with two accumulators)
+            got = g.search_batch_pq(queries, k, Ls, beam, rerank=True)
+            want = oidx.search_batch_rerank(queries, k, Ls, beam=beam, threads=4)
+            for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), ("rerank", name, k, Ls, beam)
     with dab.GpuIndex(dab.DType.f32, dab.Metric.Cosine, d, n, 1, maxdeg) as g:
         g.upload_vectors(f32)
         g.upload_graph(adj)
@@ -629,8 +627,11 @@ def test_pq_traversal_search_identical_to_oracle(dab, monkeypatch, dt, metric, d
             want = ocos.search_batch(qf, k, Ls, beam=beam, threads=4)
             for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
                 assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), ("direct cosine", name, k, Ls, beam)
-        with pytest.raises(dab.DabError):
-            g.search_batch_pq(qf[:2], 5, 10, 1, rerank=True)  # float cosine rerank: not carried by the rerank stage
+            # rerank with the float cosine schema (two accumulators, FullCosineAccumulator)
+            got = g.search_batch_pq(qf, k, Ls, beam, rerank=True)
+            want = ocos.search_batch_rerank(qf, k, Ls, beam=beam, threads=4)
+            for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), ("direct cosine + rerank", name, k, Ls, beam)
 
 
 def sq_quantizer(f32, metric):
@@ -675,11 +676,10 @@ def test_sq_traversal_search_identical_to_oracle(dab, dt, metric, d, nbits):
             want = oidx.search_batch(queries, k, Ls, beam=beam, threads=4)
             for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
                 assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, k, Ls, beam)
-            if vecs.dtype != np.float16:
-                got = g.search_batch_sq(queries, k, Ls, beam, rerank=True)
-                want = oidx.search_batch_rerank(queries, k, Ls, beam=beam, threads=4)
-                for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
-                    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), ("rerank", name, k, Ls, beam)
+            got = g.search_batch_sq(queries, k, Ls, beam, rerank=True)
+            want = oidx.search_batch_rerank(queries, k, Ls, beam=beam, threads=4)
+            for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), ("rerank", name, k, Ls, beam)
         # rows handed over by the host (set_quant_vector) give the same searches
         g.upload_sq(nbits, shift, scale, ssn, mean_norm, rows=rows)
         assert np.array_equal(g.download_sq(), rows)
