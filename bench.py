@@ -61,7 +61,7 @@ TARGET_RECALL = 0.95
 NB = 4            # distinct query batches rotated through the timed loop
 PARITY_PER_BATCH = 256
 L_SWEEP = [10, 15, 20, 25, 30, 40, 50, 60, 70, 80, 90, 100, 120, 140, 160, 200, 250]
-L_SWEEP_PQ = L_SWEEP + [300, 350, 400, 450, 500]  # the PQ traversal kernel holds lists of up to 512 entries
+L_SWEEP_PQ = L_SWEEP + [300, 350, 400, 450, 500, 600, 700, 800, 900, 1000]  # the PQ traversal kernels hold lists of up to 1024 entries
 SEED_BASE, SEED_QUERY, SEED_PQ = 0xD15C0003, 0xD15C0004, 13076402859301299683  # PQ seed of example/product.json
 NP_DTYPE = {"f32": np.float32, "f16": np.float16, "i8": np.int8}
 ELEM = {"f32": 4, "f16": 2, "i8": 1}

@@ -125,11 +125,20 @@ __global__ void __launch_bounds__(512, 1) pq_fused_kernel(const PqFusedParams p)
             if (qn < p.nq && threadIdx.x * 32u < p.c) prefetch_l2(p.ids + (size_t)qn * p.c + threadIdx.x * 32u);
         }
         __syncthreads();
-        for (uint32_t t = threadIdx.x; t < entries; t += blockDim.x) {
-            const uint32_t chunk = t / p.n_centers, center = t - chunk * p.n_centers;
-            const float v = pqs_term<CL>(sq, spiv, p.piv_stride, p.offsets, chunk, center, ip);
-            slut[t] = v;
-            if (p.lut_out) p.lut_out[(size_t)q * entries + t] = v;
+        {   // entry t = chunk * n_centers + center, walked without a division per entry
+            uint32_t chunk = threadIdx.x / p.n_centers, center = threadIdx.x - chunk * p.n_centers;
+            const uint32_t dchunk = blockDim.x / p.n_centers, dcenter = blockDim.x - dchunk * p.n_centers;
+            for (uint32_t t = threadIdx.x; t < entries; t += blockDim.x) {
+                const float v = pqs_term<CL>(sq, spiv, p.piv_stride, p.offsets, chunk, center, ip);
+                slut[t] = v;
+                if (p.lut_out) p.lut_out[(size_t)q * entries + t] = v;
+                chunk += dchunk;
+                center += dcenter;
+                if (center >= p.n_centers) {
+                    center -= p.n_centers;
+                    ++chunk;
+                }
+            }
         }
         __syncthreads();
         if (!p.ids) continue;

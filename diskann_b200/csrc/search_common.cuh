@@ -93,6 +93,87 @@ __device__ __forceinline__ void merge_round(float* qd, uint32_t* qi, uint32_t ca
     __syncwarp();
 }
 
+// The same merge for lists longer than one register tile (QT * 32 entries): the list is walked in CH tiles from the top
+// one down.  Entries only move right, by sh = #new(d_i <= d_old), which does not decrease along the sorted list, and
+// final positions are unique — so a tile's writes (all at or above its own first entry) never touch an entry a lower
+// tile still has to read, and what a lower tile writes above its own range are final positions no upper entry owns.
+template <int QT, int CH>
+__device__ __forceinline__ void merge_round_chunked(float* qd, uint32_t* qi, uint32_t cap, uint32_t& size, uint32_t& cursor_lo,
+                                                    const uint32_t* cid, const float* cd, uint32_t c0, uint32_t m, int lane) {
+    const uint32_t j = (uint32_t)lane;
+    const float dj = j < m ? cd[c0 + j] : __int_as_float(0x7FC00000);
+    const uint32_t idj = j < m ? cid[c0 + j] : 0;
+    const float worst = size == cap ? qd[cap - 1] : __int_as_float(0x7F800000);
+    const bool valid = j < m && dj == dj && !(worst < dj);
+    const unsigned vm = __ballot_sync(kFull, valid);
+    if (!vm) return;
+    uint32_t lo = 0, hi = size;
+    while (__any_sync(kFull, lo < hi)) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (lo < hi) {
+            if (qd[mid] < dj) lo = mid + 1;
+            else hi = mid;
+        }
+    }
+    uint32_t rn = 0;
+    for (unsigned it = vm; it;) {
+        const int i = __ffs(it) - 1;
+        it &= it - 1;
+        const float di = __shfl_sync(kFull, dj, i);
+        rn += (di < dj || (di == dj && (uint32_t)i > j)) ? 1u : 0u;
+    }
+    const uint32_t pos = lo + rn;
+    const bool keep_new = valid && pos < cap;
+    __syncwarp();
+#pragma unroll 1
+    for (int c = CH - 1; c >= 0; --c) {
+        const uint32_t e0 = (uint32_t)c * QT * 32;
+        if (e0 >= size) continue;  // nothing stored in this tile yet (warp-uniform)
+        float od[QT];
+        uint32_t oi[QT], sh[QT];
+#pragma unroll
+        for (int t = 0; t < QT; ++t) {
+            const uint32_t e = e0 + (uint32_t)t * 32 + lane;
+            od[t] = e < size ? qd[e] : __int_as_float(0x7F800000);
+            oi[t] = e < size ? qi[e] : kEmptyV2;
+            sh[t] = 0;
+        }
+        for (unsigned it = vm; it;) {
+            const int i = __ffs(it) - 1;
+            it &= it - 1;
+            const float di = __shfl_sync(kFull, dj, i);
+#pragma unroll
+            for (int t = 0; t < QT; ++t) sh[t] += di <= od[t] ? 1u : 0u;
+        }
+        __syncwarp();  // every lane holds its entries of the tile before any of them is overwritten
+#pragma unroll
+        for (int t = 0; t < QT; ++t) {
+            const uint32_t e = e0 + (uint32_t)t * 32 + lane;
+            const uint32_t ne = e + sh[t];
+            if (e < size && sh[t] != 0 && ne < cap) {
+                qd[ne] = od[t];
+                qi[ne] = oi[t];
+            }
+        }
+        __syncwarp();
+    }
+    if (keep_new) {
+        qd[pos] = dj;
+        qi[pos] = idj;
+    }
+    size = min(cap, size + (uint32_t)__popc(vm));
+    cursor_lo = min(cursor_lo, __reduce_min_sync(kFull, keep_new ? pos : 0xFFFFFFFFu));
+    __syncwarp();
+}
+
+// QT = 4 / 8 / 16: one register tile covers the list (<= 128 / 256 / 512 entries); QT = 32: two tiles of 16 (<= 1024)
+template <int QT>
+__device__ __forceinline__ void merge_any(float* qd, uint32_t* qi, uint32_t cap, uint32_t& size, uint32_t& cursor_lo, const uint32_t* cid,
+                                          const float* cd, uint32_t c0, uint32_t m, int lane) {
+    if constexpr (QT == 32) merge_round_chunked<16, 2>(qd, qi, cap, size, cursor_lo, cid, cd, c0, m, lane);
+    else merge_round<QT>(qd, qi, cap, size, cursor_lo, cid, cd, c0, m, lane);
+}
+
 // ---- exact visited set: bucketed open addressing, 8 ids per 32-byte bucket ------------------
 // The tables are the only data of a search that is re-read (every hop probes ~R buckets of the
 // same 10-20 KB per-query table) while ~0.6 MB of vector rows stream past per query.  Bucket

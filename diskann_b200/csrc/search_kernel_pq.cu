@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchPa
             }
             __syncwarp();
             adc(n);
-            merge_round<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, 0, n, lane);
+            merge_any<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, 0, n, lane);
             nvisited += n;
             cmps += n;
         }
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kPqWarps * 32) search_kernel_pq(const SearchPa
             __syncwarp();
             adc(ncand);
             for (uint32_t c0 = 0; c0 < ncand; c0 += 32)
-                merge_round<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, c0, min(32u, ncand - c0), lane);
+                merge_any<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, c0, min(32u, ncand - c0), lane);
             cmps += ncand;
             hops += nb;
         }
@@ -538,7 +538,7 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     if (mode == 1 && idx->metric == DAB_COSINE)
         return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_sq: the scalar-quantized store supports L2, InnerProduct and CosineNormalized");
     const uint32_t cap = l_search + idx->n_start;
-    if (cap > 512) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: L + #start must be <= 512");
+    if (cap > 1024) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: L + #start must be <= 1024");
     SearchParamsPq p;
     memset(&p, 0, sizeof(p));
     p.adj = idx->d_adj;
@@ -595,6 +595,9 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     off += round_up((size_t)beam * 4, 16);
     p.off_qc = (uint32_t)off;
     if (mode == 1) off += idx->sq_stride;
+    off = round_up(off, 16);
+    p.off_nrow = (uint32_t)off;  // search_kernel_pqs: the adjacency row copied one hop ahead
+    if (mode == 0) off += 96 * 4;
     p.warp_smem = (uint32_t)round_up(off, 16);
     // table metrics with a pivot table that fits shared memory: search_kernel_pqs (pivots resident per SM, entries
     // computed on the fly); everything else — SQ, DirectCosine, wide pivots, > 32 chunks — the per-warp kernel below
@@ -612,8 +615,8 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
         warps = (uint32_t)plan.grid * (uint32_t)plan.warps;
     } else {
         if (smem_block > 200 * 1024) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_search_batch_pq: configuration needs %zu B shared memory per CTA", smem_block);
-        if (mode == 1) kern = cap <= 128 ? search_kernel_pq<4, 1> : cap <= 256 ? search_kernel_pq<8, 1> : search_kernel_pq<16, 1>;
-        else kern = cap <= 128 ? search_kernel_pq<4, 0> : cap <= 256 ? search_kernel_pq<8, 0> : search_kernel_pq<16, 0>;
+        if (mode == 1) kern = cap <= 128 ? search_kernel_pq<4, 1> : cap <= 256 ? search_kernel_pq<8, 1> : cap <= 512 ? search_kernel_pq<16, 1> : search_kernel_pq<32, 1>;
+        else kern = cap <= 128 ? search_kernel_pq<4, 0> : cap <= 256 ? search_kernel_pq<8, 0> : cap <= 512 ? search_kernel_pq<16, 0> : search_kernel_pq<32, 0>;
         DAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block));
         int per_sm = 0;
         DAB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPqWarps * 32, smem_block));

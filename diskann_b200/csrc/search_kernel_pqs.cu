@@ -16,8 +16,12 @@
 //   * a team of four lanes owns one candidate (eight chunks per lane, one 8-byte load of its code bytes); the
 //     sequential chunk-order sum walks the team with three shuffles, so a hop with <= 8 new candidates is one pass;
 //   * a hop's global round trips are issued together: all adjacency words of the row, then all visited-set
-//     buckets, then all CAS inserts, while the code rows of the probable new candidates and the adjacency row of
-//     the probable next node are prefetched into L2.
+//     buckets, then all CAS inserts, while the code rows of the probable new candidates are prefetched into L2;
+//   * one hop ahead: the adjacency row of the node the NEXT hop will most likely expand (the closest unvisited
+//     entry after this hop's node) is copied into the warp's shared memory with cp.async while this hop runs, and
+//     once it has landed the visited-set buckets of its neighbours are prefetched into L2 — when the guess holds
+//     (a candidate of this hop rarely lands in front of it at large L) the next hop starts with its row in
+//     shared memory and its buckets in L2 instead of two dependent DRAM round trips.
 // No tensor cores: byte gathers + short FMA chains; HBM traffic is n_chunks code bytes per candidate + the adjacency.
 #include "dab_common.cuh"
 #include "quant_device.cuh"
@@ -52,6 +56,8 @@ __global__ void __launch_bounds__(kPqsMaxWarps * 32, 1) search_kernel_pqs(const 
     uint32_t* cid = reinterpret_cast<uint32_t*>(base + p.off_cid);
     float* cd = reinterpret_cast<float*>(base + p.off_cd);
     uint32_t* beam_ids = reinterpret_cast<uint32_t*>(base + p.off_beam);
+    uint32_t* nrow = reinterpret_cast<uint32_t*>(base + p.off_nrow);  // adjacency row copied one hop ahead (<= 96 words)
+    const bool spec_ok = p.adj_stride <= 96;
 
     const uint32_t warp_slot = blockIdx.x * (blockDim.x >> 5) + wib;
     const uint32_t nbk = p.n_buckets;
@@ -138,6 +144,7 @@ __global__ void __launch_bounds__(kPqsMaxWarps * 32, 1) search_kernel_pqs(const 
 
         uint32_t size = 0, cursor_lo = 0, cmps = 0, hops = 0, nvisited = 0;
         bool overflow = false;
+        uint32_t spec_id = kEmptyV2;  // the node whose adjacency row is in (or on its way to) nrow
 
         // ---- start points first (groups of <= 32), then the greedy loop; both feed the one ADC + merge below
         uint32_t s0 = 0;
@@ -172,15 +179,40 @@ __global__ void __launch_bounds__(kPqsMaxWarps * 32, 1) search_kernel_pqs(const 
                     __syncwarp();
                 }
                 if (nb == 0) break;
+                // the row copied one hop ahead, if the guess was right
+                uint32_t w0[3] = {kEmptyV2, kEmptyV2, kEmptyV2};
+                bool have_row = false;
+                if (spec_ok) {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                    have_row = spec_id == beam_ids[0];
+                    if (have_row) {
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            const uint32_t j = (uint32_t)t * 32 + lane;
+                            if (j < p.adj_stride) w0[t] = nrow[j];
+                        }
+                    }
+                    __syncwarp();  // nrow has been read before the next copy is issued
+                }
                 {
-                    // the node the next hop will most likely expand (unless a candidate of this hop lands in front of it):
-                    // its adjacency row goes to L2 while this hop runs
+                    // the node the next hop will most likely expand (unless a candidate of this hop lands in front of it)
                     const uint32_t nx = first_unvisited(qi, cursor_lo, lim, lane);
+                    spec_id = kEmptyV2;
                     if (nx < lim) {
-                        const uint8_t* r = reinterpret_cast<const uint8_t*>(p.adj + (size_t)qi[nx] * p.adj_stride);
-                        const uint32_t bytes = p.adj_stride * 4;
-                        if ((uint32_t)lane * 128u < bytes) prefetch_l2(r + (size_t)lane * 128);
-                        if (lane == 31) prefetch_l2(r + bytes - 4);
+                        const uint32_t nid = qi[nx];
+                        const uint32_t* r = p.adj + (size_t)nid * p.adj_stride;
+                        if (spec_ok) {
+                            if ((uint32_t)lane * 4u < p.adj_stride)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(nrow + lane * 4)),
+                                             "l"(r + lane * 4)
+                                             : "memory");
+                            asm volatile("cp.async.commit_group;" ::: "memory");
+                            spec_id = nid;
+                        } else {
+                            const uint32_t bytes = p.adj_stride * 4;
+                            for (uint32_t o = (uint32_t)lane * 128u; o < bytes; o += 32 * 128u) prefetch_l2(reinterpret_cast<const uint8_t*>(r) + o);
+                        }
                     }
                 }
                 for (uint32_t b = 0; b < nb; ++b) {
@@ -193,7 +225,8 @@ __global__ void __launch_bounds__(kPqsMaxWarps * 32, 1) search_kernel_pqs(const 
 #pragma unroll
                         for (int t = 0; t < 3; ++t) {
                             const uint32_t j = g0 + (uint32_t)t * 32 + lane;
-                            wd[t] = j < p.adj_stride ? __ldg(row + j) : kEmptyV2;
+                            if (b == 0 && have_row) wd[t] = w0[t];  // (adj_stride <= 96: one pass covers the row)
+                            else wd[t] = j < p.adj_stride ? __ldg(row + j) : kEmptyV2;
                         }
                         if (g0 == 0) deg = min(__shfl_sync(kFull, wd[0], 0), p.max_degree);
                         // every bucket in one round trip
@@ -264,8 +297,20 @@ __global__ void __launch_bounds__(kPqsMaxWarps * 32, 1) search_kernel_pqs(const 
             }
             __syncwarp();
             adc(ncand);
+            if (spec_id != kEmptyV2) {
+                // the next hop's row has landed by now: its neighbours' visited-set buckets go to L2 during the merge
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                const uint32_t d2 = min(nrow[0], p.max_degree);
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const uint32_t j = (uint32_t)t * 32 + lane;
+                    if (j >= 1 && j <= d2)
+                        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(table + (size_t)bucket_of(nrow[j], nbk) * 8));
+                }
+            }
             for (uint32_t c0 = 0; c0 < ncand; c0 += 32)
-                merge_round<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, c0, min(32u, ncand - c0), lane);
+                merge_any<QT>(qd, qi, p.cap, size, cursor_lo, cid, cd, c0, min(32u, ncand - c0), lane);
             cmps += ncand;
             hops += nb;
         }
@@ -337,7 +382,7 @@ bool pqs_plan(const dab_index* idx, uint32_t warp_smem, uint32_t nq, PqsPlan* ou
 int pqs_launch(dab_index* idx, const SearchParamsPq& p, const PqsPlan& plan, uint32_t cap) {
     void (*kern)(const SearchParamsPq);
 #define DAB_PQS_PICK(CL_)                                                                                        \
-    kern = cap <= 128 ? search_kernel_pqs<4, CL_> : cap <= 256 ? search_kernel_pqs<8, CL_> : search_kernel_pqs<16, CL_>
+    kern = cap <= 128 ? search_kernel_pqs<4, CL_> : cap <= 256 ? search_kernel_pqs<8, CL_> : cap <= 512 ? search_kernel_pqs<16, CL_> : search_kernel_pqs<32, CL_>
     if (plan.chunk_len == 4) DAB_PQS_PICK(4);
     else if (plan.chunk_len == 8) DAB_PQS_PICK(8);
     else DAB_PQS_PICK(0);

@@ -48,7 +48,7 @@ struct SearchParamsPq {
     uint32_t sq_stride;
     int sq_nbits, sq_metric;
     float sq_scale, sq_scale_squared, sq_shift_square_norm, sq_mean_norm;
-    uint32_t warp_smem, off_q, off_qd, off_qi, off_cid, off_cd, off_beam, off_qc;
+    uint32_t warp_smem, off_q, off_qd, off_qi, off_cid, off_cd, off_beam, off_qc, off_nrow;
     // search_kernel_pqs: the pivot table of the CTA in shared memory
     uint32_t piv_stride;  // floats between pivot rows (odd multiple of 4: rows of different centres start in different 16-byte bank groups)
     uint32_t piv_bytes;   // n_centers * piv_stride * 4, the per-warp slices follow

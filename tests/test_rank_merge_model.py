@@ -77,3 +77,58 @@ def test_full_list_accepts_equal_to_worst_and_evicts_it():
     got = merge_round(2, old, np.array([7], np.uint32), np.array([2.0], np.float32))
     assert got == [(1, np.float32(1.0)), (7, np.float32(2.0))]
     assert got == sequential(2, [(np.array([1, 2]), np.array([1.0, 2.0])), (np.array([7]), np.array([2.0]))])
+
+
+def merge_round_in_place_by_tiles(cap, old, ids, dists, tile):
+    """merge_round_chunked of search_common.cuh: the list lives in one array and is rewritten IN PLACE, a tile of
+    `tile` entries at a time from the top tile down (each tile: read all of it, then write the moved entries)."""
+    size = len(old)
+    qd = np.full(cap + 64, np.float32(np.nan), np.float32)
+    qi = np.full(cap + 64, 0xFFFFFFFF, np.uint32)
+    for e, (i, d) in enumerate(old):
+        qi[e], qd[e] = i, d
+    worst = qd[cap - 1] if size == cap else np.float32(np.inf)
+    dists = np.asarray(dists, np.float32)
+    valid = ~np.isnan(dists) & ~(worst < dists)
+    new = [(int(i), np.float32(d), j) for j, (i, d) in enumerate(zip(ids, dists)) if valid[j]]
+    if not new:
+        return list(old)
+    od_all = qd[:size].copy()
+    placed = []
+    for idn, d, j in new:
+        pos = int(np.sum(od_all < d)) + sum(1 for _, e, k in new if e < d or (e == d and k > j))
+        if pos < cap:
+            placed.append((pos, idn, d))
+    n_tiles = (cap + tile - 1) // tile
+    for c in range(n_tiles - 1, -1, -1):
+        e0 = c * tile
+        if e0 >= size:
+            continue
+        regs = [(e, qi[e], qd[e]) for e in range(e0, min(e0 + tile, size))]      # the whole tile is read first ...
+        for e, i, d in regs:                                                    # ... then its moved entries are written
+            sh = sum(1 for _, x, _ in new if x <= d)
+            if sh != 0 and e + sh < cap:
+                qi[e + sh], qd[e + sh] = i, d
+    for pos, idn, d in placed:
+        qi[pos], qd[pos] = idn, d
+    n = min(cap, size + len(new))
+    return [(int(qi[k]), np.float32(qd[k])) for k in range(n)]
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_tile_wise_in_place_merge_equals_the_rank_merge(seed):
+    """Lists longer than one register tile (the PQ traversal with L > 512): walking the tiles from the top one down and
+    rewriting the list in place gives the list the one-tile merge (and hence the sequential inserts) gives."""
+    rng = np.random.default_rng(100 + seed)
+    cap = int(rng.integers(5, 60))
+    tile = int(rng.integers(2, 9))
+    model, next_id = [], 0
+    for _ in range(int(rng.integers(2, 10))):
+        m = int(rng.integers(0, 33))
+        d = rng.choice(np.array([0.0, 0.5, 1.0, 1.0, 2.0, 3.5, 7.0, np.inf, np.nan, -1.0], np.float32), m).astype(np.float32)
+        ids = np.arange(next_id, next_id + m, dtype=np.uint32)
+        next_id += m
+        want = merge_round(cap, model, ids, d)
+        got = merge_round_in_place_by_tiles(cap, model, ids, d, tile)
+        assert [(i, float(x)) for i, x in got] == [(i, float(x)) for i, x in want], (seed, cap, tile)
+        model = want
