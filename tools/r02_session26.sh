@@ -15,7 +15,6 @@ except Exception as e:
     print("$f failed", e); print(open("$O/pq_small_$f.err").read()[-1500:])
 PY
 done
-timeout 900 python bench.py --workload c4_10Mx128_i8_pq32 --no-cpu-baseline --l-search 500 --no-parity --steps 10 > $O/bench_c4_l500.json 2> $O/bench_c4_l500.err; cut -c1-330 $O/bench_c4_l500.json; tail -2 $O/bench_c4_l500.err
 timeout 1200 python bench.py --workload c4_10Mx128_i8_pq32 > $O/bench_c4.json 2> $O/bench_c4.err; cut -c1-330 $O/bench_c4.json; tail -3 $O/bench_c4.err
 timeout 600 python tools/nq_sweep.py c2_1Mx128_f32_l2 2>&1 | tee $O/nq_sweep_c2.txt | tail -12
 ls -la $O
