@@ -18,6 +18,7 @@ SYMBOLS = {
     "dab_last_error": (C.c_char_p, []),
     "dab_set_stream": (_i, [_vp, _vp]),
     "dab_launch_count": (_u64, []),
+    "dab_reload_tuning": (_i, [_vp]),
     "dab_upload_vectors": (_i, [_vp, _vp, _u64, _u64]),
     "dab_upload_vectors_device": (_i, [_vp, _vp, _u64, _u64]),
     "dab_upload_graph": (_i, [_vp, _vp, _u32, _u64, _u64]),

@@ -1,6 +1,8 @@
 // dab_api.cu — handle lifecycle, uploads, error reporting for libdiskann_b200.so.
 #include "dab_common.cuh"
 
+#include <algorithm>
+
 #include <cstdlib>
 
 #include <vector>
@@ -77,6 +79,8 @@ void Tuning::load() {
     pq_ctas_per_sm = num("DAB_PQ_CTAS_PER_SM", 1, 16);
     pq_global_lut = flag("DAB_PQ_GLOBAL_LUT");
     pq_warps = num("DAB_PQ_WARPS", 1, 16);
+    pq_no_spec = flag("DAB_PQ_NO_SPEC");
+    pq_no_code_prefetch = flag("DAB_PQ_NO_CODE_PREFETCH");
     frontier_narrow = flag("DAB_FRONTIER_NARROW");
     v2_stage_bytes = num("DAB_V2_STAGE_BYTES", 1024, 65536);
     v2_ctas_per_sm = num("DAB_V2_CTAS_PER_SM", 1, 64);
@@ -97,6 +101,16 @@ extern "C" {
 
 const char* dab_last_error(void) { return error_buffer(); }
 uint64_t dab_launch_count(void) { return g_launches.load(); }
+
+int dab_reload_tuning(dab_index* idx) {
+    if (!idx) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_reload_tuning: idx is NULL");
+    idx->tune = Tuning();
+    idx->tune.load();
+    // what was learned under the previous settings (visited-set sizes per kernel) is forgotten
+    idx->hint_l = idx->hint_beam = idx->hint_visited = 0;
+    idx->pq_hint_l = idx->pq_hint_beam = idx->pq_hint_visited = 0;
+    return DAB_OK;
+}
 
 int dab_create(dab_index** out, int dtype, int metric, uint32_t dim, uint64_t n_points,
                uint32_t n_start, uint32_t max_degree, int device) {
@@ -213,6 +227,15 @@ int dab_upload_vectors_device(dab_index* idx, const void* d_rows, uint64_t first
     return upload_rows(idx, d_rows, first, count, true);
 }
 
+// degree check of rows that are already on the device (the host path checks before copying): first offending row, or ~0
+__global__ void __launch_bounds__(256) graph_degree_check_kernel(const uint32_t* __restrict__ adj, uint32_t src_stride, uint64_t count,
+                                                                  uint32_t max_degree, unsigned long long* __restrict__ first_bad) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < count; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t len = adj[r * (size_t)src_stride];
+        if (len > max_degree || len + 1 > src_stride) atomicMin(first_bad, (unsigned long long)r);
+    }
+}
+
 static int upload_graph(dab_index* idx, const uint32_t* adj, uint32_t src_stride, uint64_t first, uint64_t count,
                         bool on_device) {
     if (!idx || (!adj && count)) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_upload_graph: NULL argument");
@@ -229,6 +252,21 @@ static int upload_graph(dab_index* idx, const uint32_t* adj, uint32_t src_stride
                 return fail(DAB_ERR_INVALID_ARGUMENT, "dab_upload_graph: row %llu has degree %u > max_degree %u",
                             (unsigned long long)(first + r), len, idx->max_degree);
         }
+    } else {
+        int rc;
+        if ((rc = idx->s_counters.reserve(16))) return rc;
+        unsigned long long* d_bad = (unsigned long long*)idx->s_counters.p;
+        DAB_CUDA(cudaMemsetAsync(d_bad, 0xFF, 8, idx->stream));
+        const int grid = (int)std::min<uint64_t>((count + 255) / 256, (uint64_t)idx->sm_count * 8);
+        graph_degree_check_kernel<<<grid, 256, 0, idx->stream>>>(adj, src_stride, count, idx->max_degree, d_bad);
+        DAB_LAUNCHED();
+        DAB_CUDA(cudaGetLastError());
+        unsigned long long bad = 0;
+        DAB_CUDA(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, idx->stream));
+        DAB_CUDA(cudaStreamSynchronize(idx->stream));
+        if (bad != ~0ull)
+            return fail(DAB_ERR_INVALID_ARGUMENT, "dab_upload_graph_device: row %llu has a degree > max_degree %u (or beyond src_stride %u)",
+                        (unsigned long long)(first + bad), idx->max_degree, src_stride);
     }
     DAB_CUDA(cudaMemcpy2DAsync(idx->d_adj + first * idx->adj_stride, (size_t)idx->adj_stride * 4, adj,
                                (size_t)src_stride * 4, copy_words * 4, count,

@@ -71,6 +71,8 @@ struct Tuning {
     bool tc_resident = false;      // DAB_TC_RESIDENT: tensor-core scan keeps the query tile in shared memory (measured equal to streaming it)
     int pq_ctas_per_sm = 0;        // DAB_PQ_CTAS_PER_SM: resident CTAs (4 warps) per SM of the PQ traversal kernel (default 6)
     bool pq_global_lut = false;    // DAB_PQ_GLOBAL_LUT: PQ traversal with the per-warp table in global memory (search_kernel_pq) also where search_kernel_pqs fits
+    bool pq_no_spec = false;       // DAB_PQ_NO_SPEC: search_kernel_pqs without the adjacency row copied one hop ahead (L2 prefetch of the row only)
+    bool pq_no_code_prefetch = false;  // DAB_PQ_NO_CODE_PREFETCH: search_kernel_pqs without the L2 prefetch of probable candidates' codes
     int pq_warps = 0;              // DAB_PQ_WARPS: cap on the warps (queries in flight) per CTA of search_kernel_pqs (default: what shared memory holds, <= 16)
     int v3_max_cap = 0;            // DAB_V3_MAX_CAP: largest L + #start that still runs search_kernel_v3 (default 24)
     bool v3_generic = false;       // DAB_V3_GENERIC: generic distance loop also for 32 / 64 / 96 / 128-d f32 rows

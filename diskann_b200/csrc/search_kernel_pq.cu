@@ -611,6 +611,8 @@ static int run_search_pq(dab_index* idx, const void* d_queries, uint32_t nq, uin
     if (use_pqs) {
         p.piv_stride = plan.piv_stride;
         p.piv_bytes = plan.piv_bytes;
+        p.spec_row = idx->tune.pq_no_spec ? 0 : 1;
+        p.code_prefetch = idx->tune.pq_no_code_prefetch ? 0 : 1;
         grid = plan.grid;
         warps = (uint32_t)plan.grid * (uint32_t)plan.warps;
     } else {

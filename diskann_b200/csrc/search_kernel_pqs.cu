@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(kPqsMaxWarps * 32, 1) search_kernel_pqs(const 
     float* cd = reinterpret_cast<float*>(base + p.off_cd);
     uint32_t* beam_ids = reinterpret_cast<uint32_t*>(base + p.off_beam);
     uint32_t* nrow = reinterpret_cast<uint32_t*>(base + p.off_nrow);  // adjacency row copied one hop ahead (<= 96 words)
-    const bool spec_ok = p.adj_stride <= 96;
+    const bool spec_ok = p.adj_stride <= 96 && p.spec_row != 0;
+    const bool code_prefetch = p.code_prefetch != 0;
 
     const uint32_t warp_slot = blockIdx.x * (blockDim.x >> 5) + wib;
     const uint32_t nbk = p.n_buckets;
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(kPqsMaxWarps * 32, 1) search_kernel_pqs(const 
                                 }
                                 if (!found) {
                                     if (empty >= 0) {
-                                        if (wd[t] < n_total) prefetch_l2(p.codes + (size_t)wd[t] * p.n_chunks);
+                                        if (code_prefetch && wd[t] < n_total) prefetch_l2(p.codes + (size_t)wd[t] * p.n_chunks);
                                         old[t] = atomicCAS(table + (size_t)bk[t] * 8 + empty, kEmptyV2, wd[t]);
                                         state[t] = 1;
                                     } else {

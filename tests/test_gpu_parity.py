@@ -261,6 +261,30 @@ def test_search_edge_cases(dab):
             g.search_batch(q.astype(np.float16), 10, 10)
 
 
+def test_graph_upload_from_device_memory_is_validated(dab):
+    """dab_upload_graph_device: rows already in HBM get the same degree check as the host path (a kernel instead of a
+    host loop); a valid upload searches like the host upload."""
+    import torch
+    rng = np.random.default_rng(17)
+    n, d = 800, 24
+    vecs, adj, maxdeg = make_index(rng, np.float32, O.L2, n, d, 8, 20)
+    oidx = O.Index(vecs, adj, n, 1, O.L2)
+    q = clustered(rng, 40, d)
+    want = oidx.search_batch(q, 10, 20)
+    with dab.GpuIndex(dab.DType.f32, dab.Metric.L2, d, n, 1, maxdeg) as g:
+        g.upload_vectors(vecs)
+        d_adj = torch.from_numpy(adj.view(np.int32).copy()).cuda()
+        g.upload_graph_device(d_adj.data_ptr(), adj.shape[1], n + 1)
+        got = g.search_batch(q, 10, 20)
+        for a, b in zip(got, want):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        bad = adj.copy()
+        bad[123, 0] = maxdeg + 1
+        d_bad = torch.from_numpy(bad.view(np.int32).copy()).cuda()
+        with pytest.raises(dab.DabError, match="row 123"):
+            g.upload_graph_device(d_bad.data_ptr(), bad.shape[1], n + 1)
+
+
 def test_visited_table_overflow_is_retried_exactly(dab, monkeypatch):
     """Force a tiny visited table: overflowing queries are re-run with a larger table and the
     results stay identical to the oracle."""
