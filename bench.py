@@ -404,7 +404,10 @@ def run_gpu(args):
     # ---- batches in flight (dab_search_batch_async / dab_wait): SLOTS consecutive steps overlap, each on its own
     # slot (stream + visited tables + result buffers), so the draining tail of one batch is filled by the CTAs of
     # the next and, end to end, the copies of one batch run under the kernel of another
-    slots = 1 if is_pq else max(1, min(args.in_flight, dab.MAX_SLOTS))
+    # default: two batches in flight; a strong-scaled shard smaller than half the resident workers (~3400 one-warp
+    # CTAs) keeps four, so that consecutive 10K-query steps still fill the GPU (profiles/r02_nq_sweep_strong_scaling_shares.txt)
+    in_flight = args.in_flight or (4 if nq < 5000 else 2)
+    slots = 1 if is_pq else max(1, min(in_flight, dab.MAX_SLOTS))
     sd = [dict(ids=torch.empty((nq, K), dtype=torch.int32, device="cuda"), dists=torch.empty((nq, K), dtype=torch.float32, device="cuda"),
                counts=torch.empty(nq, dtype=torch.int32, device="cuda"), cmps=torch.empty(nq, dtype=torch.int32, device="cuda"),
                hops=torch.empty(nq, dtype=torch.int32, device="cuda"),
@@ -786,7 +789,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--n-points", type=int, default=0, help="override the workload's point count (C5-shaped runs)")
     ap.add_argument("--l-search", type=int, default=0, help="skip the sweep and use this L")
-    ap.add_argument("--in-flight", type=int, default=2, help="batches kept in flight by the timed loops (1: one at a time)")
+    ap.add_argument("--in-flight", type=int, default=0, help="batches kept in flight by the timed loops (1: one at a time; default 2, or 4 for shards of < 5000 queries)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity gate (tuning runs only)")
     ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed region (for ncu)")

@@ -64,10 +64,10 @@ for slots in (1, 2, 3, 4):
     print(f"nq= 10000 in flight {slots}: {ms:7.3f} ms/step   {1e4 / ms / 1e3:6.3f} M QPS", flush=True)
 # what one rank of a strong-scaled 10K-query batch runs at N = 1, 2, 4, 8 GPUs (no collective on the path, so the
 # per-rank step time IS the job's step time): efficiency(N) = t(10000) / (N * t(10000 / N))
-t1 = {s_: timed(10000, 24, s_) for s_ in (1, 2)}
+t1 = {s_: timed(10000, 24, s_) for s_ in (1, 2, 4)}
 for ngpu in (1, 2, 4, 8):
     nq = 10000 // ngpu
-    for slots in (1, 2):
+    for slots in (1, 2, 4):
         ms = timed(nq, 24, slots)
         print(f"strong-scaling share N={ngpu}: nq={nq:6d} in flight {slots}: {ms:7.3f} ms/step  job {1e4 / ms / 1e3:6.3f} M QPS  "
               f"efficiency {t1[slots] / (ngpu * ms):5.3f}", flush=True)
