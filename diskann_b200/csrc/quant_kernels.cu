@@ -96,14 +96,19 @@ struct PqFusedParams {
     const uint8_t* codes;
     uint64_t n_total;
     float* out;            // [nq][c]
+    uint32_t groups;       // thread groups of the CTA, each with its own table + query (1 or 2)
+    uint32_t group_floats; // floats of shared memory per group (table + query)
 };
 
+// The CTA is split into `groups` equal thread groups (1 or 2), each with its own table and query in shared memory and
+// its own named barrier, so two queries are in flight per SM: one group builds while the other waits for its codes.
 template <int CL>
 __global__ void __launch_bounds__(512, 1) pq_fused_kernel(const PqFusedParams p) {
     extern __shared__ __align__(16) uint8_t fsm[];
     float* spiv = reinterpret_cast<float*>(fsm);
-    float* slut = reinterpret_cast<float*>(fsm + p.piv_bytes);
     const uint32_t entries = p.n_chunks * p.n_centers;
+    const uint32_t gsize = blockDim.x / p.groups, grp = threadIdx.x / gsize, tid = threadIdx.x - grp * gsize;
+    float* slut = reinterpret_cast<float*>(fsm + p.piv_bytes) + (size_t)grp * p.group_floats;
     float* sq = slut + ((entries + 3u) & ~3u);
     {
         const uint32_t total = p.n_centers * p.dim;
@@ -112,23 +117,26 @@ __global__ void __launch_bounds__(512, 1) pq_fused_kernel(const PqFusedParams p)
             spiv[(size_t)c * p.piv_stride + d] = __ldg(p.pivots + e);
         }
     }
+    __syncthreads();  // pivots staged; from here on the groups synchronise on their own barriers (ids 1, 2)
+    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(gsize) : "memory"); };
     const bool ip = p.ip != 0;
-    for (uint32_t q = blockIdx.x; q < p.nq; q += gridDim.x) {
-        __syncthreads();  // pivots staged (first query) / the previous query's LUT no longer read
-        for (uint32_t e = threadIdx.x; e < p.dim; e += blockDim.x) sq[e] = __ldg(p.queries + (size_t)q * p.dim + e);
+    const uint32_t qstep = gridDim.x * p.groups;
+    for (uint32_t q = blockIdx.x * p.groups + grp; q < p.nq; q += qstep) {
+        group_sync();  // the previous query's table is no longer read
+        for (uint32_t e = tid; e < p.dim; e += gsize) sq[e] = __ldg(p.queries + (size_t)q * p.dim + e);
         if (p.ids) {
-            for (uint32_t j = threadIdx.x; j < p.c; j += blockDim.x) {
+            for (uint32_t j = tid; j < p.c; j += gsize) {
                 const uint32_t id = __ldg(p.ids + (size_t)q * p.c + j);
                 if (id != kNoId && id < p.n_total) prefetch_l2(p.codes + (size_t)id * p.n_chunks);
             }
-            const uint32_t qn = q + gridDim.x;  // the ids of this CTA's next query: one 128-byte line per thread
-            if (qn < p.nq && threadIdx.x * 32u < p.c) prefetch_l2(p.ids + (size_t)qn * p.c + threadIdx.x * 32u);
+            const uint32_t qn = q + qstep;  // the ids of this group's next query: one 128-byte line per thread
+            for (uint32_t o = tid * 32u; qn < p.nq && o < p.c; o += gsize * 32u) prefetch_l2(p.ids + (size_t)qn * p.c + o);
         }
-        __syncthreads();
+        group_sync();
         {   // entry t = chunk * n_centers + center, walked without a division per entry
-            uint32_t chunk = threadIdx.x / p.n_centers, center = threadIdx.x - chunk * p.n_centers;
-            const uint32_t dchunk = blockDim.x / p.n_centers, dcenter = blockDim.x - dchunk * p.n_centers;
-            for (uint32_t t = threadIdx.x; t < entries; t += blockDim.x) {
+            uint32_t chunk = tid / p.n_centers, center = tid - chunk * p.n_centers;
+            const uint32_t dchunk = gsize / p.n_centers, dcenter = gsize - dchunk * p.n_centers;
+            for (uint32_t t = tid; t < entries; t += gsize) {
                 const float v = pqs_term<CL>(sq, spiv, p.piv_stride, p.offsets, chunk, center, ip);
                 slut[t] = v;
                 if (p.lut_out) p.lut_out[(size_t)q * entries + t] = v;
@@ -140,9 +148,9 @@ __global__ void __launch_bounds__(512, 1) pq_fused_kernel(const PqFusedParams p)
                 }
             }
         }
-        __syncthreads();
+        group_sync();
         if (!p.ids) continue;
-        for (uint32_t j = threadIdx.x; j < p.c; j += blockDim.x) {
+        for (uint32_t j = tid; j < p.c; j += gsize) {
             const uint32_t id = __ldg(p.ids + (size_t)q * p.c + j);
             if (id == kNoId || id >= p.n_total) {
                 p.out[(size_t)q * p.c + j] = __int_as_float(0x7FC00000);
@@ -378,18 +386,22 @@ static int require_pq(const dab_index* idx, const char* who) {
     return DAB_OK;
 }
 
-// true when the pivot table + one LUT + one query fit the shared memory of a CTA: launches pq_fused_kernel.
+// true when the pivot table + one table + one query fit the shared memory of a CTA: launches pq_fused_kernel.
 // d_lut / d_ids may be NULL (ADC only / LUT only).
-static bool fused_fits(const dab_index* idx, uint32_t* stride_out, size_t* piv_bytes_out, size_t* smem_out) {
+static bool fused_fits(const dab_index* idx, uint32_t* stride_out, size_t* piv_bytes_out, size_t* smem_out, uint32_t* groups_out = nullptr,
+                       uint32_t* group_floats_out = nullptr) {
     uint32_t stride = (uint32_t)round_up(idx->dim, 4);
     if ((stride & 7u) == 0) stride += 4;
     const size_t piv_bytes = (size_t)idx->pq_centers * stride * 4;
     const size_t entries = (size_t)idx->pq_chunks * idx->pq_centers;
-    const size_t smem = piv_bytes + round_up(entries, 4) * 4 + round_up(idx->dim, 4) * 4;
+    const size_t group_floats = round_up(entries, 4) + round_up(idx->dim, 4);  // one table + one query
+    const uint32_t groups = piv_bytes + 2 * group_floats * 4 <= 227 * 1024 ? 2 : 1;  // two queries in flight per SM when both tables fit
     *stride_out = stride;
     *piv_bytes_out = piv_bytes;
-    *smem_out = smem;
-    return smem <= 227 * 1024 && !idx->tune.pq_global_lut;
+    *smem_out = piv_bytes + groups * group_floats * 4;
+    if (groups_out) *groups_out = groups;
+    if (group_floats_out) *group_floats_out = (uint32_t)group_floats;
+    return piv_bytes + group_floats * 4 <= 227 * 1024 && !idx->tune.pq_global_lut;
 }
 
 static int launch_fused(const dab_index* idx, const float* d_queries, uint32_t nq, int lut_metric, float* d_lut, const uint32_t* d_ids,
@@ -398,7 +410,7 @@ static int launch_fused(const dab_index* idx, const float* d_queries, uint32_t n
     memset(&p, 0, sizeof(p));
     uint32_t stride;
     size_t piv_bytes, smem;
-    fused_fits(idx, &stride, &piv_bytes, &smem);
+    fused_fits(idx, &stride, &piv_bytes, &smem, &p.groups, &p.group_floats);
     p.queries = d_queries;
     p.nq = nq;
     p.pivots = idx->d_pivots;
@@ -417,7 +429,7 @@ static int launch_fused(const dab_index* idx, const float* d_queries, uint32_t n
     p.out = d_out;
     void (*kern)(const PqFusedParams) = idx->pq_uniform_len == 4 ? pq_fused_kernel<4> : idx->pq_uniform_len == 8 ? pq_fused_kernel<8> : pq_fused_kernel<0>;
     DAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)std::min<uint32_t>(nq, (uint32_t)idx->sm_count);
+    const int grid = (int)std::min<uint32_t>((nq + p.groups - 1) / p.groups, (uint32_t)idx->sm_count);
     kern<<<grid, 512, smem, idx->stream>>>(p);
     DAB_LAUNCHED();
     DAB_CUDA(cudaGetLastError());
