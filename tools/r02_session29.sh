@@ -13,4 +13,5 @@ timeout 300 python bench.py --in-flight 4 --steps 12 --warmup 4 --no-cpu-baselin
 timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_c2.csv python bench.py --steps 2 --warmup 3 --profile-range --no-cpu-baseline --no-parity > $O/launch_bench.log 2>&1
 timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:search_kernel -s 8 -c 1 -o $O/prof_search_c2_inflight python bench.py --steps 1 --warmup 3 --profile-range --no-cpu-baseline --no-parity > $O/ncu_search_c2.log 2>&1; tail -1 $O/ncu_search_c2.log
 timeout 700 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:search_kernel_pqs -s 3 -c 1 -o $O/prof_pqs_c4 python bench.py --workload c4_10Mx128_i8_pq32 --steps 1 --warmup 3 --profile-range --no-cpu-baseline --no-parity --l-search 800 > $O/ncu_pqs.log 2>&1; tail -1 $O/ncu_pqs.log
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $O/kernel_zoo_pq_launches.csv python tools/kernel_zoo.py pq > $O/kernel_zoo_pq.log 2>&1; tail -1 $O/kernel_zoo_pq.log | cut -c1-200
 ls -la $O
