@@ -1,0 +1,334 @@
+// minmax_kernels.cu — the MinMax quantizer (diskann-quantization/src/minmax): per-vector N-bit compression with the
+// compensation coefficients in front of the codes, and the distances between two compressed vectors.
+//
+//   * MinMaxQuantizer::compress (quantizer.rs:153-228, get_range :117-151, Transform::Null) is scalar and sequential in the
+//     reference: a min / max fold (for one bit: the means of the values below / not below the mean), then one pass that
+//     rounds every value to its code and accumulates norm_squared, code_sum and the loss in index order.  Here one lane
+//     owns one vector and runs exactly those chains; a warp takes 32 vectors at a time and moves them through a
+//     [32][33] shared-memory tile so the global reads are coalesced (row-major in, column access conflict-free), and
+//     the 32 finished rows leave through shared memory as one contiguous byte range.
+//   * MinMax{IP, L2Squared, Cosine, CosineNormalized} over two Data rows (vectors.rs:206-455): an exact integer inner
+//     product of the codes (bits/distances.rs; dp4a on masked fields, popc for one bit) and a five-term f32 epilogue
+//     in the reference's association.  One warp per pair, 4-byte loads of the dense codes.
+// Row layout = the reference's canonical-front Data<NBITS> (meta/vector.rs:377-392): MinMaxCompensation {dim u32, b, n, a,
+// norm_squared} (vectors.rs:43-52, 20 bytes) then ceil(dim * NBITS / 8) bytes of codes, value i at bit i * NBITS.
+// HBM-bound byte work: no tensor cores.
+#include "dab_common.cuh"
+#include "quant_device.cuh"
+
+#include <algorithm>
+
+namespace dab {
+
+constexpr int kMmMeta = 20;
+
+struct MinMaxCompressParams {
+    float grid_scale;
+    uint32_t dim;
+    int nbits;
+    const float* vectors;  // [n][dim]
+    uint64_t n;
+    uint8_t* rows;         // [n][row_bytes]
+    uint32_t row_bytes;
+    uint32_t srow_stride;  // bytes between the staged output rows of a warp (an odd number of words: conflict-free)
+    float* loss;           // [n] or NULL
+    unsigned long long* first_nan;
+    uint32_t warp_smem;    // tile + staged rows
+};
+
+// `walk(f)` calls f(i, v_i) for i = 0 .. dim-1 in index order on the lane's own vector, the warp moving 32 x 32 tiles
+// through shared memory (all lanes must call it together).
+template <typename F>
+__device__ __forceinline__ void walk_rows(const MinMaxCompressParams& p, uint64_t v0, float (*tile)[33], int lane, F&& f) {
+    for (uint32_t t0 = 0; t0 < p.dim; t0 += 32) {
+        __syncwarp();
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            const uint64_t v = v0 + r;
+            tile[r][lane] = (v < p.n && t0 + lane < p.dim) ? __ldg(p.vectors + v * p.dim + t0 + lane) : 0.0f;
+        }
+        __syncwarp();
+        const uint32_t m = min(32u, p.dim - t0);
+        for (uint32_t j = 0; j < m; ++j) f(t0 + j, tile[lane][j]);
+    }
+}
+
+__global__ void __launch_bounds__(128) minmax_compress_kernel(const MinMaxCompressParams p) {
+    extern __shared__ __align__(16) uint8_t mm_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint8_t* base = mm_smem + (size_t)wib * p.warp_smem;
+    float (*tile)[33] = reinterpret_cast<float (*)[33]>(base);
+    uint8_t* srows = base + 32 * 33 * 4;
+    uint8_t* mine = srows + (size_t)lane * p.srow_stride;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    const float domain_max = (float)((1u << p.nbits) - 1u);
+    const uint32_t code_bytes = p.row_bytes - kMmMeta;
+
+    for (uint64_t v0 = ((uint64_t)blockIdx.x * (blockDim.x >> 5) + wib) * 32; v0 < p.n; v0 += (uint64_t)warps * 32) {
+        // ---- get_range (quantizer.rs:117-151)
+        float mn, mx;
+        if (p.nbits == 1) {
+            float sum = -0.0f;  // <f32 as Sum>::sum folds from -0.0
+            walk_rows(p, v0, tile, lane, [&](uint32_t, float e) { sum = __fadd_rn(sum, e); });
+            const float mean = __fdiv_rn(sum, (float)p.dim);
+            float a = 0.0f, ac = 0.0f, b = 0.0f, bc = 0.0f;
+            walk_rows(p, v0, tile, lane, [&](uint32_t, float e) {
+                const float m = e < mean ? 1.0f : 0.0f;
+                a = __fadd_rn(a, __fmul_rn(m, e));
+                ac = __fadd_rn(ac, m);
+                b = __fadd_rn(b, __fmul_rn(__fsub_rn(1.0f, m), e));
+                bc = __fadd_rn(bc, __fsub_rn(1.0f, m));
+            });
+            mn = fminf(__fdiv_rn(a, ac), mean);  // f32::min / max: the other operand when one is NaN (fminf / fmaxf do the same)
+            mx = fmaxf(__fdiv_rn(b, bc), mean);
+        } else {
+            mn = mx = __int_as_float(0x7FC00000);
+            walk_rows(p, v0, tile, lane, [&](uint32_t, float e) {
+                mn = fminf(mn, e);
+                mx = fmaxf(mx, e);
+            });
+        }
+        const float width = __fdiv_rn(__fsub_rn(mx, mn), 2.0f);
+        const float mid = __fadd_rn(mn, width);
+        const float lo = __fsub_rn(mid, __fmul_rn(width, p.grid_scale));
+        const float hi = __fadd_rn(mid, __fmul_rn(width, p.grid_scale));
+        const float inverse_scale = __fdiv_rn(fmaxf(__fsub_rn(hi, lo), 1e-8f), domain_max);
+
+        // ---- codes + the three sequential sums (quantizer.rs:186-209); codes packed value i at bit i * nbits
+        for (uint32_t w = 0; w < (code_bytes + 3) / 4; ++w) reinterpret_cast<uint32_t*>(mine + kMmMeta)[w] = 0;  // (stays inside the lane's stride)
+        float norm_squared = 0.0f, code_sum = 0.0f, loss = 0.0f;
+        bool nan = false;
+        const int nbits = p.nbits;
+        walk_rows(p, v0, tile, lane, [&](uint32_t i, float e) {
+            nan |= e != e;
+            const float t = __fdiv_rn(__fsub_rn(e, lo), inverse_scale);
+            float code = t != t ? t : (t < 0.0f ? 0.0f : (t > domain_max ? domain_max : t));  // f32::clamp keeps NaN
+            code = roundf(code);                                                              // half away from zero
+            const float vr = __fadd_rn(__fmul_rn(code, inverse_scale), lo);
+            norm_squared = __fadd_rn(norm_squared, __fmul_rn(vr, vr));
+            code_sum = __fadd_rn(code_sum, code);
+            const float d = __fsub_rn(vr, e);
+            loss = __fadd_rn(loss, __fmul_rn(d, d));
+            const uint32_t c = code != code ? 0u : (uint32_t)code;  // `as u8`: NaN -> 0
+            const uint32_t bit = i * (uint32_t)nbits;
+            mine[kMmMeta + (bit >> 3)] |= (uint8_t)(c << (bit & 7u));
+        });
+        {   // MinMaxCompensation {dim, b, n, a, norm_squared}
+            uint32_t* mw = reinterpret_cast<uint32_t*>(mine);
+            mw[0] = p.dim;
+            mw[1] = __float_as_uint(lo);
+            mw[2] = __float_as_uint(__fmul_rn(inverse_scale, code_sum));
+            mw[3] = __float_as_uint(inverse_scale);
+            mw[4] = __float_as_uint(norm_squared);
+        }
+        const uint64_t v = v0 + lane;
+        if (v < p.n) {
+            if (p.loss) p.loss[v] = loss;
+            if (nan) atomicMin(p.first_nan, (unsigned long long)v);
+        }
+        __syncwarp();
+        // ---- the 32 rows of the warp are one contiguous byte range of the output
+        const uint64_t nrows = min((uint64_t)32, p.n - v0);
+        for (uint32_t r = 0; r < nrows; ++r) {
+            const uint8_t* src = srows + (size_t)r * p.srow_stride;
+            uint8_t* dst = p.rows + (v0 + r) * p.row_bytes;
+            for (uint32_t bb = lane; bb < p.row_bytes; bb += 32) dst[bb] = src[bb];
+        }
+        __syncwarp();
+    }
+}
+
+struct MinMaxDistanceParams {
+    int metric, nbits_x, nbits_y;
+    uint32_t dim;
+    const uint8_t* x;
+    const uint8_t* y;
+    uint32_t row_bytes_x, row_bytes_y;
+    uint64_t n;
+    float* out;
+};
+
+__device__ __forceinline__ uint32_t mm_code_at(const uint8_t* codes, uint32_t i, int nbits) {
+    const uint32_t bit = i * (uint32_t)nbits;
+    return ((uint32_t)__ldg(codes + (bit >> 3)) >> (bit & 7u)) & ((1u << nbits) - 1u);
+}
+
+// one warp per pair
+__global__ void __launch_bounds__(256) minmax_distance_kernel(const MinMaxDistanceParams p) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const bool words = p.nbits_x == p.nbits_y && (p.row_bytes_x & 3u) == 0 && (p.row_bytes_y & 3u) == 0;
+    for (uint64_t i = warp; i < p.n; i += nwarps) {
+        const uint8_t* xr = p.x + i * p.row_bytes_x;
+        const uint8_t* yr = p.y + i * p.row_bytes_y;
+        uint32_t ip = 0, unused = 0;
+        if (words) {
+            // same width on both sides: whole 32-bit words of the dense codes (padding bits are zero)
+            const uint32_t* xw = reinterpret_cast<const uint32_t*>(xr + kMmMeta);
+            const uint32_t* yw = reinterpret_cast<const uint32_t*>(yr + kMmMeta);
+            const uint32_t nw = (p.row_bytes_x - kMmMeta) >> 2;
+            for (uint32_t w = lane; w < nw; w += 32) {
+                const uint32_t a = __ldg(xw + w), b = __ldg(yw + w);
+                switch (p.nbits_x) {
+                    case 8: sq_word<8>(a, b, true, unused, ip); break;
+                    case 4: sq_word<4>(a, b, true, unused, ip); break;
+                    case 2: sq_word<2>(a, b, true, unused, ip); break;
+                    default: sq_word<1>(a, b, true, unused, ip); break;
+                }
+            }
+        } else {
+            for (uint32_t e = lane; e < p.dim; e += 32) ip += mm_code_at(xr + kMmMeta, e, p.nbits_x) * mm_code_at(yr + kMmMeta, e, p.nbits_y);
+        }
+        ip = __reduce_add_sync(kFull, ip);
+        if (lane == 0) {
+            const uint32_t* xm = reinterpret_cast<const uint32_t*>(xr);  // rows are at least 4-byte aligned only when
+            const uint32_t* ym = reinterpret_cast<const uint32_t*>(yr);  // row_bytes % 4 == 0: read the meta bytewise otherwise
+            float xb, xn, xa, xq, yb, yn, ya, yq;
+            uint32_t dx, dy;
+            if (((p.row_bytes_x | p.row_bytes_y) & 3u) == 0) {
+                dx = xm[0], xb = __uint_as_float(xm[1]), xn = __uint_as_float(xm[2]), xa = __uint_as_float(xm[3]), xq = __uint_as_float(xm[4]);
+                dy = ym[0], yb = __uint_as_float(ym[1]), yn = __uint_as_float(ym[2]), ya = __uint_as_float(ym[3]), yq = __uint_as_float(ym[4]);
+            } else {
+                auto rd = [](const uint8_t* q) { return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24); };
+                dx = rd(xr), xb = __uint_as_float(rd(xr + 4)), xn = __uint_as_float(rd(xr + 8)), xa = __uint_as_float(rd(xr + 12)), xq = __uint_as_float(rd(xr + 16));
+                dy = rd(yr), yb = __uint_as_float(rd(yr + 4)), yn = __uint_as_float(rd(yr + 8)), ya = __uint_as_float(rd(yr + 12)), yq = __uint_as_float(rd(yr + 16));
+            }
+            float r;
+            if (dx != dy || dx != p.dim) {
+                r = __int_as_float(0x7FC00000);  // UnequalLengths
+            } else {
+                // vectors.rs:206-228: term0 + term1_x + term1_y + term2, left to right
+                const float term0 = __fmul_rn(__fmul_rn(xa, ya), (float)ip);
+                const float term1_x = __fmul_rn(xn, yb);
+                const float term1_y = __fmul_rn(yn, xb);
+                const float term2 = __fmul_rn(__fmul_rn(xb, yb), (float)dx);
+                const float v = __fadd_rn(__fadd_rn(__fadd_rn(term0, term1_x), term1_y), term2);
+                if (p.metric == DAB_INNER_PRODUCT) r = -v;
+                else if (p.metric == DAB_L2) r = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, v), xq), yq);
+                else if (p.metric == DAB_COSINE) r = __fsub_rn(1.0f, __fdiv_rn(v, __fmul_rn(__fsqrt_rn(xq), __fsqrt_rn(yq))));
+                else r = __fsub_rn(1.0f, v);
+            }
+            p.out[i] = r;
+        }
+    }
+}
+
+}  // namespace dab
+
+using namespace dab;
+
+static bool mm_bits_ok(int nbits) { return nbits == 1 || nbits == 2 || nbits == 4 || nbits == 8; }
+
+extern "C" {
+
+uint32_t dab_minmax_row_bytes(uint32_t dim, int nbits) { return mm_bits_ok(nbits) ? kMmMeta + (uint32_t)(((uint64_t)dim * nbits + 7) / 8) : 0; }
+
+int dab_minmax_compress(int device, float grid_scale, uint32_t dim, int nbits, const float* vectors, uint64_t n, uint8_t* out_rows,
+                        float* out_loss) {
+    if (!mm_bits_ok(nbits)) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_minmax_compress: nbits must be 1, 2, 4 or 8");
+    if (!(grid_scale > 0.0f)) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_minmax_compress: grid_scale must be positive (num::Positive)");
+    if (n == 0) return DAB_OK;
+    if (!vectors || !out_rows || dim == 0) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_minmax_compress: NULL argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(DAB_ERR_NO_DEVICE, "dab_minmax_compress: no CUDA device visible");
+    DAB_CUDA(cudaSetDevice(device));
+    MinMaxCompressParams p;
+    memset(&p, 0, sizeof(p));
+    p.grid_scale = grid_scale;
+    p.dim = dim;
+    p.nbits = nbits;
+    p.n = n;
+    p.row_bytes = dab_minmax_row_bytes(dim, nbits);
+    uint32_t words = (p.row_bytes + 3) / 4;
+    if ((words & 1u) == 0) ++words;
+    p.srow_stride = words * 4;
+    p.warp_smem = 32 * 33 * 4 + 32 * p.srow_stride;
+    int warps = 4;
+    while (warps > 1 && (size_t)warps * p.warp_smem > 200 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * p.warp_smem;
+    if (smem > 200 * 1024) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_minmax_compress: rows of %u bytes do not fit the staging buffers", p.row_bytes);
+    float *d_vec = nullptr, *d_loss = nullptr;
+    uint8_t* d_rows = nullptr;
+    unsigned long long* d_nan = nullptr;
+    cudaError_t e = cudaMalloc(&d_vec, n * dim * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_rows, n * p.row_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_loss, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_nan, 8);
+    if (e == cudaSuccess) e = cudaMemcpy(d_vec, vectors, n * dim * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_nan, 0xFF, 8);
+    unsigned long long first_nan = ~0ull;
+    if (e == cudaSuccess) {
+        p.vectors = d_vec;
+        p.rows = d_rows;
+        p.loss = d_loss;
+        p.first_nan = d_nan;
+        e = cudaFuncSetAttribute(minmax_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            const uint64_t groups = (n + 31) / 32;
+            const int grid = (int)std::min<uint64_t>((groups + warps - 1) / warps, 148ull * 8);
+            minmax_compress_kernel<<<grid, warps * 32, smem>>>(p);
+            DAB_LAUNCHED();
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_rows, d_rows, n * p.row_bytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_loss) e = cudaMemcpy(out_loss, d_loss, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(&first_nan, d_nan, 8, cudaMemcpyDeviceToHost);
+    int rc = DAB_OK;
+    if (e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? DAB_ERR_OUT_OF_MEMORY : DAB_ERR_CUDA, "dab_minmax_compress: %s", cudaGetErrorString(e));
+    else if (first_nan != ~0ull)
+        rc = fail(DAB_ERR_INVALID_ARGUMENT, "dab_minmax_compress: vector %llu contains NaN (InputContainsNaN); its row was written all the same", first_nan);
+    cudaFree(d_vec);
+    cudaFree(d_rows);
+    cudaFree(d_loss);
+    cudaFree(d_nan);
+    return rc;
+}
+
+int dab_minmax_distances(int device, int metric, int nbits_x, int nbits_y, uint32_t dim, const uint8_t* x_rows, const uint8_t* y_rows,
+                         uint64_t n, float* out) {
+    if (!mm_bits_ok(nbits_x) || !mm_bits_ok(nbits_y)) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_minmax_distances: nbits must be 1, 2, 4 or 8");
+    if (nbits_x != nbits_y && nbits_x != 8)
+        return fail(DAB_ERR_INVALID_ARGUMENT, "dab_minmax_distances: the reference pairs N x N and 8 x N bit vectors (got %d x %d)", nbits_x, nbits_y);
+    if (metric < DAB_COSINE || metric > DAB_COSINE_NORMALIZED) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_minmax_distances: unknown metric %d", metric);
+    if (n == 0) return DAB_OK;
+    if (!x_rows || !y_rows || !out || dim == 0) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_minmax_distances: NULL argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(DAB_ERR_NO_DEVICE, "dab_minmax_distances: no CUDA device visible");
+    DAB_CUDA(cudaSetDevice(device));
+    MinMaxDistanceParams p;
+    memset(&p, 0, sizeof(p));
+    p.metric = metric;
+    p.nbits_x = nbits_x;
+    p.nbits_y = nbits_y;
+    p.dim = dim;
+    p.row_bytes_x = dab_minmax_row_bytes(dim, nbits_x);
+    p.row_bytes_y = dab_minmax_row_bytes(dim, nbits_y);
+    p.n = n;
+    uint8_t *dx = nullptr, *dy = nullptr;
+    float* dout = nullptr;
+    cudaError_t e = cudaMalloc(&dx, n * p.row_bytes_x);
+    if (e == cudaSuccess) e = cudaMalloc(&dy, n * p.row_bytes_y);
+    if (e == cudaSuccess) e = cudaMalloc(&dout, n * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, x_rows, n * p.row_bytes_x, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dy, y_rows, n * p.row_bytes_y, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        p.x = dx;
+        p.y = dy;
+        p.out = dout;
+        const int grid = (int)std::min<uint64_t>((n + 7) / 8, 148ull * 8);
+        minmax_distance_kernel<<<grid, 256>>>(p);
+        DAB_LAUNCHED();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost);
+    int rc = DAB_OK;
+    if (e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? DAB_ERR_OUT_OF_MEMORY : DAB_ERR_CUDA, "dab_minmax_distances: %s", cudaGetErrorString(e));
+    cudaFree(dx);
+    cudaFree(dy);
+    cudaFree(dout);
+    return rc;
+}
+
+}  // extern "C"

@@ -35,27 +35,6 @@
 
 namespace dab {
 
-// integer cores over one 32-bit word of dense NBITS codes (fields never straddle bytes for 1/2/4/8 bits)
-template <int NBITS>
-__device__ __forceinline__ void sq_word(uint32_t a, uint32_t b, bool want_ip, uint32_t& l2, uint32_t& ip) {
-    if (NBITS == 1) {
-        if (want_ip) ip += __popc(a & b);
-        else l2 += __popc(a ^ b);
-        return;
-    }
-    constexpr uint32_t kMask = NBITS == 8 ? 0xFFFFFFFFu : NBITS == 4 ? 0x0F0F0F0Fu : 0x03030303u;
-#pragma unroll
-    for (int sh = 0; sh < 8; sh += NBITS) {
-        const uint32_t x = (a >> sh) & kMask, y = (b >> sh) & kMask;
-        if (want_ip) {
-            ip = __dp4a(x, y, ip);
-        } else {
-            const uint32_t d = __vabsdiffu4(x, y);
-            l2 = __dp4a(d, d, l2);
-        }
-    }
-}
-
 template <int NBITS>
 __device__ __forceinline__ void sq_row(const uint4* __restrict__ row, const uint4* qc, uint32_t vecs, bool want_ip, uint32_t& l2,
                                        uint32_t& ip) {

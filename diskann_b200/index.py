@@ -79,6 +79,30 @@ def distance_comparer(metric, dim=None, device=0):
     return call
 
 
+def minmax_compress(vectors, nbits, grid_scale=1.0, device=0):
+    """MinMaxQuantizer (Transform::Null) over the rows of `vectors` [n, dim] f32: (rows u8 [n, 20 + ceil(dim * nbits / 8)]
+    in the reference's canonical-front Data<NBITS> layout, loss f32 [n]).  Raises DabError when a vector contains NaN."""
+    vectors = np.ascontiguousarray(vectors, np.float32)
+    if vectors.ndim != 2:
+        raise DabError(1, "minmax_compress: vectors must be [n, dim] f32")
+    n, dim = vectors.shape
+    rb = _lib.lib().dab_minmax_row_bytes(dim, nbits)
+    rows = np.zeros((n, rb), np.uint8)
+    loss = np.zeros(n, np.float32)
+    check(_lib.lib().dab_minmax_compress(device, grid_scale, dim, nbits, _ptr(vectors), n, _ptr(rows), _ptr(loss)))
+    return rows, loss
+
+
+def minmax_distances(metric, nbits_x, nbits_y, dim, x_rows, y_rows, device=0):
+    """MinMax{L2Squared, IP, Cosine, CosineNormalized} between compressed rows: out[i] = d(x_rows[i], y_rows[i])."""
+    x_rows = np.ascontiguousarray(x_rows, np.uint8)
+    y_rows = np.ascontiguousarray(y_rows, np.uint8)
+    n = x_rows.shape[0]
+    out = np.empty(n, np.float32)
+    check(_lib.lib().dab_minmax_distances(device, int(metric), nbits_x, nbits_y, dim, _ptr(x_rows), _ptr(y_rows), n, _ptr(out)))
+    return out
+
+
 class GpuIndex:
     """Device-resident snapshot of an in-memory index: vectors + adjacency (+ PQ)."""
 

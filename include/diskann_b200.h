@@ -288,6 +288,28 @@ int dab_search_batch_sq_device(dab_index* idx, const void* d_queries, uint32_t n
                                uint32_t beam_width, int rerank, uint32_t* d_out_ids, float* d_out_dists,
                                uint32_t* d_out_counts, uint32_t* d_out_cmps, uint32_t* d_out_hops);
 
+/* ------------------------------------------------------------------ MinMax quantization */
+
+/* The per-vector N-bit quantizer of diskann-quantization/src/minmax (NBITS = 1, 2, 4, 8; Transform::Null).  Rows use the
+ * reference's canonical-front layout of minmax::Data<NBITS> (meta/vector.rs:377-392): MinMaxCompensation
+ * {dim: u32, b, n, a, norm_squared} (vectors.rs:43-52, 20 bytes) followed by ceil(dim * NBITS / 8) bytes of dense codes,
+ * value i at bit i * NBITS — so rows written here can be handed to DataRef::from_canonical_front and back. */
+uint32_t dab_minmax_row_bytes(uint32_t dim, int nbits);  /* Data::<NBITS>::canonical_bytes(dim); 0 for an unsupported width */
+
+/* MinMaxQuantizer::new(Transform::Null(dim), grid_scale) + CompressInto<&[f32], DataMutRef<NBITS>> for n vectors
+ * (quantizer.rs:153-228, get_range :117-151): out_rows [n][dab_minmax_row_bytes], out_loss [n] (L2Loss, may be NULL).
+ * An input vector containing NaN makes the call fail (InputContainsNaN, naming the first such vector) after every row
+ * has been written, the way the reference sets the meta before returning the error. */
+int dab_minmax_compress(int device, float grid_scale, uint32_t dim, int nbits, const float* vectors, uint64_t n,
+                        uint8_t* out_rows, float* out_loss);
+
+/* PureDistanceFunction<DataRef<NBITS>, DataRef<MBITS>, distances::Result<f32>> for MinMaxL2Squared / MinMaxIP (negated) /
+ * MinMaxCosine / MinMaxCosineNormalized (vectors.rs:206-455), selected by `metric` (Metric repr): out[i] = d(x_rows[i],
+ * y_rows[i]).  Widths: N x N, and 8 x N (the pairings the reference instantiates).  Rows whose stored dimension differs
+ * from `dim` give NaN (UnequalLengths). */
+int dab_minmax_distances(int device, int metric, int nbits_x, int nbits_y, uint32_t dim, const uint8_t* x_rows,
+                         const uint8_t* y_rows, uint64_t n, float* out);
+
 /* ------------------------------------------------------------------ build-side reuse */
 
 /* PruneAccessor::fill + robust_prune (diskann/src/graph/index.rs:2349-2380, 2565-2650;

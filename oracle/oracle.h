@@ -224,6 +224,17 @@ double orc_recall(const uint32_t* gt, uint32_t gt_stride, const uint32_t* res,
 
 int orc_hardware_threads(void);
 
+/* ---------------------------------------------------------------- MinMax quantizer (oracle/minmax.cpp)
+ * diskann-quantization/src/minmax/{quantizer.rs, vectors.rs}, Transform::Null.  Rows use the canonical-front layout of
+ * Data<NBITS>: MinMaxCompensation {dim u32, b, n, a, norm_squared} (20 bytes), then dense N-bit codes.
+ * Pinned by the reference's own closed-form and property tests (quantizer.rs:473-756, vectors.rs:520-700), restated in
+ * tests/test_oracle_minmax.py with the reference's tolerances; seeded with Rust's StdRng there, own seeds here. */
+size_t orc_minmax_row_bytes(size_t dim, int nbits);
+int orc_minmax_compress(float grid_scale, size_t dim, int nbits, const float* v, uint8_t* row, float* loss_out);
+int orc_minmax_full_query_meta(const float* v, size_t dim, float* sum_out, float* norm_squared_out);
+float orc_minmax_distance(int metric, int nbits_x, int nbits_y, const uint8_t* x_row, const uint8_t* y_row);
+void orc_minmax_decompress(const uint8_t* row, int nbits, float* out);
+
 #ifdef __cplusplus
 }
 #endif

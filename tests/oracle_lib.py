@@ -84,6 +84,16 @@ def lib():
     L.orc_sq_compress.argtypes = [vp, f, sz, i, vp, vp, C.POINTER(C.c_int)]
     L.orc_sq_distance.restype = f
     L.orc_sq_distance.argtypes = [i, i, f, f, vp, f, vp, f, sz]
+    L.orc_minmax_row_bytes.restype = sz
+    L.orc_minmax_row_bytes.argtypes = [sz, i]
+    L.orc_minmax_compress.restype = i
+    L.orc_minmax_compress.argtypes = [f, sz, i, vp, vp, vp]
+    L.orc_minmax_full_query_meta.restype = i
+    L.orc_minmax_full_query_meta.argtypes = [vp, sz, vp, vp]
+    L.orc_minmax_distance.restype = f
+    L.orc_minmax_distance.argtypes = [i, i, i, vp, vp]
+    L.orc_minmax_decompress.restype = None
+    L.orc_minmax_decompress.argtypes = [vp, i, vp]
     L.orc_search.restype = u32
     L.orc_search.argtypes = [C.POINTER(OrcIndex), vp, u32, u32, u32, i, vp, vp, vp, vp]
     L.orc_search_batch.restype = None
@@ -292,3 +302,33 @@ def recall(gt, res, counts, k, n):
     res = np.ascontiguousarray(res, np.uint32)
     c = None if counts is None else np.ascontiguousarray(counts, np.uint32)
     return lib().orc_recall(ptr(gt), gt.shape[1], ptr(res), res.shape[1], ptr(c), gt.shape[0], k, n)
+
+
+# ---------------------------------------------------------------- MinMax quantizer
+
+def minmax_compress(vectors, nbits, grid_scale=1.0):
+    """MinMaxQuantizer::compress for every row: (rows u8 [n, 20 + ceil(dim * nbits / 8)], loss f32 [n], nan flags)."""
+    vectors = np.ascontiguousarray(vectors, np.float32)
+    n, dim = vectors.shape
+    L = lib()
+    rb = L.orc_minmax_row_bytes(dim, nbits)
+    rows = np.zeros((n, rb), np.uint8)
+    loss = np.zeros(n, np.float32)
+    nan = np.zeros(n, bool)
+    for r in range(n):
+        nan[r] = L.orc_minmax_compress(grid_scale, dim, nbits, ptr(vectors[r]), ptr(rows[r]), ptr(loss[r:r + 1])) != 0
+    return rows, loss, nan
+
+
+def minmax_distances(metric, nbits_x, nbits_y, x_rows, y_rows):
+    L = lib()
+    return np.array([L.orc_minmax_distance(metric, nbits_x, nbits_y, ptr(x_rows[r]), ptr(y_rows[r])) for r in range(x_rows.shape[0])],
+                    np.float32)
+
+
+def minmax_decompress(rows, nbits, dim):
+    L = lib()
+    out = np.zeros((rows.shape[0], dim), np.float32)
+    for r in range(rows.shape[0]):
+        L.orc_minmax_decompress(ptr(rows[r]), nbits, ptr(out[r]))
+    return out

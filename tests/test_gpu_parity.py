@@ -406,6 +406,51 @@ def test_pq_lut_adc_encode_bit_exact(dab, monkeypatch, metric, dim, chunks, path
             g.pq_encode(bad)
 
 
+# ---------------------------------------------------------------- MinMax quantization
+
+@pytest.mark.parametrize("nbits", [8, 4, 2, 1])
+def test_minmax_compress_and_distances_bit_exact(dab, nbits):
+    """dab_minmax_compress / dab_minmax_distances == the oracle's restatement of MinMaxQuantizer::compress and
+    MinMax{L2Squared, IP, Cosine, CosineNormalized} (diskann-quantization/src/minmax), byte for byte and bit for bit:
+    every dimension 1..70 plus wide rows (row lengths that are and are not multiples of four bytes), three grid scales,
+    constant vectors, the N x N and 8 x N pairings, NaN input."""
+    rng = np.random.default_rng(40 + nbits)
+    for dim, n, scale in [(d, 70, 1.0) for d in range(1, 71)] + [(128, 3000, 1.0), (100, 1000, 0.9), (257, 300, 1.1), (768, 200, 1.0)]:
+        v = rng.uniform(-1.0, 1.0, (n, dim)).astype(np.float32)
+        v[0] = 42.5                       # min == max (quantizer.rs:632)
+        if n > 3:
+            v[1] = 0.0
+            v[2, ::2] = -10.0             # two distinct values
+            v[2, 1::2] = 15.0
+        want_rows, want_loss, want_nan = O.minmax_compress(v, nbits, scale)
+        assert not want_nan.any()
+        rows, loss = dab.minmax_compress(v, nbits, scale)
+        assert rows.shape == want_rows.shape and np.array_equal(rows, want_rows), (dim, nbits)
+        assert same_bits(loss, want_loss), (dim, nbits)
+        perm = rng.permutation(n)
+        for metric in METRICS:
+            got = dab.minmax_distances(metric, nbits, nbits, dim, rows, rows[perm])
+            want = O.minmax_distances(metric, nbits, nbits, want_rows, want_rows[perm])
+            assert same_bits(got, want), (dim, nbits, metric)
+        if nbits != 8 and dim in (17, 64, 100, 128):
+            rows8, _ = dab.minmax_compress(v, 8, scale)
+            want8, _, _ = O.minmax_compress(v, 8, scale)
+            assert np.array_equal(rows8, want8)
+            for metric in METRICS:
+                got = dab.minmax_distances(metric, 8, nbits, dim, rows8, rows[perm])
+                want = O.minmax_distances(metric, 8, nbits, want8, want_rows[perm])
+                assert same_bits(got, want), ("8 x N", dim, nbits, metric)
+    # InputContainsNaN: the call fails, naming the vector (quantizer.rs:728-750)
+    bad = rng.uniform(-1.0, 1.0, (40, 100)).astype(np.float32)
+    bad[33, 7] = np.nan
+    with pytest.raises(dab.DabError, match="vector 33"):
+        dab.minmax_compress(bad, nbits)
+    with pytest.raises(dab.DabError):
+        dab.minmax_compress(bad[:2], 3)                      # no Representation<3>
+    with pytest.raises(dab.DabError):
+        dab.minmax_distances(O.L2, 4, 8, 100, np.zeros((1, 70), np.uint8), np.zeros((1, 120), np.uint8))  # only N x N and 8 x N
+
+
 # ---------------------------------------------------------------- scalar quantization
 
 @pytest.mark.parametrize("nbits", [8, 4, 2, 1])

@@ -36,6 +36,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "pq":
             del os.environ["DAB_PQ_GLOBAL_LUT"]
             assert np.array_equal(a[0], a2[0]) and np.array_equal(dd.view(np.uint32), dd2.view(np.uint32))
             print(dt.__name__, d, chunks, "pq ok", int(a[2].min()), int(b[2].min()), int(c[2].min()), lut.shape)
+    for nb in (8, 4, 1):                                                       # MinMax quantizer: compress + distances
+        v = rng.uniform(-1, 1, (200, 77)).astype(np.float32)
+        rows, loss = dab.minmax_compress(v, nb, 0.9)
+        dmm = dab.minmax_distances(dab.Metric.L2, nb, nb, 77, rows, rows[::-1].copy())
+        r8, _ = dab.minmax_compress(v, 8)
+        dmx = dab.minmax_distances(dab.Metric.Cosine, 8, nb, 77, r8, rows)
+        print("minmax", nb, rows.shape, bool(np.isfinite(dmm).all() and np.isfinite(dmx).all()))
     print("sanitize_check pq done")
     sys.exit(0)
 for dt, ddt, metric, d in ((np.float32, dab.DType.f32, dab.Metric.L2, 100), (np.float16, dab.DType.f16, dab.Metric.InnerProduct, 61),
