@@ -197,3 +197,27 @@ impl<T: Element> Drop for GpuIndex<T> {
         unsafe { sys::dab_destroy(self.raw) }
     }
 }
+
+/// `MinMaxQuantizer::new(Transform::Null(dim), grid_scale)` + `compress_into` for `vectors.len() / dim` vectors:
+/// rows in the canonical-front layout of `minmax::Data<NBITS>` (`DataRef::from_canonical_front(&row, dim)`), and the
+/// `L2Loss` of every vector.  `Err` when an input vector contains NaN (`InputContainsNaN`).
+pub fn minmax_compress(device: i32, grid_scale: f32, dim: usize, nbits: i32, vectors: &[f32]) -> Result<(Vec<u8>, Vec<f32>)> {
+    let n = vectors.len() / dim;
+    let row_bytes = unsafe { sys::dab_minmax_row_bytes(dim as u32, nbits) } as usize;
+    let mut rows = vec![0u8; n * row_bytes];
+    let mut loss = vec![0f32; n];
+    check(unsafe {
+        sys::dab_minmax_compress(device, grid_scale, dim as u32, nbits, vectors.as_ptr(), n as u64, rows.as_mut_ptr(), loss.as_mut_ptr())
+    })?;
+    Ok((rows, loss))
+}
+
+/// `MinMax{L2Squared, IP, Cosine, CosineNormalized}::evaluate(DataRef<N>, DataRef<M>)` for row pairs (N x N or 8 x N bits).
+pub fn minmax_distances(device: i32, metric: Metric, nbits_x: i32, nbits_y: i32, dim: usize, x_rows: &[u8], y_rows: &[u8]) -> Result<Vec<f32>> {
+    let n = x_rows.len() / unsafe { sys::dab_minmax_row_bytes(dim as u32, nbits_x) } as usize;
+    let mut out = vec![0f32; n];
+    check(unsafe {
+        sys::dab_minmax_distances(device, metric as i32, nbits_x, nbits_y, dim as u32, x_rows.as_ptr(), y_rows.as_ptr(), n as u64, out.as_mut_ptr())
+    })?;
+    Ok(out)
+}

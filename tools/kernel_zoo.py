@@ -13,7 +13,7 @@ import diskann_b200 as dab
 
 rng = np.random.default_rng(7)
 sizes = {}
-ONLY = set(sys.argv[1:])  # e.g. `kernel_zoo.py pq`: only that family (f32, pq, i8, f16); default: all
+ONLY = set(sys.argv[1:])  # e.g. `kernel_zoo.py pq`: only that family (f32, pq, minmax, i8, f16); default: all
 
 
 def want(family):
@@ -58,6 +58,16 @@ with dab.GpuIndex(dab.DType.f32, dab.Metric.L2, dim, n, 1, 83) as g:
 del base
 
 # ---- i8 1M x 128
+if want("minmax"):
+    vmm = rng.uniform(-1.0, 1.0, (1_000_000, dim)).astype(np.float32)
+    for nb in (8, 4):
+        rows_mm, _ = twice(lambda: dab.minmax_compress(vmm, nb))
+        sizes[f"minmax_compress_kernel {nb}-bit, 1M x 128 f32"] = {"pairs": 1_000_000, "bytes_per_pair": dim * 4 + int(rows_mm.shape[1])}
+        other = np.ascontiguousarray(rows_mm[::-1])
+        twice(lambda: dab.minmax_distances(dab.Metric.L2, nb, nb, dim, rows_mm, other))
+        sizes[f"minmax_distance_kernel {nb} x {nb} bits, 1M pairs"] = {"pairs": 1_000_000, "bytes_per_pair": 2 * int(rows_mm.shape[1]) + 4}
+    del vmm
+
 if want("i8"):
     base8 = rng.integers(-128, 128, (n + 1, dim)).astype(np.int8)
     q8 = rng.integers(-128, 128, (nq, dim)).astype(np.int8)
