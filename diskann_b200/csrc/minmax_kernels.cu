@@ -9,7 +9,7 @@
 //     the 32 finished rows leave through shared memory as one contiguous byte range.
 //   * MinMax{IP, L2Squared, Cosine, CosineNormalized} over two Data rows (vectors.rs:206-455): an exact integer inner
 //     product of the codes (bits/distances.rs; dp4a on masked fields, popc for one bit) and a five-term f32 epilogue
-//     in the reference's association.  One warp per pair, 4-byte loads of the dense codes.
+//     in the reference's association.  Eight lanes per pair, 4-byte loads of the dense codes.
 // Row layout = the reference's canonical-front Data<NBITS> (meta/vector.rs:377-392): MinMaxCompensation {dim u32, b, n, a,
 // norm_squared} (vectors.rs:43-52, 20 bytes) then ceil(dim * NBITS / 8) bytes of codes, value i at bit i * NBITS.
 // HBM-bound byte work: no tensor cores.
@@ -153,22 +153,25 @@ __device__ __forceinline__ uint32_t mm_code_at(const uint8_t* codes, uint32_t i,
     return ((uint32_t)__ldg(codes + (bit >> 3)) >> (bit & 7u)) & ((1u << nbits) - 1u);
 }
 
-// one warp per pair
+// eight lanes per pair, four pairs per warp pass (rows are 36 - 150 bytes at 128 dimensions: a whole warp per pair would
+// leave most lanes without a word to load)
 __global__ void __launch_bounds__(256) minmax_distance_kernel(const MinMaxDistanceParams p) {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, team = lane >> 3, tl = lane & 7;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const bool words = p.nbits_x == p.nbits_y && (p.row_bytes_x & 3u) == 0 && (p.row_bytes_y & 3u) == 0;
-    for (uint64_t i = warp; i < p.n; i += nwarps) {
-        const uint8_t* xr = p.x + i * p.row_bytes_x;
-        const uint8_t* yr = p.y + i * p.row_bytes_y;
+    for (uint64_t i0 = warp * 4; i0 < p.n; i0 += nwarps * 4) {
+        const uint64_t i = i0 + team;
+        const bool live = i < p.n;
+        const uint8_t* xr = p.x + (live ? i : i0) * p.row_bytes_x;
+        const uint8_t* yr = p.y + (live ? i : i0) * p.row_bytes_y;
         uint32_t ip = 0, unused = 0;
         if (words) {
             // same width on both sides: whole 32-bit words of the dense codes (padding bits are zero)
             const uint32_t* xw = reinterpret_cast<const uint32_t*>(xr + kMmMeta);
             const uint32_t* yw = reinterpret_cast<const uint32_t*>(yr + kMmMeta);
             const uint32_t nw = (p.row_bytes_x - kMmMeta) >> 2;
-            for (uint32_t w = lane; w < nw; w += 32) {
+            for (uint32_t w = tl; w < nw; w += 8) {
                 const uint32_t a = __ldg(xw + w), b = __ldg(yw + w);
                 switch (p.nbits_x) {
                     case 8: sq_word<8>(a, b, true, unused, ip); break;
@@ -178,10 +181,12 @@ __global__ void __launch_bounds__(256) minmax_distance_kernel(const MinMaxDistan
                 }
             }
         } else {
-            for (uint32_t e = lane; e < p.dim; e += 32) ip += mm_code_at(xr + kMmMeta, e, p.nbits_x) * mm_code_at(yr + kMmMeta, e, p.nbits_y);
+            for (uint32_t e = tl; e < p.dim; e += 8) ip += mm_code_at(xr + kMmMeta, e, p.nbits_x) * mm_code_at(yr + kMmMeta, e, p.nbits_y);
         }
-        ip = __reduce_add_sync(kFull, ip);
-        if (lane == 0) {
+        ip += __shfl_xor_sync(kFull, ip, 4);
+        ip += __shfl_xor_sync(kFull, ip, 2);
+        ip += __shfl_xor_sync(kFull, ip, 1);
+        if (tl == 0 && live) {
             const uint32_t* xm = reinterpret_cast<const uint32_t*>(xr);  // rows are at least 4-byte aligned only when
             const uint32_t* ym = reinterpret_cast<const uint32_t*>(yr);  // row_bytes % 4 == 0: read the meta bytewise otherwise
             float xb, xn, xa, xq, yb, yn, ya, yq;
@@ -317,7 +322,7 @@ int dab_minmax_distances(int device, int metric, int nbits_x, int nbits_y, uint3
         p.x = dx;
         p.y = dy;
         p.out = dout;
-        const int grid = (int)std::min<uint64_t>((n + 7) / 8, 148ull * 8);
+        const int grid = (int)std::min<uint64_t>((n + 31) / 32, 148ull * 8);  // 8 warps x 4 pairs per CTA pass
         minmax_distance_kernel<<<grid, 256>>>(p);
         DAB_LAUNCHED();
         e = cudaGetLastError();

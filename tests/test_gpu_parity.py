@@ -704,6 +704,34 @@ def test_pq_traversal_search_identical_to_oracle(dab, monkeypatch, dt, metric, d
                 assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), ("direct cosine + rerank", name, k, Ls, beam)
 
 
+def test_pq_traversal_wide_adjacency_rows(dab):
+    """Adjacency rows longer than the 96 words search_kernel_pqs copies one hop ahead (max_degree 110): the kernel reads them in
+    two passes and falls back to the L2 prefetch of the next row; every node of this random graph has 100 neighbours."""
+    rng = np.random.default_rng(7)
+    n, d, chunks, maxdeg = 3000, 32, 8, 110
+    base = clustered(rng, n + 1, d)
+    adj = np.zeros((n + 1, maxdeg + 1), np.uint32)
+    adj[:, 0] = 100
+    adj[:, 1:101] = rng.integers(0, n, (n + 1, 100))
+    piv = base[rng.choice(n, 256, replace=False)]
+    off = O.pq_offsets(d, chunks)
+    L = O.lib()
+    codes = np.zeros((n + 1, chunks), np.uint8)
+    for i in range(n + 1):
+        assert L.orc_pq_encode(O.ptr(piv), 256, d, O.ptr(off), chunks, O.ptr(base[i]), O.ptr(codes[i])) == 0
+    queries = clustered(rng, 100, d)
+    oidx = O.Index(base, adj, n, 1, O.L2, pq=(piv, off, codes))
+    with dab.GpuIndex(dab.DType.f32, dab.Metric.L2, d, n, 1, maxdeg) as g:
+        g.upload_vectors(base)
+        g.upload_graph(adj)
+        g.upload_pq(piv, off, codes)
+        for (k, Ls, beam) in [(10, 40, 1), (10, 300, 1), (5, 64, 2)]:
+            got = g.search_batch_pq(queries, k, Ls, beam, rerank=True)
+            want = oidx.search_batch_rerank(queries, k, Ls, beam=beam, threads=4)
+            for a, b, name in zip(got, want, ("ids", "dists", "counts", "cmps", "hops")):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, k, Ls, beam)
+
+
 def sq_quantizer(f32, metric):
     """A ScalarQuantizer in the shape of scalar/train.rs: shift below the per-dimension mean, one scale."""
     mean = f32.mean(0).astype(np.float32)
