@@ -62,3 +62,17 @@ def test_reference_arm_prints_one_json_line_without_a_gpu():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference"
+
+
+def test_traffic_json_is_keyed_by_workload(tmp_path, monkeypatch):
+    """roofline.traffic comes from the committed ncu capture of the workload's own search kernel."""
+    assert bench.ncu_traffic("c2_1Mx128_f32_l2") > 1e9 and bench.ncu_traffic("c4_10Mx128_i8_pq32") > 1e9
+    assert bench.ncu_traffic("c3_1Mx768_f16_ip") is None  # no capture committed under that key
+    t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    for entry in t.values():
+        assert os.path.exists(os.path.join(ROOT, entry["source"].split(", ")[1])), entry["source"]
+    # round-1 layout (one entry, no key) still reads as the C2 kernel
+    (tmp_path / "profiles").mkdir()
+    (tmp_path / "profiles" / "traffic.json").write_text(json.dumps({"search_kernel_dram_bytes_per_launch": 7.0}))
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.ncu_traffic("c2_1Mx128_f32_l2") == 7.0 and bench.ncu_traffic("c4_10Mx128_i8_pq32") is None
