@@ -16,6 +16,8 @@
 //                                  (diskann-benchmark-core/src/search/graph/knn.rs:208-238) for a
 //                                  whole query batch (the 3' boundary of SURVEY.md §8b)
 //   SearchStats                    diskann/src/graph/index.rs:90 (cmps, hops, result_count)
+//   MinMaxQuantizer                diskann-quantization/src/minmax/quantizer.rs:69-228 (Transform::Null) + the
+//                                  MinMax distance functors over compressed rows (vectors.rs:231-455)
 //
 // Errors: every non-zero status becomes ANNError (the inmem layer returns Err on length / type
 // mismatch, layers/full.rs:203-213, 306-314; it never panics across the boundary).
@@ -220,6 +222,35 @@ class GpuKNN {
     Provider<T>& p_;
     uint32_t l_, beam_;
     Pending pending_[DAB_MAX_SLOTS];
+};
+
+// MinMaxQuantizer (diskann-quantization/src/minmax/quantizer.rs:69-110, Transform::Null) and the MinMax distance
+// functors over compressed rows (vectors.rs:231-455).  Rows are the reference's canonical-front Data<NBITS> bytes.
+class MinMaxQuantizer {
+   public:
+    MinMaxQuantizer(uint32_t dim, float grid_scale, int device = 0) : dim_(dim), grid_scale_(grid_scale), device_(device) {}
+    uint32_t dim() const { return dim_; }
+    uint32_t output_dim() const { return dim_; }
+    // Data::<NBITS>::canonical_bytes(dim)
+    size_t canonical_bytes(int nbits) const { return dab_minmax_row_bytes(dim_, nbits); }
+    // CompressInto<&[f32], DataMutRef<NBITS>> for n vectors; throws ANNError on NaN input (InputContainsNaN)
+    std::vector<uint8_t> compress(const float* vectors, uint64_t n, int nbits, std::vector<float>* loss = nullptr) const {
+        std::vector<uint8_t> rows(n * canonical_bytes(nbits));
+        if (loss) loss->resize(n);
+        check(dab_minmax_compress(device_, grid_scale_, dim_, nbits, vectors, n, rows.data(), loss ? loss->data() : nullptr));
+        return rows;
+    }
+    // MinMax{L2Squared, IP, Cosine, CosineNormalized}::evaluate(DataRef<N>, DataRef<M>) row by row (N x N, 8 x N)
+    std::vector<float> distances(Metric metric, int nbits_x, int nbits_y, const uint8_t* x_rows, const uint8_t* y_rows, uint64_t n) const {
+        std::vector<float> out(n);
+        check(dab_minmax_distances(device_, static_cast<int>(metric), nbits_x, nbits_y, dim_, x_rows, y_rows, n, out.data()));
+        return out;
+    }
+
+   private:
+    uint32_t dim_;
+    float grid_scale_;
+    int device_;
 };
 
 }  // namespace diskann_b200
