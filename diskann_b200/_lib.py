@@ -60,6 +60,7 @@ SYMBOLS = {
     "dab_minmax_row_bytes": (_u32, [_u32, _i]),
     "dab_minmax_compress": (_i, [_i, _f, _u32, _i, _vp, _u64, _vp, _vp]),
     "dab_minmax_distances": (_i, [_i, _i, _i, _i, _u32, _vp, _vp, _u64, _vp]),
+    "dab_minmax_query_distances": (_i, [_i, _i, _i, _u32, _vp, _u32, _vp, _u64, _vp]),
     "dab_robust_prune": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _f, _vp, _vp]),
     "dab_build": (_i, [_vp, _u32, _u32, _f, _u32]),
     "dab_flat_knn": (_i, [_vp, _vp, _u32, _u32, _vp, _vp]),

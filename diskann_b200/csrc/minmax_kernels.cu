@@ -219,6 +219,159 @@ __global__ void __launch_bounds__(256) minmax_distance_kernel(const MinMaxDistan
     }
 }
 
+// ---------------------------------------------------------------- full-precision query x compressed rows
+// MinMax{IP, L2Squared, Cosine, CosineNormalized}::evaluate(FullQueryRef, DataRef<NBITS>) (vectors.rs:272-305, 347-392,
+// 417-476): raw = InnerProduct(&[f32], BitSlice<NBITS>) — the x86-64-v3 kernels of bits/distances.rs for 1 / 2 / 4 bits
+// (:2295-2436, :2438-2595, :2603-2665: eight f32 lanes, FMA, one or two accumulators, zero-filled remainder loads,
+// sum_tree), the scalar mul-then-add loop for 8 bits (:2668-2725) — then ip = raw * a + sum(q) * b and the metric's
+// epilogue.  A team of eight GPU lanes is the eight SIMD lanes of the reference (every lane runs its own FMA chain, the
+// tree is xor 4, 2, 1), four (query, row) pairs per warp; for 8 bits one lane per pair runs the sequential chain.
+struct MinMaxQueryParams {
+    int metric, nbits;
+    uint32_t dim;
+    const float* queries;  // [nq][dim]
+    uint32_t nq;
+    const uint8_t* rows;   // [n][row_bytes]
+    uint32_t row_bytes;
+    uint64_t n;
+    float* meta;           // [nq][2]: sum, norm_squared (FullQueryMeta)
+    float* out;            // [nq][n]
+    unsigned long long* first_nan;
+};
+
+// CompressInto<&[f32], FullQueryMut> (quantizer.rs:393-417): sequential sums; NaN input is an error
+__global__ void __launch_bounds__(128) minmax_query_meta_kernel(const MinMaxQueryParams p) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= p.nq) return;
+    const float* v = p.queries + (size_t)q * p.dim;
+    float ns = -0.0f, s = -0.0f;  // <f32 as Sum>::sum folds from -0.0
+    bool nan = false;
+    for (uint32_t i = 0; i < p.dim; ++i) {
+        const float e = v[i];
+        nan |= e != e;
+        ns = __fadd_rn(ns, __fmul_rn(e, e));
+        s = __fadd_rn(s, e);
+    }
+    p.meta[2 * q] = s;
+    p.meta[2 * q + 1] = ns;
+    if (nan) atomicMin(p.first_nan, (unsigned long long)q);
+}
+
+__device__ __forceinline__ uint32_t mm_load_bytes(const uint8_t* ptr, uint32_t nbytes) {
+    uint32_t v = 0;
+    for (uint32_t i = 0; i < nbytes; ++i) v |= (uint32_t)__ldg(ptr + i) << (8 * i);
+    return v;
+}
+
+template <int NBITS>
+__global__ void __launch_bounds__(256) minmax_query_distance_kernel(const MinMaxQueryParams p) {
+    extern __shared__ float mq[];  // the query
+    const uint32_t q = blockIdx.y;
+    for (uint32_t e = threadIdx.x; e < p.dim; e += blockDim.x) mq[e] = __ldg(p.queries + (size_t)q * p.dim + e);
+    __syncthreads();
+    const float q_sum = p.meta[2 * q], q_ns = p.meta[2 * q + 1];
+    const uint32_t len = p.dim;
+    const int lane = threadIdx.x & 31;
+    constexpr int LPP = NBITS == 8 ? 1 : 8;  // lanes per pair
+    const int l = lane % LPP;
+    const uint64_t pair0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPP;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x / LPP;
+    const uint64_t rounds = (p.n + stride - 1) / stride;  // every lane makes the same number of passes (team shuffles)
+    for (uint64_t it = 0; it < rounds; ++it) {
+        const uint64_t r = pair0 + it * stride;
+        const bool live = r < p.n;
+        const uint8_t* row = p.rows + (live ? r : 0) * p.row_bytes;
+        const uint8_t* codes = row + kMmMeta;
+        float raw;
+        if (NBITS == 8) {
+            float s = 0.0f;
+            for (uint32_t i = 0; i < len; ++i) s = __fadd_rn(s, __fmul_rn(mq[i], (float)__ldg(codes + i)));
+            raw = s;
+        } else {
+            float s = 0.0f;
+            const uint32_t tail = (len & 7u) == 0 ? 8u : (len & 7u);
+            if (NBITS == 4) {
+                const uint32_t blocks = len / 8;
+                for (uint32_t b = 0; b < blocks; ++b) {
+                    const uint32_t w = mm_load_bytes(codes + 4 * b, 4);
+                    s = __fmaf_rn(mq[8 * b + l], (float)((w >> (4 * l)) & 15u), s);
+                }
+                const uint32_t rem = len & 7u;
+                if (rem) {
+                    const uint32_t w = mm_load_bytes(codes + 4 * blocks, (rem + 1) / 2);
+                    s = __fmaf_rn((uint32_t)l < rem ? mq[8 * blocks + l] : 0.0f, (float)((w >> (4 * l)) & 15u), s);
+                }
+            } else if (NBITS == 2) {
+                const uint32_t blocks = len / 16;
+                if (blocks) {
+                    float s0 = 0.0f, s1 = 0.0f;
+                    for (uint32_t b = 0; b < blocks; ++b) {
+                        const uint32_t w = mm_load_bytes(codes + 4 * b, 4);
+                        s0 = __fmaf_rn(mq[16 * b + l], (float)((w >> (2 * l)) & 3u), s0);
+                        s1 = __fmaf_rn(mq[16 * b + 8 + l], (float)((w >> (16 + 2 * l)) & 3u), s1);
+                    }
+                    s = __fadd_rn(s0, s1);
+                }
+                const uint32_t rem = len & 15u;
+                if (rem) {
+                    const uint32_t w = mm_load_bytes(codes + 4 * blocks, (rem + 3) / 4);
+                    const float* px = mq + 16 * blocks;
+                    if (rem <= 8) {
+                        s = __fmaf_rn((uint32_t)l < tail ? px[l] : 0.0f, (float)((w >> (2 * l)) & 3u), s);
+                    } else {
+                        s = __fmaf_rn(px[l], (float)((w >> (2 * l)) & 3u), s);
+                        s = __fmaf_rn((uint32_t)l < tail ? px[8 + l] : 0.0f, (float)((w >> (16 + 2 * l)) & 3u), s);
+                    }
+                }
+            } else {
+                const uint32_t blocks = len / 32;
+                if (blocks) {
+                    float s0 = 0.0f, s1 = 0.0f;
+                    for (uint32_t b = 0; b < blocks; ++b) {
+                        const uint32_t w = mm_load_bytes(codes + 4 * b, 4);
+                        s0 = __fmaf_rn(mq[32 * b + l], (float)((w >> l) & 1u), s0);
+                        s1 = __fmaf_rn(mq[32 * b + 8 + l], (float)((w >> (8 + l)) & 1u), s1);
+                        s0 = __fmaf_rn(mq[32 * b + 16 + l], (float)((w >> (16 + l)) & 1u), s0);
+                        s1 = __fmaf_rn(mq[32 * b + 24 + l], (float)((w >> (24 + l)) & 1u), s1);
+                    }
+                    s = __fadd_rn(s0, s1);
+                }
+                const uint32_t rem = len & 31u;
+                if (rem) {
+                    const uint32_t groups = (rem + 7) / 8;
+                    const uint32_t w = mm_load_bytes(codes + 4 * blocks, groups);
+                    const float* px = mq + 32 * blocks;
+                    for (uint32_t j = 0; j < groups; ++j) {
+                        const bool in = j + 1 < groups || (uint32_t)l < tail;
+                        s = __fmaf_rn(in ? px[8 * j + l] : 0.0f, (float)((w >> (8 * j + l)) & 1u), s);
+                    }
+                }
+            }
+            // sum_tree (diskann-wide/src/traits.rs:583-595) over the team's eight lanes
+            s = __fadd_rn(s, __shfl_xor_sync(kFull, s, 4));
+            s = __fadd_rn(s, __shfl_xor_sync(kFull, s, 2));
+            s = __fadd_rn(s, __shfl_xor_sync(kFull, s, 1));
+            raw = s;
+        }
+        if (live && l == 0) {
+            auto rd = [](const uint8_t* b) { return (uint32_t)__ldg(b) | ((uint32_t)__ldg(b + 1) << 8) | ((uint32_t)__ldg(b + 2) << 16) | ((uint32_t)__ldg(b + 3) << 24); };
+            const uint32_t d = rd(row);
+            const float yb = __uint_as_float(rd(row + 4)), ya = __uint_as_float(rd(row + 12)), yq = __uint_as_float(rd(row + 16));
+            float res;
+            if (d != p.dim) {
+                res = __int_as_float(0x7FC00000);  // UnequalLengths
+            } else {
+                const float ip = __fadd_rn(__fmul_rn(raw, ya), __fmul_rn(q_sum, yb));
+                if (p.metric == DAB_INNER_PRODUCT) res = -ip;
+                else if (p.metric == DAB_L2) res = __fsub_rn(__fadd_rn(q_ns, yq), __fmul_rn(2.0f, ip));
+                else if (p.metric == DAB_COSINE) res = __fsub_rn(1.0f, __fdiv_rn(ip, __fmul_rn(__fsqrt_rn(q_ns), __fsqrt_rn(yq))));
+                else res = __fsub_rn(1.0f, ip);
+            }
+            p.out[(size_t)q * p.n + r] = res;
+        }
+    }
+}
+
 }  // namespace dab
 
 using namespace dab;
@@ -333,6 +486,70 @@ int dab_minmax_distances(int device, int metric, int nbits_x, int nbits_y, uint3
     cudaFree(dx);
     cudaFree(dy);
     cudaFree(dout);
+    return rc;
+}
+
+int dab_minmax_query_distances(int device, int metric, int nbits, uint32_t dim, const float* queries, uint32_t nq, const uint8_t* rows,
+                               uint64_t n, float* out) {
+    if (!mm_bits_ok(nbits)) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_minmax_query_distances: nbits must be 1, 2, 4 or 8");
+    if (metric < DAB_COSINE || metric > DAB_COSINE_NORMALIZED) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_minmax_query_distances: unknown metric %d", metric);
+    if (nq == 0 || n == 0) return DAB_OK;
+    if (!queries || !rows || !out || dim == 0) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_minmax_query_distances: NULL argument");
+    if ((size_t)dim * 4 > 48 * 1024) return fail(DAB_ERR_INVALID_ARGUMENT, "dab_minmax_query_distances: dim %u too large", dim);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(DAB_ERR_NO_DEVICE, "dab_minmax_query_distances: no CUDA device visible");
+    DAB_CUDA(cudaSetDevice(device));
+    MinMaxQueryParams p;
+    memset(&p, 0, sizeof(p));
+    p.metric = metric;
+    p.nbits = nbits;
+    p.dim = dim;
+    p.nq = nq;
+    p.row_bytes = dab_minmax_row_bytes(dim, nbits);
+    p.n = n;
+    float *dq = nullptr, *dmeta = nullptr, *dout = nullptr;
+    uint8_t* drows = nullptr;
+    unsigned long long* d_nan = nullptr;
+    cudaError_t e = cudaMalloc(&dq, (size_t)nq * dim * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&drows, n * p.row_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&dmeta, (size_t)nq * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&dout, (size_t)nq * n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_nan, 8);
+    if (e == cudaSuccess) e = cudaMemcpy(dq, queries, (size_t)nq * dim * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(drows, rows, n * p.row_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_nan, 0xFF, 8);
+    unsigned long long first_nan = ~0ull;
+    if (e == cudaSuccess) {
+        p.queries = dq;
+        p.rows = drows;
+        p.meta = dmeta;
+        p.out = dout;
+        p.first_nan = d_nan;
+        minmax_query_meta_kernel<<<(nq + 127) / 128, 128>>>(p);
+        DAB_LAUNCHED();
+        const uint32_t lpp = nbits == 8 ? 1 : 8;
+        const uint64_t pairs_per_cta = 256 / lpp;
+        const dim3 grid((unsigned)std::min<uint64_t>((n + pairs_per_cta - 1) / pairs_per_cta, 148ull * 8), nq);
+        const size_t smem = (size_t)dim * 4;
+        switch (nbits) {
+            case 8: minmax_query_distance_kernel<8><<<grid, 256, smem>>>(p); break;
+            case 4: minmax_query_distance_kernel<4><<<grid, 256, smem>>>(p); break;
+            case 2: minmax_query_distance_kernel<2><<<grid, 256, smem>>>(p); break;
+            default: minmax_query_distance_kernel<1><<<grid, 256, smem>>>(p); break;
+        }
+        DAB_LAUNCHED();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(&first_nan, d_nan, 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && first_nan == ~0ull) e = cudaMemcpy(out, dout, (size_t)nq * n * 4, cudaMemcpyDeviceToHost);
+    int rc = DAB_OK;
+    if (e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? DAB_ERR_OUT_OF_MEMORY : DAB_ERR_CUDA, "dab_minmax_query_distances: %s", cudaGetErrorString(e));
+    else if (first_nan != ~0ull) rc = fail(DAB_ERR_INVALID_ARGUMENT, "dab_minmax_query_distances: query %llu contains NaN (InputContainsNaN)", first_nan);
+    cudaFree(dq);
+    cudaFree(drows);
+    cudaFree(dmeta);
+    cudaFree(dout);
+    cudaFree(d_nan);
     return rc;
 }
 

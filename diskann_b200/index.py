@@ -103,6 +103,17 @@ def minmax_distances(metric, nbits_x, nbits_y, dim, x_rows, y_rows, device=0):
     return out
 
 
+def minmax_query_distances(metric, nbits, queries, rows, device=0):
+    """Full-precision queries [nq, dim] f32 against MinMax-compressed rows [n, row_bytes]: out [nq, n]
+    (MinMax{L2Squared, IP, Cosine, CosineNormalized}::evaluate(FullQueryRef, DataRef<NBITS>))."""
+    queries = np.ascontiguousarray(queries, np.float32)
+    rows = np.ascontiguousarray(rows, np.uint8)
+    nq, dim = queries.shape
+    out = np.empty((nq, rows.shape[0]), np.float32)
+    check(_lib.lib().dab_minmax_query_distances(device, int(metric), nbits, dim, _ptr(queries), nq, _ptr(rows), rows.shape[0], _ptr(out)))
+    return out
+
+
 class GpuIndex:
     """Device-resident snapshot of an in-memory index: vectors + adjacency (+ PQ)."""
 

@@ -310,6 +310,15 @@ int dab_minmax_compress(int device, float grid_scale, uint32_t dim, int nbits, c
 int dab_minmax_distances(int device, int metric, int nbits_x, int nbits_y, uint32_t dim, const uint8_t* x_rows,
                          const uint8_t* y_rows, uint64_t n, float* out);
 
+/* The query side of the minmax-exhaustive-search benchmark (diskann-benchmark/src/exhaustive/minmax.rs): queries stay
+ * full precision — CompressInto<&[f32], FullQueryMut> (quantizer.rs:369-417: FullQueryMeta {sum, norm_squared}) — and
+ * PureDistanceFunction<FullQueryRef, DataRef<NBITS>, distances::Result<f32>> for the four MinMax distances
+ * (vectors.rs:272-305, 347-392, 417-476) is evaluated for every (query, row) pair: out [nq][n].  The f32 x N-bit inner
+ * product follows the reference's x86-64-v3 kernels lane for lane (bits/distances.rs:2295-2725).  A query containing NaN
+ * fails the call (InputContainsNaN). */
+int dab_minmax_query_distances(int device, int metric, int nbits, uint32_t dim, const float* queries, uint32_t nq,
+                               const uint8_t* rows, uint64_t n, float* out);
+
 /* ------------------------------------------------------------------ build-side reuse */
 
 /* PruneAccessor::fill + robust_prune (diskann/src/graph/index.rs:2349-2380, 2565-2650;

@@ -156,3 +156,122 @@ void orc_minmax_decompress(const uint8_t* row, int nbits, float* out) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- full-precision query x compressed vector
+// InnerProduct::evaluate(&[f32], BitSlice<NBITS>) (bits/distances.rs): the x86-64-v3 kernels for 1 / 2 / 4 bits
+// (:2295-2436, :2438-2595, :2603-2665: eight f32 lanes, FMA, one or two accumulators, zero-filled remainder loads,
+// sum_tree) and the scalar loop the 8-bit instantiation retargets to (:2668-2725).  Each SIMD lane is emulated as
+// its own sequential chain.
+namespace {
+
+inline float tree8(const float (&s)[8]) {  // diskann-wide/src/traits.rs:583-595
+    return ((s[0] + s[4]) + (s[2] + s[6])) + ((s[1] + s[5]) + (s[3] + s[7]));
+}
+
+// the little-endian value of the first `nbytes` (<= 4) bytes at p (load_one .. load_four, distances.rs:180-234)
+inline uint32_t load_bytes(const uint8_t* p, size_t nbytes) {
+    uint32_t v = 0;
+    for (size_t i = 0; i < nbytes; ++i) v |= (uint32_t)p[i] << (8 * i);
+    return v;
+}
+
+float full_ip(const float* x, const uint8_t* codes, size_t len, int nbits) {
+    if (nbits == 8) {
+        float s = 0.0f;
+        for (size_t i = 0; i < len; ++i) s += x[i] * (float)codes[i];
+        return s;
+    }
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const size_t tail = len % 8 == 0 ? 8 : len % 8;
+    if (nbits == 4) {
+        const size_t blocks = len / 8;
+        for (size_t b = 0; b < blocks; ++b) {
+            const uint32_t w = load_bytes(codes + 4 * b, 4);
+            for (int l = 0; l < 8; ++l) s[l] = std::fmaf(x[8 * b + l], (float)((w >> (4 * l)) & 15u), s[l]);
+        }
+        const size_t rem = len % 8;
+        if (rem) {
+            const uint32_t w = load_bytes(codes + 4 * blocks, (rem + 1) / 2);
+            for (int l = 0; l < 8; ++l) s[l] = std::fmaf((size_t)l < rem ? x[8 * blocks + l] : 0.0f, (float)((w >> (4 * l)) & 15u), s[l]);
+        }
+        return tree8(s);
+    }
+    if (nbits == 2) {
+        const size_t blocks = len / 16;
+        if (blocks) {
+            float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (size_t b = 0; b < blocks; ++b) {
+                const uint32_t w = load_bytes(codes + 4 * b, 4);
+                for (int l = 0; l < 8; ++l) {
+                    s0[l] = std::fmaf(x[16 * b + l], (float)((w >> (2 * l)) & 3u), s0[l]);
+                    s1[l] = std::fmaf(x[16 * b + 8 + l], (float)((w >> (16 + 2 * l)) & 3u), s1[l]);
+                }
+            }
+            for (int l = 0; l < 8; ++l) s[l] = s0[l] + s1[l];
+        }
+        const size_t rem = len % 16;
+        if (rem) {
+            const uint32_t w = load_bytes(codes + 4 * blocks, (rem + 3) / 4);
+            const float* px = x + 16 * blocks;
+            if (rem <= 8) {
+                for (int l = 0; l < 8; ++l) s[l] = std::fmaf((size_t)l < tail ? px[l] : 0.0f, (float)((w >> (2 * l)) & 3u), s[l]);
+            } else {
+                for (int l = 0; l < 8; ++l) s[l] = std::fmaf(px[l], (float)((w >> (2 * l)) & 3u), s[l]);
+                for (int l = 0; l < 8; ++l) s[l] = std::fmaf((size_t)l < tail ? px[8 + l] : 0.0f, (float)((w >> (16 + 2 * l)) & 3u), s[l]);
+            }
+        }
+        return tree8(s);
+    }
+    // one bit
+    const size_t blocks = len / 32;
+    if (blocks) {
+        float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (size_t b = 0; b < blocks; ++b) {
+            const uint32_t w = load_bytes(codes + 4 * b, 4);
+            for (int l = 0; l < 8; ++l) {
+                s0[l] = std::fmaf(x[32 * b + l], (float)((w >> l) & 1u), s0[l]);
+                s1[l] = std::fmaf(x[32 * b + 8 + l], (float)((w >> (8 + l)) & 1u), s1[l]);
+                s0[l] = std::fmaf(x[32 * b + 16 + l], (float)((w >> (16 + l)) & 1u), s0[l]);
+                s1[l] = std::fmaf(x[32 * b + 24 + l], (float)((w >> (24 + l)) & 1u), s1[l]);
+            }
+        }
+        for (int l = 0; l < 8; ++l) s[l] = s0[l] + s1[l];
+    }
+    const size_t rem = len % 32;
+    if (rem) {
+        const size_t groups = (rem + 7) / 8;
+        const uint32_t w = load_bytes(codes + 4 * blocks, groups);
+        const float* px = x + 32 * blocks;
+        for (size_t j = 0; j < groups; ++j)
+            for (int l = 0; l < 8; ++l) {
+                const bool in = j + 1 < groups || (size_t)l < tail;
+                s[l] = std::fmaf(in ? px[8 * j + l] : 0.0f, (float)((w >> (8 * j + l)) & 1u), s[l]);
+            }
+    }
+    return tree8(s);
+}
+
+}  // namespace
+
+extern "C" {
+
+// MinMax{IP, L2Squared, Cosine, CosineNormalized}::evaluate(FullQueryRef, DataRef<NBITS>) (vectors.rs:272-305, 347-392,
+// 417-436, 457-476), similarity-score convention.  q_sum / q_norm_squared = FullQueryMeta of the query.
+float orc_minmax_query_distance(int metric, int nbits, const float* query, float q_sum, float q_norm_squared, const uint8_t* row) {
+    uint32_t d;
+    float yb, ya, ynorm;
+    memcpy(&d, row, 4);
+    memcpy(&yb, row + 4, 4);
+    memcpy(&ya, row + 12, 4);
+    memcpy(&ynorm, row + 16, 4);
+    const float raw = full_ip(query, row + 20, d, nbits);
+    const float ip = raw * ya + q_sum * yb;
+    switch (metric) {
+        case ORC_INNER_PRODUCT: return -ip;
+        case ORC_L2: return q_norm_squared + ynorm - 2.0f * ip;
+        case ORC_COSINE: return 1.0f - ip / (std::sqrt(q_norm_squared) * std::sqrt(ynorm));
+        default: return 1.0f - ip;
+    }
+}
+
+}  // extern "C"

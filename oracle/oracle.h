@@ -234,6 +234,9 @@ int orc_minmax_compress(float grid_scale, size_t dim, int nbits, const float* v,
 int orc_minmax_full_query_meta(const float* v, size_t dim, float* sum_out, float* norm_squared_out);
 float orc_minmax_distance(int metric, int nbits_x, int nbits_y, const uint8_t* x_row, const uint8_t* y_row);
 void orc_minmax_decompress(const uint8_t* row, int nbits, float* out);
+/* FullQueryRef x DataRef<NBITS>: the f32 x N-bit inner product of bits/distances.rs:2295-2725 (x86-64-v3 lane order for
+ * 1 / 2 / 4 bits, the scalar loop for 8) + the epilogue of vectors.rs:272-476 */
+float orc_minmax_query_distance(int metric, int nbits, const float* query, float q_sum, float q_norm_squared, const uint8_t* row);
 
 #ifdef __cplusplus
 }

@@ -92,6 +92,8 @@ def lib():
     L.orc_minmax_full_query_meta.argtypes = [vp, sz, vp, vp]
     L.orc_minmax_distance.restype = f
     L.orc_minmax_distance.argtypes = [i, i, i, vp, vp]
+    L.orc_minmax_query_distance.restype = f
+    L.orc_minmax_query_distance.argtypes = [i, i, vp, f, f, vp]
     L.orc_minmax_decompress.restype = None
     L.orc_minmax_decompress.argtypes = [vp, i, vp]
     L.orc_search.restype = u32
@@ -331,4 +333,17 @@ def minmax_decompress(rows, nbits, dim):
     out = np.zeros((rows.shape[0], dim), np.float32)
     for r in range(rows.shape[0]):
         L.orc_minmax_decompress(ptr(rows[r]), nbits, ptr(out[r]))
+    return out
+
+
+def minmax_query_distances(metric, nbits, queries, rows):
+    """FullQuery x Data distances, all pairs: out[q, r] (the FullQueryMeta of every query is computed first)."""
+    L = lib()
+    queries = np.ascontiguousarray(queries, np.float32)
+    out = np.zeros((queries.shape[0], rows.shape[0]), np.float32)
+    for qi in range(queries.shape[0]):
+        s, ns = np.zeros(1, np.float32), np.zeros(1, np.float32)
+        assert L.orc_minmax_full_query_meta(ptr(queries[qi]), queries.shape[1], ptr(s), ptr(ns)) == 0
+        for r in range(rows.shape[0]):
+            out[qi, r] = L.orc_minmax_query_distance(metric, nbits, ptr(queries[qi]), float(s[0]), float(ns[0]), ptr(rows[r]))
     return out

@@ -451,6 +451,28 @@ def test_minmax_compress_and_distances_bit_exact(dab, nbits):
         dab.minmax_distances(O.L2, 4, 8, 100, np.zeros((1, 70), np.uint8), np.zeros((1, 120), np.uint8))  # only N x N and 8 x N
 
 
+@pytest.mark.parametrize("nbits", [8, 4, 2, 1])
+def test_minmax_full_query_distances_bit_exact(dab, nbits):
+    """dab_minmax_query_distances == the oracle's restatement of MinMax*::evaluate(FullQueryRef, DataRef<NBITS>): the f32 x N-bit
+    inner product in the reference's x86-64-v3 lane order (every remainder length: dims 1..100 and wide rows), the
+    FullQueryMeta sums and the four epilogues, bit for bit."""
+    rng = np.random.default_rng(60 + nbits)
+    for dim in list(range(1, 101)) + [128, 250, 257, 768]:
+        n, nq = (300, 5) if dim > 100 else (37, 3)
+        v = rng.uniform(-1.0, 1.0, (n, dim)).astype(np.float32)
+        q = rng.uniform(-1.0, 1.0, (nq, dim)).astype(np.float32)
+        rows, _, _ = O.minmax_compress(v, nbits, 1.0)
+        for metric in METRICS:
+            got = dab.minmax_query_distances(metric, nbits, q, rows)
+            want = O.minmax_query_distances(metric, nbits, q, rows)
+            assert same_bits(got, want), (dim, nbits, metric)
+    bad = rng.uniform(-1.0, 1.0, (4, 64)).astype(np.float32)
+    bad[2, 5] = np.nan
+    rows, _, _ = O.minmax_compress(rng.uniform(-1.0, 1.0, (10, 64)).astype(np.float32), nbits, 1.0)
+    with pytest.raises(dab.DabError, match="query 2"):
+        dab.minmax_query_distances(O.L2, nbits, bad, rows)
+
+
 # ---------------------------------------------------------------- scalar quantization
 
 @pytest.mark.parametrize("nbits", [8, 4, 2, 1])

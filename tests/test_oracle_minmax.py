@@ -124,3 +124,31 @@ def test_one_bit_range_uses_the_side_means():
     _, b, n, a, _ = meta_of(rows[0])
     assert abs(b - 0.4) < 1e-6 and abs(a - 9.6) < 1e-5
     assert codes_of(rows[0], 1, 6).tolist() == [0, 0, 0, 0, 0, 1] and abs(n - a * 1.0) < 1e-6
+
+
+@pytest.mark.parametrize("nbits", NBITS)
+def test_full_query_distances(nbits):
+    """FullQuery x Data (vectors.rs:596-650 of the reference's test): the query stays f32; against the f32 arithmetic on the
+    reconstructed data vector with the reference's tolerances, and against a float64 evaluation of the same formula (the
+    lane order of the f32 x N-bit inner product must only change rounding) for every length 1..150."""
+    rng = np.random.default_rng(200 + nbits)
+    L = O.lib()
+    for dim in list(range(1, 151)) + [256, 384, 1000]:
+        v = rng.uniform(-1.0, 1.0, (2, dim)).astype(np.float32)
+        rows, _, _ = O.minmax_compress(v[1:], nbits, 1.0)
+        q = v[0]
+        y = O.minmax_decompress(rows, nbits, dim)[0]
+        got = O.minmax_query_distances(O.INNER_PRODUCT, nbits, q[None], rows)[0, 0]
+        codes = codes_of(rows[0], nbits, dim).astype(np.float64)
+        _, b, _, a, ns = meta_of(rows[0])
+        exact_ip = float((q.astype(np.float64) * codes).sum()) * a + float(q.astype(np.float64).sum()) * b
+        assert abs(-got - exact_ip) <= 1e-5 * max(1.0, float(np.abs(q).sum()) * max(abs(a) * ((1 << nbits) - 1), abs(b))), (dim, nbits)
+        ip = float((q * y).sum(dtype=np.float32))
+        l2 = float(((q - y) ** 2).sum(dtype=np.float32))
+        d = {m: float(O.minmax_query_distances(m, nbits, q[None], rows)[0, 0]) for m in (O.L2, O.COSINE, O.COSINE_NORMALIZED)}
+        assert abs(d[O.L2] - l2) <= 1e-3 * max(l2, 1e-3) + 1e-4
+        nq, ny = float((q * q).sum(dtype=np.float32)), float((y * y).sum(dtype=np.float32))
+        if nq > 0 and ny > 0:
+            cos = 1.0 - ip / (np.sqrt(nq) * np.sqrt(ny))
+            assert abs(d[O.COSINE] - cos) < 1e-4
+        assert abs(d[O.COSINE_NORMALIZED] - (1.0 - ip)) < 1e-4 * max(1.0, abs(1.0 - ip))
