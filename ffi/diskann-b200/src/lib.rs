@@ -221,3 +221,15 @@ pub fn minmax_distances(device: i32, metric: Metric, nbits_x: i32, nbits_y: i32,
     })?;
     Ok(out)
 }
+
+/// Full-precision queries (`FullQuery`) against compressed rows: `MinMax*::evaluate(FullQueryRef, DataRef<NBITS>)` for
+/// every (query, row) pair, row-major `[nq][n]`.
+pub fn minmax_query_distances(device: i32, metric: Metric, nbits: i32, dim: usize, queries: &[f32], rows: &[u8]) -> Result<Vec<f32>> {
+    let nq = queries.len() / dim;
+    let n = rows.len() / unsafe { sys::dab_minmax_row_bytes(dim as u32, nbits) } as usize;
+    let mut out = vec![0f32; nq * n];
+    check(unsafe {
+        sys::dab_minmax_query_distances(device, metric as i32, nbits, dim as u32, queries.as_ptr(), nq as u32, rows.as_ptr(), n as u64, out.as_mut_ptr())
+    })?;
+    Ok(out)
+}

@@ -247,6 +247,13 @@ class MinMaxQuantizer {
         return out;
     }
 
+    // CompressInto<&[f32], FullQueryMut> + MinMax*::evaluate(FullQueryRef, DataRef<NBITS>) for every (query, row): [nq][n]
+    std::vector<float> query_distances(Metric metric, int nbits, const float* queries, uint32_t nq, const uint8_t* rows, uint64_t n) const {
+        std::vector<float> out(static_cast<size_t>(nq) * n);
+        check(dab_minmax_query_distances(device_, static_cast<int>(metric), nbits, dim_, queries, nq, rows, n, out.data()));
+        return out;
+    }
+
    private:
     uint32_t dim_;
     float grid_scale_;

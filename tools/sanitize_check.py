@@ -42,7 +42,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "pq":
         dmm = dab.minmax_distances(dab.Metric.L2, nb, nb, 77, rows, rows[::-1].copy())
         r8, _ = dab.minmax_compress(v, 8)
         dmx = dab.minmax_distances(dab.Metric.Cosine, 8, nb, 77, r8, rows)
-        print("minmax", nb, rows.shape, bool(np.isfinite(dmm).all() and np.isfinite(dmx).all()))
+        dq = dab.minmax_query_distances(dab.Metric.L2, nb, v[:9], rows)           # full-precision queries x compressed rows
+        print("minmax", nb, rows.shape, bool(np.isfinite(dmm).all() and np.isfinite(dmx).all() and np.isfinite(dq).all()))
     print("sanitize_check pq done")
     sys.exit(0)
 for dt, ddt, metric, d in ((np.float32, dab.DType.f32, dab.Metric.L2, 100), (np.float16, dab.DType.f16, dab.Metric.InnerProduct, 61),
