@@ -690,6 +690,20 @@ uint32_t orc_build_batch_size(uint32_t batch_size, uint64_t n_points, uint64_t i
     return (uint32_t)std::min<uint64_t>(b, n_points - inserted);
 }
 
+// multi_insert's bootstrap routine (index.rs:589-747, triggered at :917-937): when the batch's back-edges reach few distinct
+// targets (ceil(#targets / 8) <= batch length — always the case while the graph is smaller than eight batches) every
+// pending edge list is re-pruned against its own edges plus ALL other members of the batch, with saturation
+// (multi_insert_bootstrap_leaf: robust_prune_list with force_saturate), and the back-edges are aggregated again.
+// Off by default: the device build grows its batches and does not run it; the reference's batch-insert
+// baselines need it (tests/test_oracle_golden.py).  0: never, 1: under the reference's condition.
+static int g_bootstrap = 0;
+void orc_set_multi_insert_bootstrap(int mode) { g_bootstrap = mode; }
+static uint64_t g_bootstrap_batches = 0, g_bootstrap_would = 0;
+void orc_last_bootstrap_counts(uint64_t* ran, uint64_t* condition_held) {
+    *ran = g_bootstrap_batches;
+    *condition_held = g_bootstrap_would;
+}
+
 void orc_build_batched(int dtype, int metric, uint32_t dim, uint64_t n_points, uint32_t n_start,
                        const void* vectors, uint64_t row_stride, uint32_t pruned_degree,
                        uint32_t max_degree, uint32_t l_build, float alpha, uint32_t batch_size,
@@ -712,8 +726,13 @@ void orc_build_batched(int dtype, int metric, uint32_t dim, uint64_t n_points, u
     std::vector<std::vector<uint32_t>> edges;
     std::vector<std::pair<uint32_t, uint32_t>> back;  // (target, source)
     uint64_t inserted = 0;
+    g_bootstrap_batches = g_bootstrap_would = 0;
+    g_build_sets = g_build_appends = 0;  // provider writes: one set per inserted point (set_neighbors_bulk), then one
+                                         // append or set per back-edge target (add_edge_and_prune)
     while (inserted < n_points) {
-        const uint32_t b = orc_build_batch_size(batch_size, n_points, inserted);
+        // (with the bootstrap on, the reference's own drivers feed fixed chunks: no growth rule)
+        const uint32_t b = g_bootstrap ? (uint32_t)std::min<uint64_t>(batch_size ? batch_size : 1, n_points - inserted)
+                                       : orc_build_batch_size(batch_size, n_points, inserted);
         edges.assign(b, {});
         for (uint32_t i = 0; i < b; ++i) {
             const uint32_t id = (uint32_t)(inserted + i);
@@ -726,14 +745,51 @@ void orc_build_batched(int dtype, int metric, uint32_t dim, uint64_t n_points, u
             sort_pool(record, MAX_OCCLUSION);
             occlude_list(&idx, record, id, pruned_degree, alpha, flavour, edges[i]);
         }
-        back.clear();
-        for (uint32_t i = 0; i < b; ++i)
-            for (uint32_t t : edges[i]) back.emplace_back(t, (uint32_t)(inserted + i));
-        std::sort(back.begin(), back.end());
+        auto aggregate = [&]() {
+            back.clear();
+            for (uint32_t i = 0; i < b; ++i)
+                for (uint32_t t : edges[i]) back.emplace_back(t, (uint32_t)(inserted + i));
+            std::sort(back.begin(), back.end());
+        };
+        aggregate();
+        {
+            // aggregate_backedges(...).len() = distinct targets; intra_batch_candidates = None resolves to max(0, 1) = 1
+            size_t targets = 0;
+            for (size_t e = 0; e < back.size(); ++e)
+                if (e == 0 || back[e].first != back[e - 1].first) ++targets;
+            const bool cond = 1 < b && (targets + 7) / 8 <= b;
+            if (cond) ++g_bootstrap_would;
+            if (cond && g_bootstrap) {
+                ++g_bootstrap_batches;
+                std::vector<std::vector<uint32_t>> next(b);
+                for (uint32_t i = 0; i < b; ++i) {
+                    const uint32_t id = (uint32_t)(inserted + i);
+                    // AdjacencyList::from_iter_untrusted(current.edges ++ other batch sources): duplicates dropped
+                    list.assign(edges[i].begin(), edges[i].end());
+                    for (uint32_t o = 0; o < b; ++o) {
+                        const uint32_t other = (uint32_t)(inserted + o);
+                        if (other != id && std::find(list.begin(), list.end(), other) == list.end()) list.push_back(other);
+                    }
+                    // robust_prune_list (index.rs:2397-2454): distances from the source, sorted pool, occlude, saturate
+                    pool.clear();
+                    for (uint32_t other : list)
+                        if (other != id) pool.push_back(Visit{other, pair_distance(&idx, flavour, id, other)});
+                    sort_pool(pool, MAX_OCCLUSION);
+                    occlude_list(&idx, pool, id, pruned_degree, alpha, flavour, next[i]);
+                    for (const Visit& v : pool) {  // force_saturate (index.rs:2637-2650)
+                        if (next[i].size() >= pruned_degree) break;
+                        if (v.id != id && std::find(next[i].begin(), next[i].end(), v.id) == next[i].end()) next[i].push_back(v.id);
+                    }
+                }
+                edges.swap(next);
+                aggregate();
+            }
+        }
         for (uint32_t i = 0; i < b; ++i) {
             uint32_t* r = row((uint32_t)(inserted + i));
             r[0] = (uint32_t)edges[i].size();
             for (size_t j = 0; j < edges[i].size(); ++j) r[1 + j] = edges[i][j];
+            ++g_build_sets;
         }
         for (size_t e = 0; e < back.size();) {
             const uint32_t target = back[e].first;
@@ -751,6 +807,7 @@ void orc_build_batched(int dtype, int metric, uint32_t dim, uint64_t n_points, u
             if (list.size() <= max_degree) {
                 r[0] = (uint32_t)list.size();
                 for (size_t j = 0; j < list.size(); ++j) r[1 + j] = list[j];
+                ++g_build_appends;
                 continue;
             }
             pool.clear();
@@ -758,6 +815,7 @@ void orc_build_batched(int dtype, int metric, uint32_t dim, uint64_t n_points, u
                 if (other != target) pool.push_back(Visit{other, pair_distance(&idx, flavour, target, other)});
             sort_pool(pool, MAX_OCCLUSION);
             occlude_list(&idx, pool, target, pruned_degree, alpha, flavour, pruned);
+            ++g_build_sets;
             r[0] = (uint32_t)pruned.size();
             for (size_t j = 0; j < pruned.size(); ++j) r[1 + j] = pruned[j];
         }

@@ -224,6 +224,12 @@ double orc_recall(const uint32_t* gt, uint32_t gt_stride, const uint32_t* res,
 
 int orc_hardware_threads(void);
 
+/* multi_insert's bootstrap routine (index.rs:589-747, 917-937) inside orc_build_batched: 0 (default) never — batches then
+ * follow the device build's growth rule; 1: under the reference's condition, with fixed chunks of `batch_size` like the
+ * reference's drivers.  orc_last_bootstrap_counts: batches that ran it / batches for which the condition held. */
+void orc_set_multi_insert_bootstrap(int mode);
+void orc_last_bootstrap_counts(uint64_t* ran, uint64_t* condition_held);
+
 /* ---------------------------------------------------------------- MinMax quantizer (oracle/minmax.cpp)
  * diskann-quantization/src/minmax/{quantizer.rs, vectors.rs}, Transform::Null.  Rows use the canonical-front layout of
  * Data<NBITS>: MinMaxCompensation {dim u32, b, n, a, norm_squared} (20 bytes), then dense N-bit codes.

@@ -12,6 +12,8 @@ Sources (paths relative to the reference checkout):
   * diskann-wide/test_data/float16_conversion.txt — f16 <-> f32 conversion table (a sample).
   * diskann/test/generated/graph/test/cases/grid_insert/insert_{1_100,3_5,4_4}_single/ibc_none.json —
     searches after inserting the lattice points one by one (driver grid_insert.rs:46-250).
+  * diskann/test/generated/graph/test/cases/grid_insert/insert_*_batch_*/ibc_none.json — the same after
+    DiskANNIndex::multi_insert over fixed chunks of the lattice points (intra_batch_candidates = None).
   * diskann/test/generated/flat/test/cases/flat_knn_search/search_{1_100,2_5,3_4}.json — exhaustive-scan
     baselines (brute-force ground truth ordered by (distance, id), k in the reference's sweep).
 Only data (numeric literals / JSON payloads) is extracted; no reference source is copied.
@@ -116,11 +118,32 @@ def f16_table():
     print("float16_sample.json", len(sample))
 
 
+def grid_insert_batch():
+    out = []
+    for name, batch in (("insert_1_100_batch_100", 100), ("insert_3_5_batch_125", 125), ("insert_3_5_batch_25", 25),
+                        ("insert_4_4_batch_25", 25), ("insert_4_4_batch_256", 256)):
+        path = f"{REF}/diskann/test/generated/graph/test/cases/grid_insert/{name}/ibc_none.json"
+        p = json.load(open(path))["payload"]
+        out.append({
+            "case": name, "batch": batch, "grid_dims": p["grid_dims"], "grid_size": p["grid_size"], "num_inserted": p["num_inserted"],
+            "set_neighbors": p["insert_metrics"]["set_neighbors"], "append_neighbors": p["insert_metrics"]["append_neighbors"],
+            "searches": [{"beam_width": q["beam_width"], "query": q["query"], "num_results": q["num_results"],
+                          "results": q["results"], "comparisons": q["comparisons"], "hops": q["hops"]} for q in p["searches"]],
+        })
+    json.dump({"source": "diskann/test/generated/graph/test/cases/grid_insert/insert_*_batch_*/ibc_none.json (driver "
+                         "diskann/src/graph/test/cases/grid_insert.rs:46-250, run_build with batchsize = Some(batch): "
+                         "DiskANNIndex::multi_insert over consecutive chunks of the lattice points, intra_batch_candidates = None; "
+                         "same provider / degrees / L_build as the single-insert cases; then k = 10, L = 10 searches)",
+               "cases": out}, open(f"{OUT}/grid_insert_batch.json", "w"), indent=0)
+    print("grid_insert_batch.json", len(out))
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("reference checkout not present; fixtures are already committed")
     kat_l2()
     grid_search()
     grid_insert()
+    grid_insert_batch()
     flat_knn()
     f16_table()

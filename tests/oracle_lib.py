@@ -271,14 +271,26 @@ def build_graph(vectors, n_points, n_start, metric, pruned_degree, max_degree, l
     return adj
 
 
-def build_graph_batched(vectors, n_points, n_start, metric, pruned_degree, max_degree, l_build, alpha=1.2, batch_size=0):
-    """DiskANNIndex::multi_insert over the device build's batch schedule (batch_size 1 == build_graph)."""
+def build_graph_batched(vectors, n_points, n_start, metric, pruned_degree, max_degree, l_build, alpha=1.2, batch_size=0,
+                        bootstrap=False):
+    """DiskANNIndex::multi_insert over the device build's batch schedule (batch_size 1 == build_graph).
+    bootstrap=True: fixed chunks of `batch_size` points and the reference's bootstrap routine under its own condition
+    (what the reference's drivers run; the device build does not)."""
     vectors = np.ascontiguousarray(vectors)
     stride = max_degree + 1
     adj = np.zeros((n_points + n_start, stride), np.uint32)
+    lib().orc_set_multi_insert_bootstrap(1 if bootstrap else 0)
     lib().orc_build_batched(dtype_code(vectors), metric, vectors.shape[1], n_points, n_start, ptr(vectors),
                             vectors.strides[0], pruned_degree, max_degree, l_build, alpha, batch_size, ptr(adj), stride)
+    lib().orc_set_multi_insert_bootstrap(0)
     return adj
+
+
+def last_bootstrap_counts():
+    """(batches of the last build_graph_batched that ran the bootstrap routine, batches for which the reference's condition held)."""
+    a, b = C.c_uint64(), C.c_uint64()
+    lib().orc_last_bootstrap_counts(C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 def last_build_counts():

@@ -525,6 +525,81 @@ def test_grid_insert_baselines():
                 assert [int(i) for i in ids[0]] == [r[0] for r in s["results"]]
 
 
+def test_grid_batch_insert_baselines():
+    """The reference's batch-insert baselines (grid_insert.rs run_build with a batch size: DiskANNIndex::multi_insert over
+    consecutive chunks, intra_batch_candidates = None).  On these tiny graphs every batch meets the bootstrap condition
+    (index.rs:917-937), so the oracle's multi_insert runs with its restatement of the bootstrap routine switched on:
+      * 1-D, one batch of 100: everything is reproduced — result ids, distances, hops (101: the bootstrap leaves a chain),
+        comparisons and the provider's set_neighbors / append_neighbors write counts;
+      * 4-D, one batch of 256: hops, comparisons, distances and both write counts; 3-D, one batch of 125 and batches of 25:
+        hops, comparisons, distances and the set_neighbors count (appends within 10 %: tied prune pools);
+      * 4-D in batches of 25: the distance profile, hops within one, comparisons and write counts within 5 %.
+    This pins search_and_prune_batch + aggregate_backedges + the bootstrap + add_edge_and_prune of the restatement the device
+    build is compared with (the device build itself never runs the bootstrap: test_bootstrap_condition_of_the_device_schedule)."""
+    g = json.load(open(os.path.join(GOLDEN, "grid_insert_batch.json")))
+    assert len(g["cases"]) == 5
+    for case in g["cases"]:
+        dims, size, name = case["grid_dims"], case["grid_size"], case["case"]
+        data, _, n = grid(dims, size)
+        max_degree = 2 * dims
+        pruned = min(max(max_degree - 2, 2), max_degree)
+        adj = O.build_graph_batched(data, n, 1, O.L2, pruned, max_degree, 100, 1.2, batch_size=case["batch"], bootstrap=True)
+        ran, held = O.last_bootstrap_counts()
+        assert ran == held == -(-n // case["batch"])          # every batch of these graphs bootstraps
+        assert adj[:, 0].max() <= max_degree
+        sets, appends = O.last_build_counts()
+        exact = name in ("insert_1_100_batch_100", "insert_4_4_batch_256")
+        loose = name == "insert_4_4_batch_25"
+        if exact:
+            assert (sets, appends) == (case["set_neighbors"], case["append_neighbors"])
+        elif loose:
+            assert abs(sets - case["set_neighbors"]) <= 0.05 * case["set_neighbors"]
+            assert abs(appends - case["append_neighbors"]) <= 0.05 * case["append_neighbors"]
+        else:
+            assert sets == case["set_neighbors"] and abs(appends - case["append_neighbors"]) <= 0.1 * case["append_neighbors"]
+        idx = O.Index(data, adj, n, 1, O.L2)
+        for s in case["searches"]:
+            q = np.array([s["query"]], np.float32)
+            ids, dists, counts, cmps, hops = idx.search_batch(q, 10, 10, beam=s["beam_width"], flavour=O.SIMD)
+            assert int(counts[0]) == s["num_results"]
+            assert [float(x) for x in dists[0]] == [r[1] for r in s["results"]], name
+            if loose:
+                assert abs(int(hops[0]) - s["hops"]) <= 1 and abs(int(cmps[0]) - s["comparisons"]) <= 0.05 * s["comparisons"]
+            else:
+                assert (int(hops[0]), int(cmps[0])) == (s["hops"], s["comparisons"]), name
+            if dims == 1:
+                assert [int(i) for i in ids[0]] == [r[0] for r in s["results"]]
+
+
+def test_bootstrap_condition_of_the_device_schedule():
+    """The device build (and the restatement it is compared with, bootstrap off) grows its batches as inserted / 8 up to a
+    cap.  The reference's condition — ceil(#distinct back-edge targets / 8) <= batch length — holds for every batch of that
+    growth phase and stops holding once the batch size is capped and the graph has grown past eight batches: this test
+    states that fact for a 6000-point build, so DESIGN.md can say exactly where the device build and the reference's
+    multi_insert differ (the bootstrap's extra saturating prune of the growth-phase batches)."""
+    rng = np.random.default_rng(3)
+    n, d = 6000, 16
+    centers = rng.normal(size=(16, d)).astype(np.float32)
+    base = (centers[rng.integers(0, 16, n)] + 0.3 * rng.normal(size=(n, d))).astype(np.float32)
+    medoid = base[np.argmin(((base - base.mean(0)) ** 2).sum(1))]
+    vecs = np.concatenate([base, medoid[None]])
+    O.build_graph_batched(vecs, n, 1, O.L2, 16, 20, 32, 1.2, batch_size=64)
+    ran, held = O.last_bootstrap_counts()
+    assert ran == 0
+    # growth phase: batches of 1, 1, ..., then inserted / 8 until the cap of 64 is reached at 512 points; single-point batches
+    # never bootstrap (index.rs:925-926), so the condition holds for the batches of 2..63 points and not in the capped phase
+    growth_batches = 0
+    inserted = 0
+    while inserted < n:
+        b = min(64, max(1, inserted // 8), n - inserted)
+        if 1 < b < 64:
+            growth_batches += 1
+        inserted += b
+    assert held >= growth_batches
+    capped_batches = (n - 512) // 64
+    assert held <= growth_batches + capped_batches // 4, (held, growth_batches, capped_batches)
+
+
 def test_flat_knn_baselines():
     """The reference's exhaustive-scan baselines (flat_knn_search.rs:95-196): brute-force top-k
     ordered by (distance asc, id asc) over the size^dims lattice, result_count = min(k, len)."""
