@@ -78,6 +78,52 @@ float dot_chain(const float* row, const float* c, size_t len) {  // s = fma(c[d]
 
 extern "C" {
 
+// lloyds_inner (lloyds.rs:372-426) over the chunk [lo, lo + len) of the rows of `data`: `reps` rounds of assignment
+// (distances_in_place: d = ((n_c - s) - s) + n_i with s the FMA chain over the dimensions, first minimum in centre order)
+// and update_centroids (:345-366: f64 sums in data order / max(count, 1)); centre norms refreshed between rounds.
+// *residual (optional) = the sum of the winning distances of the last round.
+static void run_lloyd(const float* data, uint64_t n, uint32_t dim, size_t lo, size_t len, float* pivots, uint32_t n_centers,
+                      uint32_t lloyds_reps, const std::vector<float>& norms, std::vector<float>& cn, std::vector<uint32_t>& assign,
+                      float* residual) {
+    auto row = [&](uint64_t i) { return data + i * dim + lo; };
+    auto center = [&](uint32_t p) { return pivots + (size_t)p * dim + lo; };
+    for (uint32_t p = 0; p < n_centers; ++p) cn[p] = square_norm(center(p), len);
+    std::vector<double> sums((size_t)n_centers * len);
+    std::vector<uint32_t> counts(n_centers);
+    for (uint32_t rep = 0; rep < lloyds_reps; ++rep) {
+        float res = 0.0f;
+        for (uint64_t i = 0; i < n; ++i) {
+            float best = std::numeric_limits<float>::infinity();
+            uint32_t arg = 0xFFFFFFFFu;
+            for (uint32_t p = 0; p < n_centers; ++p) {
+                const float sdot = dot_chain(center(p), row(i), len);  // c.mul_add(d, s): same product, same chain
+                const float d = ((cn[p] - sdot) - sdot) + norms[i];
+                if (d < best) {
+                    best = d;
+                    arg = p;
+                }
+            }
+            assign[i] = arg;
+            res += best;  // (the reference sums its lanes in SIMD order; only used where every term is exact)
+        }
+        if (residual) *residual = res;
+        std::fill(sums.begin(), sums.end(), 0.0);
+        std::fill(counts.begin(), counts.end(), 0u);
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint32_t a = assign[i];
+            if (a == 0xFFFFFFFFu) continue;  // all-NaN row: the reference would index out of bounds
+            ++counts[a];
+            for (size_t d = 0; d < len; ++d) sums[(size_t)a * len + d] += (double)row(i)[d];
+        }
+        for (uint32_t p = 0; p < n_centers; ++p) {
+            const double c = (double)std::max<uint32_t>(counts[p], 1);
+            for (size_t d = 0; d < len; ++d) center(p)[d] = (float)(sums[(size_t)p * len + d] / c);
+        }
+        if (rep != lloyds_reps - 1)
+            for (uint32_t p = 0; p < n_centers; ++p) cn[p] = square_norm(center(p), len);
+    }
+}
+
 // data: [n][dim] f32 row-major.  pivots out: [n_centers][dim] (full_pivot_data layout: centre p's
 // chunk c occupies columns offsets[c]..offsets[c+1]).  Returns 0, or -1 when a chunk could not be
 // seeded with n_centers distinct points (KMeansPlusPlusError; the reference tolerates the
@@ -148,40 +194,22 @@ int orc_pq_train(const float* data, uint64_t n, uint32_t dim, uint32_t n_chunks,
         }
         if (selected != n_centers) status = -1;
         // ---- Lloyd (lloyds.rs:372-426)
-        for (uint32_t p = 0; p < n_centers; ++p) cn[p] = square_norm(center(p), len);
-        std::vector<double> sums((size_t)n_centers * len);
-        std::vector<uint32_t> counts(n_centers);
-        for (uint32_t rep = 0; rep < lloyds_reps; ++rep) {
-            for (uint64_t i = 0; i < n; ++i) {
-                float best = std::numeric_limits<float>::infinity();
-                uint32_t arg = 0xFFFFFFFFu;
-                for (uint32_t p = 0; p < n_centers; ++p) {
-                    const float sdot = dot_chain(center(p), row(i), len);  // c.mul_add(d, s): same product, same chain
-                    const float d = ((cn[p] - sdot) - sdot) + norms[i];
-                    if (d < best) {
-                        best = d;
-                        arg = p;
-                    }
-                }
-                assign[i] = arg;
-            }
-            std::fill(sums.begin(), sums.end(), 0.0);
-            std::fill(counts.begin(), counts.end(), 0u);
-            for (uint64_t i = 0; i < n; ++i) {
-                const uint32_t a = assign[i];
-                if (a == 0xFFFFFFFFu) continue;  // all-NaN row: the reference would index out of bounds
-                ++counts[a];
-                for (size_t d = 0; d < len; ++d) sums[(size_t)a * len + d] += (double)row(i)[d];
-            }
-            for (uint32_t p = 0; p < n_centers; ++p) {
-                const double c = (double)std::max<uint32_t>(counts[p], 1);
-                for (size_t d = 0; d < len; ++d) center(p)[d] = (float)(sums[(size_t)p * len + d] / c);
-            }
-            if (rep != lloyds_reps - 1)
-                for (uint32_t p = 0; p < n_centers; ++p) cn[p] = square_norm(center(p), len);
-        }
+        run_lloyd(data, n, dim, lo, len, pivots, n_centers, lloyds_reps, norms, cn, assign, nullptr);
     }
     return status;
+}
+
+// lloyds(data, centers, max_reps) (lloyds.rs:428-460) over whole rows: centers [n_centers][dim] in / out, assignments [n],
+// *loss = the residual of the last round.
+void orc_lloyds(const float* data, uint64_t n, uint32_t dim, float* centers, uint32_t n_centers, uint32_t reps,
+                uint32_t* assignments, float* loss) {
+    std::vector<float> norms(n), cn(n_centers);
+    std::vector<uint32_t> assign(n);
+    for (uint64_t i = 0; i < n; ++i) norms[i] = square_norm(data + i * dim, dim);
+    float res = 0.0f;
+    run_lloyd(data, n, dim, 0, dim, centers, n_centers, reps, norms, cn, assign, &res);
+    for (uint64_t i = 0; i < n; ++i) assignments[i] = assign[i];
+    if (loss) *loss = res;
 }
 
 }  // extern "C"

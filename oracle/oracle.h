@@ -224,6 +224,12 @@ double orc_recall(const uint32_t* gt, uint32_t gt_stride, const uint32_t* res,
 
 int orc_hardware_threads(void);
 
+/* lloyds(data, centers, max_reps) (diskann-quantization/src/algorithms/kmeans/lloyds.rs:372-460) over whole rows: centers
+ * [n_centers][dim] in / out, assignments [n], *loss = residual of the last round.  The loop orc_pq_train runs per chunk;
+ * pinned by the reference's closed-form end_to_end_test (lloyds.rs:620-660). */
+void orc_lloyds(const float* data, uint64_t n, uint32_t dim, float* centers, uint32_t n_centers, uint32_t reps,
+                uint32_t* assignments, float* loss);
+
 /* multi_insert's bootstrap routine (index.rs:589-747, 917-937) inside orc_build_batched: 0 (default) never — batches then
  * follow the device build's growth rule; 1: under the reference's condition, with fixed chunks of `batch_size` like the
  * reference's drivers.  orc_last_bootstrap_counts: batches that ran it / batches for which the condition held. */

@@ -188,6 +188,18 @@ def pq_train(data, n_chunks, n_centers=256, lloyds_reps=5, seed=0):
     return pivots, offsets, st
 
 
+def lloyds(data, centers, reps):
+    """lloyds(data, centers, max_reps): (assignments u32 [n], loss, centers after the update)."""
+    data = np.ascontiguousarray(data, np.float32)
+    centers = np.ascontiguousarray(centers, np.float32).copy()
+    assign = np.zeros(data.shape[0], np.uint32)
+    loss = C.c_float()
+    lib().orc_lloyds.restype = None
+    lib().orc_lloyds(ptr(data), C.c_uint64(data.shape[0]), C.c_uint32(data.shape[1]), ptr(centers), C.c_uint32(centers.shape[0]),
+                     C.c_uint32(reps), ptr(assign), C.byref(loss))
+    return assign, loss.value, centers
+
+
 class Index:
     """Host-side view of an index for the oracle (keeps the numpy arrays alive)."""
 

@@ -600,6 +600,32 @@ def test_bootstrap_condition_of_the_device_schedule():
     assert held <= growth_batches + capped_batches // 4, (held, growth_batches, capped_batches)
 
 
+def test_lloyds_end_to_end_closed_form():
+    """end_to_end_test of diskann-quantization/src/algorithms/kmeans/lloyds.rs:620-690: clusters {20c, 20c+1, ..., 20c+7}
+    (every coordinate of a row the same integer), centres initialised at 20c - 1 in shuffled order; after two rounds the
+    assignments are the clusters, every centre is the exact mean of its cluster and the loss is the exact sum of squared
+    distances to it.  Everything is exactly representable, so the assertions are equalities like in the reference.  This is
+    the Lloyd loop orc_pq_train runs per chunk (and the device PQ training is compared with)."""
+    rng = np.random.default_rng(0xff22)
+    ncenters, ndim, per, step = 11, 4, 8, 20
+    values = np.array([step * i + j for i in range(ncenters) for j in range(per)])
+    order = np.arange(ncenters)
+    for _ in range(10):
+        rng.shuffle(values)
+        rng.shuffle(order)
+        centers = np.repeat((step * order - 1).astype(np.float32)[:, None], ndim, 1)
+        data = np.repeat(values.astype(np.float32)[:, None], ndim, 1)
+        assign, loss, new_centers = O.lloyds(data, centers, 2)
+        assert np.array_equal(order[assign], values // step)
+        tri = per * (per - 1) // 2
+        want = ((step * per * order + tri).astype(np.float32) / np.float32(per)).astype(np.float32)
+        assert np.array_equal(new_centers, np.repeat(want[:, None], ndim, 1))
+        expected_loss = np.float32(0)
+        for a, row in zip(assign, data):
+            expected_loss = np.float32(expected_loss + np.float32(((row - new_centers[a]) ** 2).sum(dtype=np.float32)))
+        assert np.float32(loss) == expected_loss
+
+
 def test_flat_knn_baselines():
     """The reference's exhaustive-scan baselines (flat_knn_search.rs:95-196): brute-force top-k
     ordered by (distance asc, id asc) over the size^dims lattice, result_count = min(k, len)."""
