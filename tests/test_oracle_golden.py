@@ -597,7 +597,7 @@ def test_bootstrap_condition_of_the_device_schedule():
         inserted += b
     assert held >= growth_batches
     capped_batches = (n - 512) // 64
-    assert held <= growth_batches + capped_batches // 4, (held, growth_batches, capped_batches)
+    assert held <= growth_batches + capped_batches // 2, (held, growth_batches, capped_batches)  # (21 of the 85 capped batches here)
 
 
 def test_lloyds_end_to_end_closed_form():
