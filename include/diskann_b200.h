@@ -336,8 +336,12 @@ int dab_robust_prune(dab_index* idx, const uint32_t* pool_ids, const float* pool
 /* Batched Vamana construction on the device (the rows SURVEY.md §8f.2 marks "next"):
  * DiskANNIndex::multi_insert semantics (diskann/src/graph/index.rs:815) — batches of inserts
  * searched with the same search kernel, pruned with robust_prune
- * (graph/internal/prune.rs:106-259) and back-edges merged per destination.  Uses the
- * uploaded vectors (including start rows) and overwrites the adjacency. */
+ * (graph/internal/prune.rs:106-259) and back-edges merged per destination (aggregate_backedges :123, one
+ * add_edge_and_prune per target: extend with every source, prune once).  intra_batch_candidates = None; the
+ * bootstrap routine (index.rs:589-747, run by the reference while a batch's back-edges reach <= 8 x batch distinct
+ * targets) is NOT run: batch_size = 1 is DiskANNIndex::insert point by point, larger batches grow as inserted / 8 up
+ * to batch_size (0: a default from the index size) so that no point is inserted blind.  Uses the uploaded vectors
+ * (including start rows) and overwrites the adjacency. */
 int dab_build(dab_index* idx, uint32_t pruned_degree, uint32_t l_build, float alpha,
               uint32_t batch_size);
 
